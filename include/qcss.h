@@ -1,0 +1,149 @@
+/*
+ * qcss.h -- C ABI of libqcss.so, the B200 (sm_100a) implementation of the quantum-css-codes hot
+ * path: Pauli-error sampling -> syndrome H.e mod 2 -> lookup decode -> logical-failure tally,
+ * plus the batched GF(2) row-reduction toolkit.
+ *
+ * The reference (jimpo/quantum-css-codes) is pure Python and has no FFI; its boundary for this
+ * path is the module surface of bin_matrix.py / css_code.py.  Every entry point below names the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - Every function returns 0 (QCSS_OK) or a negative QCSS_ERR_* code; qcss_last_error() gives
+ *     a thread-local message for the last failure.
+ *   - The caller owns every host buffer; the library never keeps a caller pointer after return.
+ *     Device memory lives behind opaque handles.  No callbacks.  A handle is not thread-safe.
+ *   - One process drives one GPU (qcss_set_device); multi-GPU runs are one process per GPU.
+ *   - Batches are BIT PLANES: a batch of `shots` binary vectors of length n is n planes of
+ *     uint64 words; shot s of plane j is bit (s % 64) of word planes[j * stride + s / 64].
+ *     `stride` (in uint64 words) must be a multiple of 2 and >= ceil(shots / 128) * 2; padding
+ *     bits are ignored on input and written as zero on output.
+ *   - `which` follows the reference's naming (css_code.py:28-30, 461-470):
+ *         which = 2 : X errors  -> parity_check_c2, _c2_syndromes, logical Z row (Lz)
+ *         which = 1 : Z errors  -> parity_check_c1, _c1_syndromes, logical X row (Lx)
+ *   - Table keys are big-endian: key = sum_i s[i] << (m-1-i)   (bin_matrix.py:36-43).
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef QCSS_H
+#define QCSS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QCSS_API __attribute__((visibility("default")))
+#else
+#define QCSS_API
+#endif
+
+#define QCSS_OK               0
+#define QCSS_ERR_INVALID     -1   /* bad argument (Python side raises ValueError)            */
+#define QCSS_ERR_CUDA        -2   /* CUDA runtime / driver failure                            */
+#define QCSS_ERR_UNSUPPORTED -3   /* shape outside what the kernels cover (no fallback)       */
+#define QCSS_ERR_NOMEM       -4
+
+typedef struct qcss_code qcss_code;
+
+/* Tallies of one run: fail_x counts Lz.(e_x ^ c_x) = 1, fail_z counts
+ * Lx.(e_z ^ c_z) = 1, fail_any their union, miss_* syndromes absent from the table. */
+typedef struct qcss_tally {
+    uint64_t shots, fail_x, fail_z, fail_any, miss_x, miss_z;
+} qcss_tally;
+
+/* Optional inputs/outputs of one decode pass, all DEVICE pointers, NULL = not wanted.
+ * ex/ez: error planes [n][e_stride].  synd_*: syndrome planes [m][s_stride] in reference row
+ * order.  corr_*: correction planes [n][c_stride].  flip_* / miss_*: one plane each
+ * (length e_stride).  tally: uint64[6] in qcss_tally order, ACCUMULATED atomically. */
+typedef struct qcss_decode_io {
+    const uint64_t* ex;
+    const uint64_t* ez;
+    int64_t e_stride;
+    uint64_t* synd_x;
+    uint64_t* synd_z;
+    int64_t s_stride;
+    uint64_t* corr_x;
+    uint64_t* corr_z;
+    int64_t c_stride;
+    uint64_t* flip_x;
+    uint64_t* flip_z;
+    uint64_t* miss_x;
+    uint64_t* miss_z;
+    uint64_t* tally;
+} qcss_decode_io;
+
+/* ---- library / device ------------------------------------------------------------------ */
+QCSS_API int qcss_version(void);
+QCSS_API const char* qcss_last_error(void);
+QCSS_API int qcss_device_count(int* count);
+QCSS_API int qcss_set_device(int device);
+QCSS_API int qcss_host_alloc(void** ptr, size_t bytes);          /* pinned host memory for the e2e path */
+QCSS_API int qcss_host_free(void* ptr);
+
+/* ---- code object ----------------------------------------------------------------------- */
+/* Uploads what CSSCode.__init__ computed (css_code.py:32-75): the NORMALISED parity checks
+ * H1 (m1 x n) and H2 (m2 x n) as row-major 0/1 bytes, the logical rows Lx, Lz (n bytes each,
+ * css_code.py:124-161; NULL for syndrome-only codes), and the flattened syndrome tables
+ * _c1_syndromes / _c2_syndromes (css_code.py:715-735): n_k keys and n_k x n correction bytes
+ * (NULL / 0 when the code has no table).  Decoding needs n <= 32 and m <= 16; syndromes work
+ * for any n, m. */
+QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const uint8_t* H2,
+                     const uint8_t* Lx, const uint8_t* Lz,
+                     int64_t n1, const int64_t* keys1, const uint8_t* corr1,
+                     int64_t n2, const int64_t* keys2, const uint8_t* corr2,
+                     qcss_code** out);
+QCSS_API int qcss_code_destroy(qcss_code* code);
+/* Human-readable name of the kernel family the code dispatches to (tests). */
+QCSS_API int qcss_code_kernel_name(const qcss_code* code, char* buf, int buflen);
+
+/* ---- K1 syndrome: replaces np.mod(np.matmul(parity_check, e), 2), css_code.py:728 ------- */
+QCSS_API int qcss_syndrome(qcss_code* code, int which, const uint64_t* e_planes, int64_t e_stride,
+                  int64_t shots, uint64_t* s_planes, int64_t s_stride);
+QCSS_API int qcss_syndrome_dev(qcss_code* code, int which, const uint64_t* d_e_planes, int64_t e_stride,
+                      int64_t shots, uint64_t* d_s_planes, int64_t s_stride, void* stream);
+
+/* ---- K1+K2 lookup decode + logical check: replaces the table scan of
+ *      quil_classical_correct (css_code.py:649-685) and the Lz/Lx readout (css_code.py:641-646).
+ *      corr/flip/miss planes may be NULL; tally may be NULL. ------------------------------ */
+QCSS_API int qcss_decode(qcss_code* code, int which, const uint64_t* e_planes, int64_t e_stride,
+                int64_t shots, uint64_t* corr_planes, uint64_t* flip_plane, uint64_t* miss_plane,
+                qcss_tally* tally);
+/* Both Pauli types of the same shots, tallies only; streams the host buffers through the GPU
+ * in chunks (copies overlap the kernels). */
+QCSS_API int qcss_decode_xz(qcss_code* code, const uint64_t* ex_planes, const uint64_t* ez_planes,
+                   int64_t e_stride, int64_t shots, qcss_tally* tally);
+/* General device-pointer form, asynchronous on `stream` (a cudaStream_t, NULL = default). */
+QCSS_API int qcss_decode_dev(qcss_code* code, const qcss_decode_io* io, int64_t shots, void* stream);
+
+/* ---- K3 fused Philox sampler + K1 + K2 (no reference counterpart).
+ *      Depolarising noise: each qubit of each shot gets X, Y or Z with probability p/3 each,
+ *      p quantised to floor(p * 2^32) / 2^32.  Streams are keyed by (seed, global shot word,
+ *      qubit) so results do not depend on how shots are split over calls or GPUs;
+ *      first_shot must be a multiple of 128. ------------------------------------------------ */
+QCSS_API int qcss_mc_run(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                qcss_tally* tally);
+QCSS_API int qcss_mc_run_dev(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                    uint64_t* d_tally, void* stream);
+/* The same sampler writing its error planes out (parity tests against the oracle sampler). */
+QCSS_API int qcss_mc_sample(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                   uint64_t* ex_planes, uint64_t* ez_planes, int64_t e_stride);
+QCSS_API int qcss_mc_sample_dev(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                       uint64_t* d_ex_planes, uint64_t* d_ez_planes, int64_t e_stride, void* stream);
+
+/* ---- K4 batched GF(2) Gauss-Jordan: replaces bin_matrix.reduced_row_echelon_form
+ *      (bin_matrix.py:8-34; the reference has no batch API and no rank/pivot outputs).
+ *      mats: batch matrices of m rows, each row ceil(n/64) uint64 words, column 64w+j is bit j
+ *      of word w.  out: same layout, the canonical RREF (zero rows last).  rank: [batch].
+ *      pivots: [batch][min(m,n)] pivot column of row i, -1 past the rank; may be NULL.
+ *      in and out must not overlap. ------------------------------------------------------- */
+QCSS_API int qcss_gf2_rref(const uint64_t* mats, int batch, int m, int n, uint64_t* out, int32_t* rank,
+                  int32_t* pivots);
+QCSS_API int qcss_gf2_rref_dev(const uint64_t* d_mats, int batch, int m, int n, uint64_t* d_out,
+                      int32_t* d_rank, int32_t* d_pivots, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCSS_H */

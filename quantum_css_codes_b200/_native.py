@@ -1,0 +1,315 @@
+"""
+ctypes binding of libqcss.so (C ABI in include/qcss.h).
+
+The library is built in-tree (``python -m quantum_css_codes_b200.build`` or
+``__graft_entry__.build()``) as ``quantum_css_codes_b200/libqcss.so``.  There is no CPU
+fallback: if the library is missing or a CUDA call fails, ``NativeLibraryError`` is raised.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import planes as _planes
+from .errors import NativeLibraryError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqcss.so")
+
+QCSS_ERR_INVALID = -1
+QCSS_ERR_CUDA = -2
+QCSS_ERR_UNSUPPORTED = -3
+QCSS_ERR_NOMEM = -4
+
+_c_u64p = ctypes.POINTER(ctypes.c_uint64)
+_c_u8p = ctypes.POINTER(ctypes.c_uint8)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+class Tally(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_uint64)
+                for name in ("shots", "fail_x", "fail_z", "fail_any", "miss_x", "miss_z")]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+TALLY_FIELDS = tuple(name for name, _ in Tally._fields_)
+
+
+class DecodeIO(ctypes.Structure):
+    _fields_ = [("ex", ctypes.c_void_p), ("ez", ctypes.c_void_p), ("e_stride", ctypes.c_int64),
+                ("synd_x", ctypes.c_void_p), ("synd_z", ctypes.c_void_p), ("s_stride", ctypes.c_int64),
+                ("corr_x", ctypes.c_void_p), ("corr_z", ctypes.c_void_p), ("c_stride", ctypes.c_int64),
+                ("flip_x", ctypes.c_void_p), ("flip_z", ctypes.c_void_p),
+                ("miss_x", ctypes.c_void_p), ("miss_z", ctypes.c_void_p),
+                ("tally", ctypes.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/qcss.h declares
+PROTOTYPES = {
+    "qcss_version": (ctypes.c_int, []),
+    "qcss_last_error": (ctypes.c_char_p, []),
+    "qcss_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "qcss_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "qcss_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
+    "qcss_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcss_code_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_u8p, ctypes.c_int, _c_u8p,
+                                        _c_u8p, _c_u8p,
+                                        ctypes.c_int64, _c_i64p, _c_u8p,
+                                        ctypes.c_int64, _c_i64p, _c_u8p,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "qcss_code_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcss_code_kernel_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    "qcss_syndrome": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
+    "qcss_syndrome_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "qcss_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                   ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.POINTER(Tally)]),
+    "qcss_decode_xz": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.POINTER(Tally)]),
+    "qcss_decode_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(DecodeIO), ctypes.c_int64,
+                                       ctypes.c_void_p]),
+    "qcss_mc_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                   ctypes.c_int64, ctypes.POINTER(Tally)]),
+    "qcss_mc_run_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_mc_sample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "qcss_mc_sample_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_void_p]),
+    "qcss_gf2_rref": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, _c_i32p, _c_i32p]),
+    "qcss_gf2_rref_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libqcss.so once; raise NativeLibraryError (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: build it with `python -m quantum_css_codes_b200.build` "
+                "(needs nvcc).  There is no CPU fallback.")
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as exc:
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return _lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().qcss_last_error().decode("utf-8", "replace")
+    if rc == QCSS_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == QCSS_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise NativeLibraryError(f"libqcss error {rc}: {msg}")
+
+
+def _ptr(arr):
+    return ctypes.c_void_p(arr.ctypes.data) if arr is not None else ctypes.c_void_p(0)
+
+
+def _table_arrays(table, n):
+    if table is None:
+        return 0, None, None
+    keys = np.array([int(k) for k in table.keys()], dtype=np.int64)
+    corr = np.zeros((len(keys), n), dtype=np.uint8)
+    for row, vec in enumerate(table.values()):
+        corr[row] = np.asarray(vec, dtype=np.int64) & 1
+    return len(keys), keys, corr
+
+
+def _u8(mat):
+    return None if mat is None else np.ascontiguousarray(np.asarray(mat) & 1, dtype=np.uint8)
+
+
+class DeviceCode:
+    """Owns a qcss_code handle; numpy-in / numpy-out wrappers over the host-buffer entry points
+    and thin pass-throughs for the device-pointer ones."""
+
+    def __init__(self, n, h1, h2, lx, lz, table1, table2):
+        lib = load()
+        h1, h2 = _u8(h1), _u8(h2)
+        self.n, self.m1, self.m2 = int(n), h1.shape[0], h2.shape[0]
+        lx, lz = _u8(lx), _u8(lz)
+        n1, keys1, corr1 = _table_arrays(table1, n)
+        n2, keys2, corr2 = _table_arrays(table2, n)
+        handle = ctypes.c_void_p()
+        as_u8 = lambda a: a.ctypes.data_as(_c_u8p) if a is not None else None
+        as_i64 = lambda a: a.ctypes.data_as(_c_i64p) if a is not None else None
+        check(lib.qcss_code_create(self.n, self.m1, as_u8(h1), self.m2, as_u8(h2), as_u8(lx), as_u8(lz),
+                                   n1, as_i64(keys1), as_u8(corr1), n2, as_i64(keys2), as_u8(corr2),
+                                   ctypes.byref(handle)))
+        self._lib = lib
+        self.handle = handle
+
+    def __del__(self):
+        handle, self.handle = getattr(self, "handle", None), None
+        if handle:
+            try:
+                self._lib.qcss_code_destroy(handle)
+            except Exception:
+                pass
+
+    def m(self, which):
+        if which not in (1, 2):
+            raise ValueError("which must be 1 (Z errors, C_1) or 2 (X errors, C_2)")
+        return self.m1 if which == 1 else self.m2
+
+    def kernel_name(self):
+        buf = ctypes.create_string_buffer(256)
+        check(self._lib.qcss_code_kernel_name(self.handle, buf, 256))
+        return buf.value.decode()
+
+    # ---- host-buffer entry points ---------------------------------------------------------
+    def _check_planes(self, e_planes, shots):
+        e_planes = np.ascontiguousarray(e_planes, dtype=np.uint64)
+        if e_planes.ndim != 2 or e_planes.shape[0] != self.n:
+            raise ValueError(f"expected ({self.n}, stride) uint64 planes")
+        if e_planes.shape[1] % 2 or e_planes.shape[1] * 64 < shots:
+            raise ValueError("plane stride must be even and cover all shots")
+        return e_planes
+
+    def syndrome_planes(self, e_planes, shots, which):
+        e_planes = self._check_planes(e_planes, shots)
+        stride = e_planes.shape[1]
+        out = np.zeros((self.m(which), stride), dtype=np.uint64)
+        check(self._lib.qcss_syndrome(self.handle, which, _ptr(e_planes), stride, shots, _ptr(out), stride))
+        return out
+
+    def decode_planes(self, e_planes, shots, which):
+        e_planes = self._check_planes(e_planes, shots)
+        self.m(which)
+        stride = e_planes.shape[1]
+        corr = np.zeros((self.n, stride), dtype=np.uint64)
+        flip = np.zeros(stride, dtype=np.uint64)
+        miss = np.zeros(stride, dtype=np.uint64)
+        tally = Tally()
+        check(self._lib.qcss_decode(self.handle, which, _ptr(e_planes), stride, shots,
+                                    _ptr(corr), _ptr(flip), _ptr(miss), ctypes.byref(tally)))
+        return corr, flip, miss, tally.as_dict()
+
+    def decode_xz_planes(self, ex_planes, ez_planes, shots):
+        ex_planes = self._check_planes(ex_planes, shots)
+        ez_planes = self._check_planes(ez_planes, shots)
+        if ex_planes.shape != ez_planes.shape:
+            raise ValueError("x and z planes must have the same stride")
+        tally = Tally()
+        check(self._lib.qcss_decode_xz(self.handle, _ptr(ex_planes), _ptr(ez_planes),
+                                       ex_planes.shape[1], shots, ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def decode_xz_host_ptr(self, ex_ptr, ez_ptr, stride, shots):
+        """Same call with raw (e.g. pinned) host pointers -- the e2e benchmark path."""
+        tally = Tally()
+        check(self._lib.qcss_decode_xz(self.handle, ctypes.c_void_p(ex_ptr), ctypes.c_void_p(ez_ptr),
+                                       stride, shots, ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def mc_run(self, p, shots, seed=0, first_shot=0):
+        tally = Tally()
+        check(self._lib.qcss_mc_run(self.handle, float(p), int(shots), int(seed), int(first_shot),
+                                    ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def mc_sample(self, p, shots, seed=0, first_shot=0):
+        stride = _planes.stride_words(shots)
+        ex = np.zeros((self.n, stride), dtype=np.uint64)
+        ez = np.zeros((self.n, stride), dtype=np.uint64)
+        check(self._lib.qcss_mc_sample(self.handle, float(p), int(shots), int(seed), int(first_shot),
+                                       _ptr(ex), _ptr(ez), stride))
+        return ex, ez
+
+    # ---- device-pointer entry points (pointers are ints, e.g. torch.Tensor.data_ptr()) -----
+    def decode_dev(self, shots, stream=0, **ptrs):
+        io = DecodeIO()
+        for name, value in ptrs.items():
+            setattr(io, name, value)
+        check(self._lib.qcss_decode_dev(self.handle, ctypes.byref(io), int(shots), ctypes.c_void_p(stream)))
+
+    def syndrome_dev(self, which, e_ptr, e_stride, shots, s_ptr, s_stride, stream=0):
+        check(self._lib.qcss_syndrome_dev(self.handle, which, ctypes.c_void_p(e_ptr), e_stride, int(shots),
+                                          ctypes.c_void_p(s_ptr), s_stride, ctypes.c_void_p(stream)))
+
+    def mc_run_dev(self, p, shots, seed, first_shot, tally_ptr, stream=0):
+        check(self._lib.qcss_mc_run_dev(self.handle, float(p), int(shots), int(seed), int(first_shot),
+                                        ctypes.c_void_p(tally_ptr), ctypes.c_void_p(stream)))
+
+    def mc_sample_dev(self, p, shots, seed, first_shot, ex_ptr, ez_ptr, e_stride, stream=0):
+        check(self._lib.qcss_mc_sample_dev(self.handle, float(p), int(shots), int(seed), int(first_shot),
+                                           ctypes.c_void_p(ex_ptr), ctypes.c_void_p(ez_ptr), e_stride,
+                                           ctypes.c_void_p(stream)))
+
+
+# ---- GF(2) toolkit (K4) ------------------------------------------------------------------------
+
+def gf2_rref_packed(packed, n):
+    """(batch, m, words) uint64 packed rows -> (rref, rank (batch,), pivots (batch, min(m,n)))."""
+    lib = load()
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    if packed.ndim != 3:
+        raise ValueError("expected (batch, m, words) packed matrices")
+    batch, m, words = packed.shape
+    if words != (n + 63) // 64:
+        raise ValueError("words must be ceil(n / 64)")
+    out = np.empty_like(packed)
+    rank = np.zeros(batch, dtype=np.int32)
+    npiv = min(m, n)
+    piv = np.full((batch, max(npiv, 1)), -1, dtype=np.int32)
+    check(lib.qcss_gf2_rref(_ptr(packed), batch, m, n, _ptr(out),
+                            rank.ctypes.data_as(_c_i32p), piv.ctypes.data_as(_c_i32p)))
+    return out, rank, piv[:, :npiv]
+
+
+def gf2_rref_bits(mats_u8):
+    """(batch, m, n) uint8 0/1 -> (rref uint8, rank, pivots) through the packed entry point."""
+    batch, m, n = mats_u8.shape
+    words = (n + 63) // 64
+    padded = np.zeros((batch, m, words * 64), dtype=np.uint8)
+    padded[:, :, :n] = mats_u8
+    packed = np.packbits(padded, axis=2, bitorder="little").view(np.uint64).reshape(batch, m, words)
+    out, rank, piv = gf2_rref_packed(packed, n)
+    bits = np.unpackbits(out.view(np.uint8).reshape(batch, m, words * 8), axis=2, bitorder="little")
+    return np.ascontiguousarray(bits[:, :, :n]), rank, piv
+
+
+def host_alloc(nbytes):
+    """Pinned host buffer as a uint64 numpy array (freed by host_free(arr))."""
+    lib = load()
+    ptr = ctypes.c_void_p()
+    check(lib.qcss_host_alloc(ctypes.byref(ptr), nbytes))
+    buf = (ctypes.c_uint8 * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.uint64)
+    arr.flags.writeable = True
+    return arr, ptr.value
+
+
+def host_free(ptr_value):
+    check(load().qcss_host_free(ctypes.c_void_p(ptr_value)))

@@ -1,0 +1,625 @@
+// C ABI of libqcss.so (include/qcss.h): code objects, argument checking, launches, and the
+// host-buffer entry points that stream caller memory through the GPU.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/qcss.h"
+#include "launch.h"
+
+using namespace qcss;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define QCSS_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA,     \
+                        "%s failed: %s", #expr, cudaGetErrorString(_e));                      \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int kSlots = 3;
+
+}  // namespace
+
+struct qcss_code {
+    int n = 0, m1 = 0, m2 = 0;
+    bool small = false;                 // register-resident kernels apply (n <= 32, m <= 16)
+    GenericSide side_x{}, side_z{};     // x: which = 2 (H2, _c2_syndromes, Lz); z: which = 1
+    uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
+    uint32_t lmask_x = 0, lmask_z = 0;
+    int named_id = -1;
+    DevBuf fm_x, fm_z, co_x, co_z;      // lookup tables
+    SparseRows sp1{}, sp2{};            // CSR of H1 / H2 for the tiled kernel
+    DevBuf sp1_ptr, sp1_cols, sp2_ptr, sp2_cols;
+    // host-buffer paths
+    cudaStream_t stream = nullptr;
+    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+    DevBuf slot_x[kSlots], slot_z[kSlots];
+    DevBuf buf_a, buf_b, buf_c, buf_d, buf_e;
+    DevBuf tally;
+};
+
+namespace {
+
+uint32_t tail_mask_for(int64_t shots) {
+    const int r = (int)(shots & 31);
+    return r ? ((1u << r) - 1u) : 0xFFFFFFFFu;
+}
+
+int check_planes(const void* p, int64_t stride, int64_t shots, const char* what) {
+    if (p == nullptr) return fail(QCSS_ERR_INVALID, "%s is NULL", what);
+    if (((uintptr_t)p & 15u) != 0) return fail(QCSS_ERR_INVALID, "%s must be 16-byte aligned", what);
+    if (stride < 2 || (stride & 1) || stride * 64 < ((shots + 127) / 128) * 128)
+        return fail(QCSS_ERR_INVALID, "%s: stride (%lld words) must be even and cover %lld shots",
+                    what, (long long)stride, (long long)shots);
+    return QCSS_OK;
+}
+
+// Build one side: masks, logical row, dense tables.
+int build_side(qcss_code* c, GenericSide& s, uint32_t* rows, uint32_t& lmask, int m, const uint8_t* H,
+               const uint8_t* L, int64_t nk, const int64_t* keys, const uint8_t* corr, DevBuf& d_fm,
+               DevBuf& d_co) {
+    const int n = c->n;
+    memset(&s, 0, sizeof(s));
+    s.n = n;
+    s.m = m;
+    s.mode = kModeNone;
+    lmask = 0;
+    for (int t = 0; t < m; ++t) {
+        uint32_t r = 0;
+        for (int j = 0; j < n; ++j)
+            if (H[(size_t)(m - 1 - t) * n + j] & 1) { r |= 1u << j; s.mask[t][j] = 0xFFFFFFFFu; }
+        rows[t] = r;
+    }
+    if (L != nullptr)
+        for (int j = 0; j < n; ++j)
+            if (L[j] & 1) { lmask |= 1u << j; s.lexp[j] = 0xFFFFFFFFu; }
+    if (keys == nullptr || nk <= 0) return QCSS_OK;
+    if (L == nullptr) return fail(QCSS_ERR_INVALID, "a syndrome table needs the logical operator row");
+    const size_t size = (size_t)1 << m;
+    std::vector<uint8_t> fm(size, 2);           // default: miss
+    std::vector<uint32_t> co(size, 0);
+    for (int64_t k = 0; k < nk; ++k) {
+        if (keys[k] < 0 || (uint64_t)keys[k] >= size)
+            return fail(QCSS_ERR_INVALID, "table key %lld out of range for m = %d", (long long)keys[k], m);
+        uint32_t cm = 0;
+        for (int j = 0; j < n; ++j)
+            if (corr[(size_t)k * n + j] & 1) cm |= 1u << j;
+        co[keys[k]] = cm;
+        fm[keys[k]] = (uint8_t)(__builtin_popcount(cm & lmask) & 1);
+    }
+    s.has_miss = 0;
+    for (size_t k = 0; k < size; ++k)
+        if (fm[k] & 2) s.has_miss = 1;
+    s.mode = (m <= kSlicedM) ? kModeSliced : kModeLut;
+    if (m <= kSlicedM) {
+        for (size_t k = 0; k < size; ++k) {
+            s.tt_flip |= (uint32_t)(fm[k] & 1) << k;
+            s.tt_miss |= (uint32_t)((fm[k] >> 1) & 1) << k;
+            for (int j = 0; j < n; ++j) s.tt_corr[j] |= ((co[k] >> j) & 1u) << k;
+        }
+    }
+    QCSS_CUDA(d_fm.reserve(size));
+    QCSS_CUDA(d_co.reserve(size * sizeof(uint32_t)));
+    QCSS_CUDA(cudaMemcpy(d_fm.p, fm.data(), size, cudaMemcpyHostToDevice));
+    QCSS_CUDA(cudaMemcpy(d_co.p, co.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s.lut_fm = (const uint8_t*)d_fm.p;
+    s.lut_corr = (const uint32_t*)d_co.p;
+    return QCSS_OK;
+}
+
+int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, DevBuf& d_cols) {
+    std::vector<int32_t> ptr(m + 1, 0);
+    std::vector<uint16_t> cols;
+    int maxw = 0;
+    for (int i = 0; i < m; ++i) {
+        int w = 0;
+        for (int j = 0; j < n; ++j)
+            if (H[(size_t)i * n + j] & 1) { cols.push_back((uint16_t)j); ++w; }
+        ptr[i + 1] = (int32_t)cols.size();
+        if (w > maxw) maxw = w;
+    }
+    if (cols.empty()) cols.push_back(0);
+    QCSS_CUDA(d_ptr.reserve(ptr.size() * sizeof(int32_t)));
+    QCSS_CUDA(d_cols.reserve(cols.size() * sizeof(uint16_t)));
+    QCSS_CUDA(cudaMemcpy(d_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    QCSS_CUDA(cudaMemcpy(d_cols.p, cols.data(), cols.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    sp.m = m;
+    sp.n = n;
+    sp.max_row_weight = maxw;
+    sp.row_ptr = (const int32_t*)d_ptr.p;
+    sp.cols = (const uint16_t*)d_cols.p;
+    return QCSS_OK;
+}
+
+int ensure_streams(qcss_code* c) {
+    if (c->stream == nullptr) QCSS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i)
+        if (c->slot_stream[i] == nullptr)
+            QCSS_CUDA(cudaStreamCreateWithFlags(&c->slot_stream[i], cudaStreamNonBlocking));
+    return QCSS_OK;
+}
+
+DecodeIO make_io(const qcss_decode_io* io, int64_t shots) {
+    DecodeIO d;
+    memset(&d, 0, sizeof(d));
+    d.ex = (const uint32_t*)io->ex;
+    d.ez = (const uint32_t*)io->ez;
+    d.e_stride = io->e_stride * 2;
+    d.synd_x = (uint32_t*)io->synd_x;
+    d.synd_z = (uint32_t*)io->synd_z;
+    d.s_stride = io->s_stride * 2;
+    d.corr_x = (uint32_t*)io->corr_x;
+    d.corr_z = (uint32_t*)io->corr_z;
+    d.c_stride = io->c_stride * 2;
+    d.flip_x = (uint32_t*)io->flip_x;
+    d.flip_z = (uint32_t*)io->flip_z;
+    d.miss_x = (uint32_t*)io->miss_x;
+    d.miss_z = (uint32_t*)io->miss_z;
+    d.tally = (unsigned long long*)io->tally;
+    d.words = (shots + 31) / 32;
+    d.tail_mask = tail_mask_for(shots);
+    d.sides = (io->ex ? 1 : 0) | (io->ez ? 2 : 0);
+    return d;
+}
+
+int threshold_from_p(double p, uint32_t* thr) {
+    if (!(p >= 0.0) || p > 1.0) return fail(QCSS_ERR_INVALID, "p must be in [0, 1]");
+    double t = std::floor(p * 4294967296.0);
+    if (t > 4294967295.0) t = 4294967295.0;
+    *thr = (uint32_t)t;
+    return QCSS_OK;
+}
+
+int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStream_t stream) {
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (io->ex == nullptr && io->ez == nullptr) return fail(QCSS_ERR_INVALID, "no error planes given");
+    int rc;
+    if (io->ex && (rc = check_planes(io->ex, io->e_stride, shots, "ex planes"))) return rc;
+    if (io->ez && (rc = check_planes(io->ez, io->e_stride, shots, "ez planes"))) return rc;
+    if ((io->synd_x || io->synd_z) && io->s_stride * 64 < shots)
+        return fail(QCSS_ERR_INVALID, "syndrome stride too small");
+    if ((io->corr_x || io->corr_z) && io->c_stride * 64 < shots)
+        return fail(QCSS_ERR_INVALID, "correction stride too small");
+    if (!c->small)
+        return fail(QCSS_ERR_UNSUPPORTED,
+                    "lookup decode covers n <= %d and m <= %d (this code: n = %d, m1 = %d, m2 = %d); "
+                    "use qcss_syndrome for syndrome extraction", kMaxN, kMaxM, c->n, c->m1, c->m2);
+    const bool wants_decode = io->corr_x || io->corr_z || io->flip_x || io->flip_z || io->miss_x ||
+                              io->miss_z || io->tally;
+    if (wants_decode) {
+        if (io->ex && c->side_x.mode == kModeNone)
+            return fail(QCSS_ERR_INVALID, "code has no _c2_syndromes table: cannot decode X errors");
+        if (io->ez && c->side_z.mode == kModeNone)
+            return fail(QCSS_ERR_INVALID, "code has no _c1_syndromes table: cannot decode Z errors");
+    }
+    if (shots == 0) return QCSS_OK;
+    SmallLaunch l;
+    l.x = &c->side_x;
+    l.z = &c->side_z;
+    l.io = make_io(io, shots);
+    l.named_id = c->named_id;
+    l.sample = false;
+    QCSS_CUDA(launch_small(l, stream));
+    return QCSS_OK;
+}
+
+int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+              uint64_t* d_tally, uint64_t* d_ex, uint64_t* d_ez, int64_t e_stride, cudaStream_t stream) {
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (first_shot < 0 || (first_shot & 127)) return fail(QCSS_ERR_INVALID, "first_shot must be a multiple of 128");
+    if (!c->small) return fail(QCSS_ERR_UNSUPPORTED, "Monte-Carlo run covers n <= %d and m <= %d", kMaxN, kMaxM);
+    uint32_t thr = 0;
+    int rc = threshold_from_p(p, &thr);
+    if (rc) return rc;
+    if (d_tally && (c->side_x.mode == kModeNone || c->side_z.mode == kModeNone))
+        return fail(QCSS_ERR_INVALID, "Monte-Carlo tallies need both syndrome tables");
+    if (d_ex || d_ez) {
+        if (d_ex && (rc = check_planes(d_ex, e_stride, shots, "ex planes"))) return rc;
+        if (d_ez && (rc = check_planes(d_ez, e_stride, shots, "ez planes"))) return rc;
+    }
+    if (shots == 0) return QCSS_OK;
+    SmallLaunch l;
+    l.x = &c->side_x;
+    l.z = &c->side_z;
+    memset(&l.io, 0, sizeof(l.io));
+    l.io.words = (shots + 31) / 32;
+    l.io.tail_mask = tail_mask_for(shots);
+    l.io.sides = 3;
+    l.io.tally = (unsigned long long*)d_tally;
+    l.io.ex_out = (uint32_t*)d_ex;
+    l.io.ez_out = (uint32_t*)d_ez;
+    l.io.e_stride = e_stride * 2;
+    l.io.seed = seed;
+    l.io.first_word = (uint64_t)(first_shot / 32);
+    l.io.thr = thr;
+    l.named_id = c->named_id;
+    l.sample = true;
+    QCSS_CUDA(launch_small(l, stream));
+    return QCSS_OK;
+}
+
+int launch_syndrome(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stride, int64_t shots,
+                    uint64_t* d_s, int64_t s_stride, cudaStream_t stream) {
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    int rc;
+    if ((rc = check_planes(d_e, e_stride, shots, "error planes"))) return rc;
+    if ((rc = check_planes(d_s, s_stride, shots, "syndrome planes"))) return rc;
+    if (shots == 0) return QCSS_OK;
+    if (c->small) {
+        qcss_decode_io io;
+        memset(&io, 0, sizeof(io));
+        io.e_stride = e_stride;
+        io.s_stride = s_stride;
+        if (which == 2) { io.ex = d_e; io.synd_x = d_s; }
+        else            { io.ez = d_e; io.synd_z = d_s; }
+        SmallLaunch l;
+        l.x = &c->side_x;
+        l.z = &c->side_z;
+        l.io = make_io(&io, shots);
+        l.named_id = c->named_id;
+        l.sample = false;
+        QCSS_CUDA(launch_small(l, stream));
+        return QCSS_OK;
+    }
+    const SparseRows& sp = (which == 1) ? c->sp1 : c->sp2;
+    cudaError_t e = launch_syndrome_tiled(sp, (const uint32_t*)d_e, e_stride * 2, (uint32_t*)d_s,
+                                          s_stride * 2, (shots + 31) / 32, tail_mask_for(shots), stream);
+    if (e == cudaErrorInvalidValue && (size_t)c->n * 16 > 200 * 1024)
+        return fail(QCSS_ERR_UNSUPPORTED, "n = %d is too large for the shared-memory tile", c->n);
+    QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+void tally_from(const uint64_t* h, int64_t shots, qcss_tally* t) {
+    t->shots = (uint64_t)shots;
+    t->fail_x = h[1];
+    t->fail_z = h[2];
+    t->fail_any = h[3];
+    t->miss_x = h[4];
+    t->miss_z = h[5];
+}
+
+}  // namespace
+
+extern "C" {
+
+QCSS_API int qcss_version(void) { return 100; }
+
+QCSS_API const char* qcss_last_error(void) { return g_err; }
+
+QCSS_API int qcss_device_count(int* count) {
+    if (!count) return fail(QCSS_ERR_INVALID, "count is NULL");
+    QCSS_CUDA(cudaGetDeviceCount(count));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_set_device(int device) {
+    QCSS_CUDA(cudaSetDevice(device));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(QCSS_ERR_INVALID, "ptr is NULL");
+    QCSS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_host_free(void* ptr) {
+    if (ptr) QCSS_CUDA(cudaFreeHost(ptr));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const uint8_t* H2, const uint8_t* Lx,
+                     const uint8_t* Lz, int64_t n1, const int64_t* keys1, const uint8_t* corr1,
+                     int64_t n2, const int64_t* keys2, const uint8_t* corr2, qcss_code** out) {
+    if (!out) return fail(QCSS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || m1 <= 0 || m2 <= 0 || !H1 || !H2) return fail(QCSS_ERR_INVALID, "bad code dimensions");
+    if (n > 65535) return fail(QCSS_ERR_UNSUPPORTED, "n = %d exceeds 65535", n);
+    if ((keys1 && !corr1) || (keys2 && !corr2)) return fail(QCSS_ERR_INVALID, "table keys without corrections");
+    qcss_code* c = new (std::nothrow) qcss_code();
+    if (!c) return fail(QCSS_ERR_NOMEM, "out of host memory");
+    c->n = n;
+    c->m1 = m1;
+    c->m2 = m2;
+    c->small = (n <= kMaxN && m1 <= kMaxM && m2 <= kMaxM);
+    int rc = QCSS_OK;
+    if (c->small) {
+        rc = build_side(c, c->side_x, c->rows_x, c->lmask_x, m2, H2, Lz, n2, keys2, corr2, c->fm_x, c->co_x);
+        if (!rc) rc = build_side(c, c->side_z, c->rows_z, c->lmask_z, m1, H1, Lx, n1, keys1, corr1, c->fm_z, c->co_z);
+        if (!rc) c->named_id = match_named(c->side_x, c->rows_x, c->lmask_x, c->side_z, c->rows_z, c->lmask_z);
+    } else if ((keys1 && n1 > 0) || (keys2 && n2 > 0)) {
+        // tables are accepted but unusable: decode entry points will report UNSUPPORTED
+    }
+    if (!rc) rc = build_sparse(m1, n, H1, c->sp1, c->sp1_ptr, c->sp1_cols);
+    if (!rc) rc = build_sparse(m2, n, H2, c->sp2, c->sp2_ptr, c->sp2_cols);
+    if (rc) {
+        qcss_code_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_code_destroy(qcss_code* c) {
+    if (!c) return QCSS_OK;
+    c->fm_x.release(); c->fm_z.release(); c->co_x.release(); c->co_z.release();
+    c->sp1_ptr.release(); c->sp1_cols.release(); c->sp2_ptr.release(); c->sp2_cols.release();
+    for (int i = 0; i < kSlots; ++i) {
+        c->slot_x[i].release();
+        c->slot_z[i].release();
+        if (c->slot_stream[i]) cudaStreamDestroy(c->slot_stream[i]);
+    }
+    c->buf_a.release(); c->buf_b.release(); c->buf_c.release(); c->buf_d.release(); c->buf_e.release();
+    c->tally.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_code_kernel_name(const qcss_code* c, char* buf, int buflen) {
+    if (!c || !buf || buflen <= 0) return fail(QCSS_ERR_INVALID, "bad arguments");
+    if (!c->small)
+        snprintf(buf, buflen, "tiled-sparse(n=%d)", c->n);
+    else if (c->named_id >= 0)
+        snprintf(buf, buflen, "small-static(%s)", named_name(c->named_id));
+    else
+        snprintf(buf, buflen, "small-generic(nb=%d,mb=%d)", c->n <= 16 ? 16 : 32,
+                 small_bucket_m(c->side_x.m, c->side_z.m));
+    return QCSS_OK;
+}
+
+// ---- device-pointer entry points ------------------------------------------------------------
+
+QCSS_API int qcss_syndrome_dev(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stride, int64_t shots,
+                      uint64_t* d_s, int64_t s_stride, void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    return launch_syndrome(c, which, d_e, e_stride, shots, d_s, s_stride, (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_decode_dev(qcss_code* c, const qcss_decode_io* io, int64_t shots, void* stream) {
+    if (!c || !io) return fail(QCSS_ERR_INVALID, "code or io is NULL");
+    return launch_decode(c, io, shots, (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_mc_run_dev(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                    uint64_t* d_tally, void* stream) {
+    if (!c || !d_tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    return launch_mc(c, p, shots, seed, first_shot, d_tally, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_mc_sample_dev(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                       uint64_t* d_ex, uint64_t* d_ez, int64_t e_stride, void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (!d_ex && !d_ez) return fail(QCSS_ERR_INVALID, "no output planes given");
+    return launch_mc(c, p, shots, seed, first_shot, nullptr, d_ex, d_ez, e_stride, (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+
+QCSS_API int qcss_syndrome(qcss_code* c, int which, const uint64_t* e_planes, int64_t e_stride, int64_t shots,
+                  uint64_t* s_planes, int64_t s_stride) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!e_planes || !s_planes) return fail(QCSS_ERR_INVALID, "NULL planes");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const int m = (which == 1) ? c->m1 : c->m2;
+    const size_t eb = (size_t)c->n * e_stride * 8, sb = (size_t)m * s_stride * 8;
+    QCSS_CUDA(c->buf_a.reserve(eb));
+    QCSS_CUDA(c->buf_b.reserve(sb));
+    QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_planes, eb, cudaMemcpyHostToDevice, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_b.p, 0, sb, c->stream));
+    rc = launch_syndrome(c, which, (const uint64_t*)c->buf_a.p, e_stride, shots, (uint64_t*)c->buf_b.p,
+                         s_stride, c->stream);
+    if (rc) return rc;
+    QCSS_CUDA(cudaMemcpyAsync(s_planes, c->buf_b.p, sb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_decode(qcss_code* c, int which, const uint64_t* e_planes, int64_t e_stride, int64_t shots,
+                uint64_t* corr_planes, uint64_t* flip_plane, uint64_t* miss_plane, qcss_tally* tally) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!e_planes) return fail(QCSS_ERR_INVALID, "NULL planes");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const size_t eb = (size_t)c->n * e_stride * 8, pb = (size_t)e_stride * 8;
+    QCSS_CUDA(c->buf_a.reserve(eb));
+    QCSS_CUDA(c->buf_b.reserve(eb));
+    QCSS_CUDA(c->buf_c.reserve(pb));
+    QCSS_CUDA(c->buf_d.reserve(pb));
+    QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_planes, eb, cudaMemcpyHostToDevice, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_b.p, 0, eb, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_c.p, 0, pb, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_d.p, 0, pb, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
+    qcss_decode_io io;
+    memset(&io, 0, sizeof(io));
+    io.e_stride = io.c_stride = e_stride;
+    io.tally = (uint64_t*)c->tally.p;
+    if (which == 2) {
+        io.ex = (const uint64_t*)c->buf_a.p;
+        io.corr_x = corr_planes ? (uint64_t*)c->buf_b.p : nullptr;
+        io.flip_x = (uint64_t*)c->buf_c.p;
+        io.miss_x = (uint64_t*)c->buf_d.p;
+    } else {
+        io.ez = (const uint64_t*)c->buf_a.p;
+        io.corr_z = corr_planes ? (uint64_t*)c->buf_b.p : nullptr;
+        io.flip_z = (uint64_t*)c->buf_c.p;
+        io.miss_z = (uint64_t*)c->buf_d.p;
+    }
+    rc = launch_decode(c, &io, shots, c->stream);
+    if (rc) return rc;
+    uint64_t h[6] = {0, 0, 0, 0, 0, 0};
+    if (corr_planes) QCSS_CUDA(cudaMemcpyAsync(corr_planes, c->buf_b.p, eb, cudaMemcpyDeviceToHost, c->stream));
+    if (flip_plane) QCSS_CUDA(cudaMemcpyAsync(flip_plane, c->buf_c.p, pb, cudaMemcpyDeviceToHost, c->stream));
+    if (miss_plane) QCSS_CUDA(cudaMemcpyAsync(miss_plane, c->buf_d.p, pb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    if (tally) tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int64_t shots,
+                   qcss_tally* tally) {
+    if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    if (!ex || !ez) return fail(QCSS_ERR_INVALID, "NULL planes");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (e_stride < 2 || (e_stride & 1) || e_stride * 64 < shots)
+        return fail(QCSS_ERR_INVALID, "stride must be even and cover all shots");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    // chunk = a slice of every plane, sized so one slot holds ~32 MB per Pauli type
+    const int64_t total_words = (shots + 63) / 64;
+    int64_t chunk_words = ((int64_t)(32u << 20) / ((int64_t)c->n * 8)) & ~(int64_t)1;
+    if (chunk_words < 2) chunk_words = 2;
+    if (chunk_words > ((total_words + 1) & ~(int64_t)1)) chunk_words = (total_words + 1) & ~(int64_t)1;
+    const size_t slot_bytes = (size_t)c->n * chunk_words * 8;
+    for (int i = 0; i < kSlots; ++i) {
+        QCSS_CUDA(c->slot_x[i].reserve(slot_bytes));
+        QCSS_CUDA(c->slot_z[i].reserve(slot_bytes));
+    }
+    int slot = 0;
+    for (int64_t w0 = 0; w0 < total_words; w0 += chunk_words, slot = (slot + 1) % kSlots) {
+        const int64_t cw = (total_words - w0 < chunk_words) ? (total_words - w0) : chunk_words;
+        const int64_t cshots = (w0 + cw == total_words) ? (shots - w0 * 64) : cw * 64;
+        cudaStream_t st = c->slot_stream[slot];
+        // a partial last chunk leaves stale words behind cw inside the slot: they sit past
+        // `words` for this launch and are masked out by the kernel
+        QCSS_CUDA(cudaMemcpy2DAsync(c->slot_x[slot].p, chunk_words * 8, ex + w0, e_stride * 8, cw * 8, c->n,
+                                    cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(cudaMemcpy2DAsync(c->slot_z[slot].p, chunk_words * 8, ez + w0, e_stride * 8, cw * 8, c->n,
+                                    cudaMemcpyHostToDevice, st));
+        qcss_decode_io io;
+        memset(&io, 0, sizeof(io));
+        io.ex = (const uint64_t*)c->slot_x[slot].p;
+        io.ez = (const uint64_t*)c->slot_z[slot].p;
+        io.e_stride = chunk_words;
+        io.tally = (uint64_t*)c->tally.p;
+        rc = launch_decode(c, &io, cshots, st);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < kSlots; ++i) QCSS_CUDA(cudaStreamSynchronize(c->slot_stream[i]));
+    uint64_t h[6];
+    QCSS_CUDA(cudaMemcpy(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost));
+    tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_mc_run(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot, qcss_tally* tally) {
+    if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
+    rc = launch_mc(c, p, shots, seed, first_shot, (uint64_t*)c->tally.p, nullptr, nullptr, 0, c->stream);
+    if (rc) return rc;
+    uint64_t h[6];
+    QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_mc_sample(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot, uint64_t* ex,
+                   uint64_t* ez, int64_t e_stride) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (!ex || !ez) return fail(QCSS_ERR_INVALID, "NULL planes");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const size_t eb = (size_t)c->n * e_stride * 8;
+    QCSS_CUDA(c->buf_a.reserve(eb));
+    QCSS_CUDA(c->buf_b.reserve(eb));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_a.p, 0, eb, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_b.p, 0, eb, c->stream));
+    rc = launch_mc(c, p, shots, seed, first_shot, nullptr, (uint64_t*)c->buf_a.p, (uint64_t*)c->buf_b.p,
+                   e_stride, c->stream);
+    if (rc) return rc;
+    QCSS_CUDA(cudaMemcpyAsync(ex, c->buf_a.p, eb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaMemcpyAsync(ez, c->buf_b.p, eb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
+// ---- K4 -------------------------------------------------------------------------------------
+
+QCSS_API int qcss_gf2_rref_dev(const uint64_t* d_mats, int batch, int m, int n, uint64_t* d_out, int32_t* d_rank,
+                      int32_t* d_pivots, void* stream) {
+    if (batch < 0 || m < 0 || n < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!d_mats || !d_out) return fail(QCSS_ERR_INVALID, "NULL matrices");
+    if (d_mats == d_out) return fail(QCSS_ERR_INVALID, "in-place reduction is not supported");
+    QCSS_CUDA(launch_gf2_rref(d_mats, batch, m, n, d_out, d_rank, d_pivots, (cudaStream_t)stream));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_gf2_rref(const uint64_t* mats, int batch, int m, int n, uint64_t* out, int32_t* rank,
+                  int32_t* pivots) {
+    if (batch < 0 || m < 0 || n < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!mats || !out) return fail(QCSS_ERR_INVALID, "NULL matrices");
+    const size_t W = (size_t)(n + 63) / 64, bytes = (size_t)batch * m * W * 8;
+    const size_t npiv = (size_t)(m < n ? m : n);
+    void *d_in = nullptr, *d_out = nullptr;
+    int32_t *d_rank = nullptr, *d_piv = nullptr;
+    int rc = QCSS_OK;
+    cudaError_t e = cudaMalloc(&d_in, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_rank, (size_t)batch * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_piv, (size_t)batch * npiv * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, mats, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_gf2_rref((const uint64_t*)d_in, batch, m, n, (uint64_t*)d_out, d_rank, d_piv, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rank) e = cudaMemcpy(rank, d_rank, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && pivots) e = cudaMemcpy(pivots, d_piv, (size_t)batch * npiv * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+        rc = fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "gf2_rref: %s", cudaGetErrorString(e));
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_rank); cudaFree(d_piv);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// Per-thread bit logic of the hot path, shared by the sm_100a kernels (kernels.cu) and by the
+// test-only host emulation (tests/hostemu).  Everything here is branch-uniform integer work on
+// 32-shot words: one bit of a word is one Monte-Carlo shot ("bit-sliced" / plane-major layout).
+//
+// Reference semantics implemented (jimpo/quantum-css-codes):
+//   syndrome      s = H.e mod 2                         css_code.py:728
+//   table key     big-endian vec_to_int(s)              bin_matrix.py:36-43
+//   lookup decode errors ^= table.get(key, 0)           css_code.py:649-685 (miss => unchanged)
+//   logical check L.(e ^ c) mod 2                       css_code.py:124-161, 641-646
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QCSS_HD __host__ __device__ __forceinline__
+#else
+#define QCSS_HD inline
+#endif
+
+namespace qcss {
+
+constexpr int kMaxN = 32;        // register-resident ("small code") kernels: n <= 32 qubits
+constexpr int kMaxM = 16;        // lookup decode: m <= 16 syndrome bits (table in shared memory)
+constexpr int kSlicedM = 5;      // fully bit-sliced decode when m <= 5
+
+enum Mode : int32_t { kModeNone = 0, kModeSliced = 1, kModeLut = 2 };
+
+// One Pauli side of a small code, generic (runtime H).  Internal row order is *key-bit order*:
+// row t of `mask` produces bit t of the big-endian table key, i.e. reference row m-1-t.
+struct GenericSide {
+    int32_t n, m, mode, has_miss;
+    uint32_t tt_flip, tt_miss;            // sliced mode: bit k = value at key k
+    uint32_t lexp[kMaxN];                 // 0 / ~0 : logical operator row L[j]
+    uint32_t mask[kMaxM][kMaxN];          // 0 / ~0 : H[m-1-t][j]
+    uint32_t tt_corr[kMaxN];              // sliced mode: correction truth table of qubit j
+    const uint8_t* lut_fm;                // lut mode: [2^m] bytes, bit0 = L.corr parity, bit1 = miss
+    const uint32_t* lut_corr;             // lut mode: [2^m] correction bit masks (bit j = qubit j)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Bit-matrix transpose inside registers.  w[i] holds plane i for 32 shots; afterwards, for every
+// block b of W shots, bits [b*W, b*W+W) of w[j] hold the W plane-bits of shot b*W + j
+// (bit i of that field = plane i).  Classic butterfly network, W in {8, 16, 32}.
+template <int W>
+QCSS_HD void transpose_blocks(uint32_t (&w)[W]) {
+#pragma unroll
+    for (int d = W / 2; d >= 1; d >>= 1) {
+        // mask with d ones then d zeros, repeating
+        uint32_t mk = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) if (((b / d) & 1) == 0) mk |= (1u << b);
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if ((j & d) == 0) {
+                uint32_t a = w[j], b = w[j + d];
+                uint32_t t = ((a >> d) ^ b) & mk;
+                w[j + d] = b ^ t;
+                w[j] = a ^ (t << d);
+            }
+        }
+    }
+}
+
+// Arbitrary boolean function of M bit-sliced variables given its truth table (bit k = value when
+// the variables spell k, v[0] = LSB).  Mux tree, 2^M - 1 three-input logic ops.
+template <int M>
+QCSS_HD uint32_t eval_truth_table(const uint32_t (&v)[M], uint32_t tt) {
+    uint32_t node[1 << (M > 0 ? M - 1 : 0)];
+    if (M == 0) return 0u - (tt & 1u);
+#pragma unroll
+    for (int k = 0; k < (1 << (M - 1)); ++k) {
+        uint32_t l0 = 0u - ((tt >> (2 * k)) & 1u), l1 = 0u - ((tt >> (2 * k + 1)) & 1u);
+        node[k] = (v[0] & l1) | (~v[0] & l0);
+    }
+#pragma unroll
+    for (int lvl = 1; lvl < M; ++lvl) {
+#pragma unroll
+        for (int k = 0; k < (1 << (M - 1 - lvl)); ++k)
+            node[k] = (v[lvl] & node[2 * k + 1]) | (~v[lvl] & node[2 * k]);
+    }
+    return node[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the fused sampler.
+struct Philox {
+    uint32_t k0, k1;
+    QCSS_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+        lo = a * b;
+        hi = __umulhi(a, b);
+#else
+        uint64_t p = (uint64_t)a * (uint64_t)b;
+        lo = (uint32_t)p;
+        hi = (uint32_t)(p >> 32);
+#endif
+    }
+    QCSS_HD void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) const {
+        uint32_t ka = k0, kb = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, c0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+            uint32_t n0 = hi1 ^ c1 ^ ka, n2 = hi0 ^ c3 ^ kb;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// Depolarising draw for 32 shots of qubit j (one word): each shot independently suffers a Pauli
+// error with probability thr / 2^32, uniformly X, Y or Z.  Returns x = X|Y and z = Z|Y planes.
+// Random words come from Philox blocks with key = seed, counter = (g_lo, g_hi, j, block index),
+// g = global index of the 32-shot word, so the draw is independent of launch shape and GPU count.
+//   stage 1 ("r < thr" for 32 lanes at once): block q = 0..7 supplies the random words for
+//     threshold bits 31-4q .. 28-4q (one word per bit, MSB first); lanes whose random bit differs
+//     from the threshold bit are decided.  Stops after the first block that leaves no lane
+//     undecided (2-3 blocks typically); lanes equal to thr in all 32 bits count as "no error".
+//   stage 2 (only if some lane has an error): each further block gives two attempts
+//     (w0,w1) and (w2,w3) = (x bits, z bits); (0,0) is rejected and retried, so X, Z, Y each
+//     have probability exactly 1/3.
+QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t thr,
+                              uint32_t& x, uint32_t& z) {
+    Philox px;
+    px.k0 = (uint32_t)seed;
+    px.k1 = (uint32_t)(seed >> 32);
+    const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+    uint32_t blk = 0u;
+    uint32_t buf[4];
+    uint32_t und = 0xFFFFFFFFu, err = 0u;
+#pragma unroll 1
+    for (int q = 0; q < 8 && und != 0u; ++q) {
+        px.block(g_lo, g_hi, j, blk++, buf);
+        const uint32_t tq = thr >> (28 - 4 * q);      // low 4 bits: threshold bits of this block
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t tb = 0u - ((tq >> (3 - k)) & 1u);   // all-ones when the bit is set
+            const uint32_t r = buf[k];
+            err |= und & ~r & tb;
+            und &= r ^ ~tb;
+        }
+    }
+    x = 0u;
+    z = 0u;
+    uint32_t need = err;
+#pragma unroll 1
+    while (need != 0u) {
+        px.block(g_lo, g_hi, j, blk++, buf);
+        uint32_t ok = need & (buf[0] | buf[1]);
+        x |= ok & buf[0];
+        z |= ok & buf[1];
+        need &= ~ok;
+        ok = need & (buf[2] | buf[3]);
+        x |= ok & buf[2];
+        z |= ok & buf[3];
+        need &= ~ok;
+    }
+}
+
+QCSS_HD uint32_t popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Side accumulators.  add(j, e) folds one error plane word into the syndrome words; after all n
+// planes, finish() yields the bit-sliced decode outputs.
+struct WordOut {
+    uint32_t flip;      // L.(e ^ c) per shot
+    uint32_t miss;      // syndrome not in table
+};
+
+// Lookup over transposed keys.  LutRead(k) returns the byte at key k (shared memory on device).
+template <int MB, class LutRead>
+QCSS_HD void lut_flip_miss(uint32_t (&s)[MB], int has_miss, LutRead rd, uint32_t& fc, uint32_t& miss) {
+    static_assert(MB == 8 || MB == 16, "lut key width");
+    transpose_blocks<MB>(s);
+    fc = 0u; miss = 0u;
+    constexpr int kBlocks = 32 / MB;
+    constexpr uint32_t kKeyMask = (1u << MB) - 1u;
+#pragma unroll
+    for (int j = 0; j < MB; ++j) {
+#pragma unroll
+        for (int b = 0; b < kBlocks; ++b) {
+            uint32_t key = (s[j] >> (b * MB)) & kKeyMask;
+            uint32_t ent = rd(key);
+            fc |= (ent & 1u) << (b * MB + j);
+            if (has_miss) miss |= ((ent >> 1) & 1u) << (b * MB + j);
+        }
+    }
+}
+
+// Same walk, but fetching the n-bit correction of every shot and re-slicing it into planes.
+template <int MB, class CorrRead>
+QCSS_HD void lut_corrections(const uint32_t (&keys_t)[MB], CorrRead rd, uint32_t (&planes)[32]) {
+    constexpr int kBlocks = 32 / MB;
+    constexpr uint32_t kKeyMask = (1u << MB) - 1u;
+    // planes[] first holds one correction mask per shot, then is transposed 32x32 in place:
+    // afterwards planes[q] bit s = bit q of shot s's mask.
+#pragma unroll
+    for (int j = 0; j < MB; ++j)
+#pragma unroll
+        for (int b = 0; b < kBlocks; ++b)
+            planes[b * MB + j] = rd((keys_t[j] >> (b * MB)) & kKeyMask);
+    transpose_blocks<32>(planes);
+}
+
+}  // namespace qcss

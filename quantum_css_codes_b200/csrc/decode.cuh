@@ -1,0 +1,227 @@
+// Small-code (n <= 32) syndrome + lookup-decode + logical-check pipeline for one "unit" of
+// VEC 32-shot words.  Shared by the sm_100a kernels and the test-only host emulation.
+#pragma once
+#include "core.cuh"
+
+namespace qcss {
+
+struct Counters {
+    uint32_t fail_x, fail_z, fail_any, miss_x, miss_z;
+};
+
+// Device-side view of qcss_decode_io in 32-bit words (all strides in uint32 units).
+struct DecodeIO {
+    const uint32_t* ex;
+    const uint32_t* ez;
+    int64_t e_stride;
+    uint32_t* synd_x;
+    uint32_t* synd_z;
+    int64_t s_stride;
+    uint32_t* corr_x;
+    uint32_t* corr_z;
+    int64_t c_stride;
+    uint32_t* flip_x;
+    uint32_t* flip_z;
+    uint32_t* miss_x;
+    uint32_t* miss_z;
+    unsigned long long* tally;   // [6]
+    int64_t words;               // ceil(shots / 32)
+    uint32_t tail_mask;          // valid bits of word words-1
+    int32_t sides;               // bit0: X side (which = 2), bit1: Z side (which = 1)
+    // fused sampler
+    uint32_t* ex_out;            // sampled planes written here when non-null
+    uint32_t* ez_out;
+    uint64_t seed;
+    uint64_t first_word;         // global index of word 0 (first_shot / 32)
+    uint32_t thr;                // floor(p * 2^32)
+};
+
+// ---- loads ------------------------------------------------------------------------------------
+template <int VEC>
+QCSS_HD void load_words(const uint32_t* p, uint32_t (&out)[VEC]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]) : "l"(p));
+    } else if constexpr (VEC == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                     : "=r"(out[0]), "=r"(out[1]) : "l"(p));
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) out[v] = __ldg(p + v);
+    }
+#else
+    for (int v = 0; v < VEC; ++v) out[v] = p[v];
+#endif
+}
+
+template <int VEC>
+QCSS_HD void store_words(uint32_t* p, const uint32_t (&in)[VEC]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(in[0], in[1], in[2], in[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(in[0], in[1]);
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) p[v] = in[v];
+    }
+#else
+    for (int v = 0; v < VEC; ++v) p[v] = in[v];
+#endif
+}
+
+// ---- side policies ----------------------------------------------------------------------------
+// Generic: H, L and truth tables are runtime data (kernel parameters -> constant bank operands).
+//   MB == kSlicedM : fully bit-sliced decode (m <= 5)
+//   MB == 8 or 16  : transpose + shared-memory table
+template <int NB_, int MB_>
+struct GenericPolicy {
+    static constexpr int NB = NB_, MB = MB_;
+    static constexpr bool kSliced = (MB_ == kSlicedM);
+    const GenericSide* p;
+    QCSS_HD int n() const { return p->n; }
+    QCSS_HD int m() const { return p->m; }
+    QCSS_HD bool has_table() const { return p->mode != kModeNone; }
+    QCSS_HD bool has_miss() const { return p->has_miss != 0; }
+    QCSS_HD uint32_t tt_flip() const { return p->tt_flip; }
+    QCSS_HD uint32_t tt_miss() const { return p->tt_miss; }
+    QCSS_HD uint32_t tt_corr(int j) const { return p->tt_corr[j]; }
+    QCSS_HD void add(int j, uint32_t e, uint32_t (&s)[MB], uint32_t& le) const {
+#pragma unroll
+        for (int t = 0; t < MB; ++t) s[t] ^= e & p->mask[t][j];
+        le ^= e & p->lexp[j];
+    }
+};
+
+// Static: everything about H, L (and, for sliced sides, the truth tables) is a compile-time
+// constant supplied by a descriptor D (named_codes.inc).  XORs against zero entries vanish.
+template <class D>
+struct StaticPolicy {
+    static constexpr int NB = D::N, MB = D::MB;
+    static constexpr bool kSliced = D::kSliced;
+    QCSS_HD int n() const { return D::N; }
+    QCSS_HD int m() const { return D::M; }
+    QCSS_HD bool has_table() const { return true; }
+    QCSS_HD bool has_miss() const { return D::kHasMiss; }
+    QCSS_HD uint32_t tt_flip() const { return D::kTtFlip; }
+    QCSS_HD uint32_t tt_miss() const { return D::kTtMiss; }
+    QCSS_HD uint32_t tt_corr(int j) const { return D::tt_corr(j); }
+    QCSS_HD void add(int j, uint32_t e, uint32_t (&s)[MB], uint32_t& le) const {
+#pragma unroll
+        for (int t = 0; t < MB; ++t)
+            if ((D::row(t) >> j) & 1u) s[t] ^= e;
+        if ((D::kL >> j) & 1u) le ^= e;
+    }
+};
+
+// ---- finish one word of one side ---------------------------------------------------------------
+template <class P, class LutFm, class LutCorr>
+QCSS_HD WordOut finish_side(const P& pol, uint32_t (&s)[P::MB], uint32_t le, LutFm lut_fm,
+                            LutCorr lut_corr, uint32_t* synd, int64_t s_stride, uint32_t* corr,
+                            int64_t c_stride, uint32_t* flip_p, uint32_t* miss_p, int64_t w,
+                            uint32_t valid) {
+    constexpr int MB = P::MB;
+    const int m = pol.m(), n = pol.n();
+    const bool in_range = valid != 0u;
+    if (synd != nullptr && in_range) {
+#pragma unroll
+        for (int t = 0; t < MB; ++t)
+            if (t < m) synd[(int64_t)(m - 1 - t) * s_stride + w] = s[t] & valid;
+    }
+    WordOut o;
+    o.flip = 0u;
+    o.miss = 0u;
+    if (!pol.has_table()) return o;
+    uint32_t fc = 0u;
+    if constexpr (P::kSliced) {
+        fc = eval_truth_table<MB>(s, pol.tt_flip());
+        if (pol.has_miss()) o.miss = eval_truth_table<MB>(s, pol.tt_miss());
+        if (corr != nullptr && in_range) {
+#pragma unroll
+            for (int j = 0; j < P::NB; ++j)
+                if (j < n)
+                    corr[(int64_t)j * c_stride + w] = eval_truth_table<MB>(s, pol.tt_corr(j)) & valid;
+        }
+    } else {
+        lut_flip_miss<MB>(s, pol.has_miss() ? 1 : 0, lut_fm, fc, o.miss);
+        if (corr != nullptr && in_range) {
+            uint32_t planes[32];
+            lut_corrections<MB>(s, lut_corr, planes);
+#pragma unroll
+            for (int j = 0; j < P::NB; ++j)
+                if (j < n) corr[(int64_t)j * c_stride + w] = planes[j] & valid;
+        }
+    }
+    o.flip = le ^ fc;
+    if (flip_p != nullptr && in_range) flip_p[w] = o.flip & valid;
+    if (miss_p != nullptr && in_range) miss_p[w] = o.miss & valid;
+    return o;
+}
+
+// ---- one unit: VEC consecutive words of both sides -------------------------------------------
+template <class PX, class PZ, int VEC, bool SAMPLE, class LutFmX, class LutCorrX, class LutFmZ,
+          class LutCorrZ>
+QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_t unit,
+                          LutFmX fm_x, LutCorrX co_x, LutFmZ fm_z, LutCorrZ co_z, Counters& c) {
+    static_assert(PX::NB == PZ::NB, "sides share the qubit count");
+    constexpr int NB = PX::NB;
+    const int64_t w0 = unit * VEC;
+    const bool do_x = SAMPLE || (io.sides & 1), do_z = SAMPLE || (io.sides & 2);
+    uint32_t sx[VEC][PX::MB], sz[VEC][PZ::MB], lex[VEC], lez[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+        for (int t = 0; t < PX::MB; ++t) sx[v][t] = 0u;
+#pragma unroll
+        for (int t = 0; t < PZ::MB; ++t) sz[v][t] = 0u;
+        lex[v] = 0u;
+        lez[v] = 0u;
+    }
+    const int n = px.n();
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+            uint32_t xe[VEC], ze[VEC];
+            if constexpr (SAMPLE) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
+                                     xe[v], ze[v]);
+                if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xe);
+                if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, ze);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { xe[v] = 0u; ze[v] = 0u; }
+                if (do_x) load_words<VEC>(io.ex + (int64_t)j * io.e_stride + w0, xe);
+                if (do_z) load_words<VEC>(io.ez + (int64_t)j * io.e_stride + w0, ze);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                px.add(j, xe[v], sx[v], lex[v]);
+                pz.add(j, ze[v], sz[v], lez[v]);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int64_t w = w0 + v;
+        const bool in_range = w < io.words;
+        const uint32_t valid = in_range ? ((w == io.words - 1) ? io.tail_mask : 0xFFFFFFFFu) : 0u;
+        WordOut ox, oz;
+        ox.flip = ox.miss = oz.flip = oz.miss = 0u;
+        if (do_x)
+            ox = finish_side(px, sx[v], lex[v], fm_x, co_x, io.synd_x, io.s_stride, io.corr_x,
+                             io.c_stride, io.flip_x, io.miss_x, w, valid);
+        if (do_z)
+            oz = finish_side(pz, sz[v], lez[v], fm_z, co_z, io.synd_z, io.s_stride, io.corr_z,
+                             io.c_stride, io.flip_z, io.miss_z, w, valid);
+        c.fail_x += popc32(ox.flip & valid);
+        c.fail_z += popc32(oz.flip & valid);
+        c.fail_any += popc32((ox.flip | oz.flip) & valid);
+        c.miss_x += popc32(ox.miss & valid);
+        c.miss_z += popc32(oz.miss & valid);
+    }
+}
+
+}  // namespace qcss

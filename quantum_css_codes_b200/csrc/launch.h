@@ -1,0 +1,38 @@
+// Internal launch interface between the C ABI (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "decode.cuh"
+
+namespace qcss {
+
+// ---- small codes (small_kernels.cu) -----------------------------------------------------------
+struct SmallLaunch {
+    const GenericSide* x;      // which = 2 side (X errors)
+    const GenericSide* z;      // which = 1 side (Z errors)
+    DecodeIO io;
+    int named_id;              // index into named::kNamed, or -1 for the generic kernels
+    bool sample;               // fused Philox sampler instead of loading error planes
+};
+cudaError_t launch_small(const SmallLaunch& l, cudaStream_t stream);
+int match_named(const GenericSide& x, const uint32_t* rows_x, uint32_t lx, const GenericSide& z,
+                const uint32_t* rows_z, uint32_t lz);
+const char* named_name(int id);
+int small_bucket_m(int mx, int mz);
+
+// ---- any-size sparse syndrome (tiled_kernels.cu) --------------------------------------------
+struct SparseRows {            // CSR of one parity-check matrix, device pointers
+    int m, n, max_row_weight;
+    const int32_t* row_ptr;    // [m + 1]
+    const uint16_t* cols;      // [nnz]
+};
+cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes, int64_t e_stride,
+                                  uint32_t* s_planes, int64_t s_stride, int64_t words,
+                                  uint32_t tail_mask, cudaStream_t stream);
+
+// ---- batched GF(2) Gauss-Jordan (gf2_kernels.cu) --------------------------------------------
+cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out,
+                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
+
+}  // namespace qcss

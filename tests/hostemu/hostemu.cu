@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product package.
+// Runs the per-thread bodies of the CUDA kernels (csrc/core.cuh, csrc/decode.cuh: the same
+// __host__ __device__ functions the sm_100a kernels call) sequentially on the host, so the bit
+// logic (transposes, truth-table muxes, table walk, Philox sampler, static code descriptors)
+// can be checked against the oracle in the GPU-less build container.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../quantum_css_codes_b200/csrc/decode.cuh"
+#include "../../quantum_css_codes_b200/csrc/named_codes.inc"
+
+using namespace qcss;
+
+namespace {
+
+template <class PX, class PZ, int VEC, bool SAMPLE>
+void run(const PX& px, const PZ& pz, const DecodeIO& io, const uint8_t* fmx, const uint32_t* cox,
+         const uint8_t* fmz, const uint32_t* coz, uint64_t* tally) {
+    auto fm_x = [fmx](uint32_t k) { return (uint32_t)fmx[k]; };
+    auto fm_z = [fmz](uint32_t k) { return (uint32_t)fmz[k]; };
+    auto co_x = [cox](uint32_t k) { return cox[k]; };
+    auto co_z = [coz](uint32_t k) { return coz[k]; };
+    const int64_t units = (io.words + VEC - 1) / VEC;
+    for (int64_t u = 0; u < units; ++u) {
+        Counters c = {0, 0, 0, 0, 0};
+        process_unit<PX, PZ, VEC, SAMPLE>(px, pz, io, u, fm_x, co_x, fm_z, co_z, c);
+        tally[1] += c.fail_x; tally[2] += c.fail_z; tally[3] += c.fail_any;
+        tally[4] += c.miss_x; tally[5] += c.miss_z;
+    }
+}
+
+template <int NB, int MB, int VEC>
+void run_generic(const GenericSide* x, const GenericSide* z, const DecodeIO& io, int sample, uint64_t* tally) {
+    GenericPolicy<NB, MB> px{x}, pz{z};
+    if (sample) run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, true>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+    else run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, false>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+}
+
+template <class DX, class DZ>
+void run_named(const GenericSide* x, const GenericSide* z, const DecodeIO& io, int sample, uint64_t* tally) {
+    StaticPolicy<DX> px;
+    StaticPolicy<DZ> pz;
+    if (sample) run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, true>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+    else run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, false>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+}
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int emu_sizeof_side(void) { return (int)sizeof(GenericSide); }
+__attribute__((visibility("default"))) int emu_sizeof_io(void) { return (int)sizeof(DecodeIO); }
+
+// named_id < 0: generic kernels with the launch_small bucket rule; else the static descriptor.
+__attribute__((visibility("default")))
+int emu_decode(const GenericSide* x, const GenericSide* z, const DecodeIO* io, int named_id, int sample,
+               uint64_t* tally) {
+#define EMU_CASE(ID, DX, DZ) \
+    if (named_id == ID) { run_named<named::DX, named::DZ>(x, z, *io, sample, tally); return 0; }
+    QCSS_FOR_EACH_NAMED(EMU_CASE)
+#undef EMU_CASE
+    const int m = x->m > z->m ? x->m : z->m;
+    const int mb = m <= kSlicedM ? kSlicedM : (m <= 8 ? 8 : 16);
+    if (x->n <= 16) {
+        if (mb == kSlicedM) run_generic<16, kSlicedM, 4>(x, z, *io, sample, tally);
+        else if (mb == 8) run_generic<16, 8, 4>(x, z, *io, sample, tally);
+        else run_generic<16, 16, 4>(x, z, *io, sample, tally);
+    } else {
+        if (mb == kSlicedM) run_generic<32, kSlicedM, 2>(x, z, *io, sample, tally);
+        else if (mb == 8) run_generic<32, 8, 2>(x, z, *io, sample, tally);
+        else run_generic<32, 16, 2>(x, z, *io, sample, tally);
+    }
+    return 0;
+}
+
+__attribute__((visibility("default")))
+void emu_transpose32(uint32_t* w) {
+    uint32_t a[32];
+    memcpy(a, w, sizeof(a));
+    transpose_blocks<32>(a);
+    memcpy(w, a, sizeof(a));
+}
+
+__attribute__((visibility("default")))
+void emu_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    Philox px;
+    px.k0 = key[0];
+    px.k1 = key[1];
+    uint32_t o[4];
+    px.block(ctr[0], ctr[1], ctr[2], ctr[3], o);
+    memcpy(out, o, sizeof(o));
+}
+
+__attribute__((visibility("default")))
+int emu_named_side(int id, int which_x, int* n, int* m, uint32_t* rows, uint32_t* l) {
+    if (id < 0 || id >= named::kNumNamed) return -1;
+    const named::SideInfo& s = which_x ? named::kNamed[id].x : named::kNamed[id].z;
+    *n = s.n; *m = s.m; *l = s.l;
+    for (int t = 0; t < 16; ++t) rows[t] = s.rows[t];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libqcss.so via ctypes),
+against the oracle on the same inputs.  Bit-exact everywhere (integer work)."""
+
+import numpy as np
+import pytest
+
+from oracle import css as ocss, montecarlo as omc, philox as ophilox
+from quantum_css_codes_b200 import CSSCode, SyndromeCode, codes, planes, _native
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["steane", "qrm15", "golay23"]
+_cache = {}
+
+
+def pair(name):
+    if name not in _cache:
+        h1, h2 = getattr(codes, name)()
+        _cache[name] = (CSSCode(np.array(h1), np.array(h2)), ocss.build_css(np.array(h1), np.array(h2)))
+    return _cache[name]
+
+
+def test_library_loaded_and_device_present():
+    import ctypes
+    lib = _native.load()
+    count = ctypes.c_int()
+    _native.check(lib.qcss_device_count(ctypes.byref(count)))
+    assert count.value >= 1
+    assert lib.qcss_version() >= 100
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_named_codes_use_static_kernels(name):
+    code, _ = pair(name)
+    assert code.device.kernel_name() == f"small-static({name})"
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_weight_le_1_errors(name):
+    """BASELINE config 1 on the GPU: syndrome + decode of every weight <= 1 X / Z error."""
+    code, ref = pair(name)
+    errs = np.vstack([np.zeros((1, code.n), dtype=np.uint8), np.eye(code.n, dtype=np.uint8)])
+    for which in (1, 2):
+        h, table, lop = ocss.pauli_side(ref, which)
+        assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(h, errs))
+        out = code.decode(errs, which)
+        assert np.array_equal(out["correction"], errs)
+        assert not out["flip"].any() and not out["miss"].any()
+        keys = omc.keys_batch(omc.syndromes_batch(h, errs))
+        assert all(int(k) in table for k in keys)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("shots,p", [(1, 0.3), (127, 0.1), (128, 0.5), (129, 0.02), (100003, 0.05)])
+def test_random_batches_bit_exact(name, shots, p):
+    code, ref = pair(name)
+    rng = np.random.default_rng(shots)
+    ex, ez = omc.sample_depolarizing(rng, shots, code.n, p)
+    for which, errs in ((2, ex), (1, ez)):
+        h, table, lop = ocss.pauli_side(ref, which)
+        want = omc.decode_batch(h, table, lop, errs)
+        assert np.array_equal(code.syndromes(errs, which), want["synd"])
+        out = code.decode(errs, which)
+        assert np.array_equal(out["correction"], want["corr"])
+        assert np.array_equal(out["flip"], want["flip"])
+        assert np.array_equal(out["miss"], want["miss"])
+    assert code.decode_xz(ex, ez) == omc.tally_xz(ref, ex, ez)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("which", [1, 2])
+def test_golden_reference_decodes(golden, name, which):
+    """Outputs of the unmodified reference (tests/golden) reproduced by the CUDA path."""
+    code, _ = pair(name)
+    pre = f"{name}_w{which}"
+    errs = golden[pre + "_errs"].astype(np.uint8)
+    assert np.array_equal(code.syndromes(errs, which), golden[pre + "_synd"])
+    out = code.decode(errs, which)
+    assert np.array_equal(out["correction"], golden[pre + "_corr"])
+    assert np.array_equal(out["flip"], golden[pre + "_flip"])
+    assert np.array_equal(out["miss"], golden[pre + "_miss"])
+
+
+def test_steane_all_pauli_patterns():
+    """All 4^7 Pauli patterns (joint X/Z): tallies equal the oracle's, incl. fail_any."""
+    code, ref = pair("steane")
+    pats = omc.all_patterns(14)
+    ex, ez = pats[:, :7].copy(), pats[:, 7:].copy()
+    got = code.decode_xz(ex, ez)
+    assert got == omc.tally_xz(ref, ex, ez)
+    assert got["fail_x"] == 64 * 128 and got["fail_z"] == 64 * 128
+
+
+A4 = {("qrm15", 1): [0, 0, 105, 35, 1260, 168, 4725, 435, 6000, 280, 2835, 105, 420, 0, 15, 1],
+      ("qrm15", 2): [0, 0, 0, 0, 965, 1211, 3625, 2055, 4380, 1380, 1792, 400, 455, 105, 15, 1],
+      ("golay23", 1): [0, 0, 0, 0, 8855, 5313, 86779, 28589, 429088, 101200, 1005928, 171304, 1180774, 138138,
+                       715990, 61226, 216568, 14168, 28336, 0, 1771, 253, 23, 1]}
+A4["golay23", 2] = A4["golay23", 1]
+A4_MISS_QRM_X = [0, 0, 0, 0, 840, 1848, 1960, 2520, 2520, 1960, 1848, 840, 0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("name,which", list(A4.keys()))
+def test_exhaustive_failure_weight_enumerators(name, which):
+    """Every one of the 2^n patterns of one Pauli type: flips (and misses) by weight = SURVEY A.4."""
+    code, _ = pair(name)
+    n = code.n
+    flips = np.zeros(n + 1, dtype=np.int64)
+    misses = np.zeros(n + 1, dtype=np.int64)
+    chunk = 1 << 21
+    for lo in range(0, 1 << n, chunk):
+        pats = omc.all_patterns(n, lo, min(1 << n, lo + chunk))
+        out = code.decode(pats, which)
+        wt = pats.sum(axis=1)
+        flips += np.bincount(wt[out["flip"] == 1], minlength=n + 1)
+        misses += np.bincount(wt[out["miss"] == 1], minlength=n + 1)
+    assert flips.tolist() == A4[(name, which)]
+    assert misses.tolist() == (A4_MISS_QRM_X if (name, which) == ("qrm15", 2) else [0] * (n + 1))
+
+
+@pytest.mark.parametrize("n,m1,m2", [(5, 2, 2), (12, 5, 4), (16, 8, 7), (20, 3, 12), (32, 16, 9), (9, 6, 1),
+                                     (32, 5, 5), (17, 8, 8)])
+def test_generic_kernels_partial_tables(n, m1, m2):
+    """Codes that match no compiled-in descriptor run the generic (runtime-H) kernels."""
+    rng = np.random.default_rng(n * 100 + m1)
+    sides = {}
+    for which, m in ((1, m1), (2, m2)):
+        h = rng.integers(0, 2, size=(m, n))
+        lrow = rng.integers(0, 2, size=n)
+        keys = rng.permutation(1 << m)[: max(1, (1 << m) * 2 // 3)]
+        sides[which] = (h, {int(k): rng.integers(0, 2, size=n) for k in keys}, lrow[None, :])
+    dev = _native.DeviceCode(n, sides[1][0], sides[2][0], sides[1][2][0], sides[2][2][0], sides[1][1], sides[2][1])
+    assert dev.kernel_name().startswith("small-generic")
+    shots = 5000
+    ex = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+    ez = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+    tall = {}
+    for which, errs in ((2, ex), (1, ez)):
+        want = omc.decode_batch(*sides[which], errs)
+        e_planes = planes.pack_planes(errs)
+        s = planes.unpack_planes(dev.syndrome_planes(e_planes, shots, which), shots)
+        assert np.array_equal(s, want["synd"])
+        corr, flip, miss, tally = dev.decode_planes(e_planes, shots, which)
+        assert np.array_equal(planes.unpack_planes(corr, shots), want["corr"])
+        assert np.array_equal(planes.unpack_plane(flip, shots), want["flip"])
+        assert np.array_equal(planes.unpack_plane(miss, shots), want["miss"])
+        tall[which] = want
+    got = dev.decode_xz_planes(planes.pack_planes(ex), planes.pack_planes(ez), shots)
+    assert got["fail_any"] == int((tall[2]["flip"] | tall[1]["flip"]).sum())
+    assert got["miss_x"] == int(tall[2]["miss"].sum()) and got["miss_z"] == int(tall[1]["miss"].sum())
+
+
+# ---- fused Philox sampler -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("p", [1e-3, 0.05, 0.5, 0.0, 1.0])
+def test_fused_sampler_bit_exact_vs_oracle(name, p):
+    code, ref = pair(name)
+    shots, seed, first = 6000, 0xC0FFEE1234, 128 * 11
+    ex, ez = code.sample_errors(p, shots, seed, first)
+    ox, oz = ophilox.sample_bits(seed, first, shots, code.n, p)
+    assert np.array_equal(ex, ox) and np.array_equal(ez, oz)
+    assert code.monte_carlo(p, shots, seed, first) == omc.tally_xz(ref, ox, oz)
+
+
+def test_monte_carlo_independent_of_sharding():
+    code, _ = pair("steane")
+    whole = code.monte_carlo(0.05, 1 << 20, seed=11)
+    parts = [code.monte_carlo(0.05, 1 << 18, seed=11, first_shot=i << 18) for i in range(4)]
+    for key in whole:
+        assert whole[key] == sum(p[key] for p in parts)
+
+
+@pytest.mark.parametrize("name,p,shots", [("steane", 1e-2, 1 << 30), ("steane", 5e-2, 1 << 28),
+                                          ("qrm15", 5e-2, 1 << 28), ("golay23", 5e-2, 1 << 28)])
+def test_monte_carlo_rates_within_binomial_ci(name, p, shots):
+    """GPU-sampled logical error rates vs the exact enumerator rates, 5 sigma."""
+    code, ref = pair(name)
+    got = code.monte_carlo(p, shots, seed=2026)
+    q = 2 * p / 3
+    for key, which in (("fail_x", 2), ("fail_z", 1)):
+        h, table, lop = ocss.pauli_side(ref, which)
+        flips, misses = (A4[(name, which)], None) if (name, which) in A4 else omc.failure_enumerator(h, table, lop)
+        rate = omc.exact_rate(flips, q)
+        sigma = np.sqrt(rate * (1 - rate) / shots)
+        assert abs(got[key] / shots - rate) < 5 * sigma, (key, got[key] / shots, rate)
+    assert got["shots"] == shots
+
+
+def test_large_host_buffer_decode_crosses_chunks():
+    """qcss_decode_xz streams host planes in chunks; a batch spanning several chunks must tally
+    exactly like the fused run that sampled the same planes on the device."""
+    code, ref = pair("steane")
+    shots = 90_000_001
+    ex, ez = code.device.mc_sample(0.02, shots, seed=5)
+    got = code.device.decode_xz_planes(ex, ez, shots)
+    assert got == code.monte_carlo(0.02, shots, seed=5)
+    sub = 200_000
+    ox, oz = planes.unpack_planes(ex[:, : sub // 64], sub), planes.unpack_planes(ez[:, : sub // 64], sub)
+    sx, sz = ophilox.sample_bits(5, 0, sub, code.n, 0.02)
+    assert np.array_equal(ox, sx) and np.array_equal(oz, sz)
+
+
+# ---- hypergraph-product code: syndrome only ---------------------------------------------------
+
+def test_hgp1600_syndromes_golden_and_random(golden):
+    hx, hz = codes.hgp1600()
+    code = SyndromeCode(hx, hz)
+    assert code.device.kernel_name().startswith("tiled-sparse")
+    errs = np.unpackbits(golden["hgp_errs"], axis=1, bitorder="little")[:, :1600]
+    for which, h, key in ((2, hz, "hgp_synd_hz"), (1, hx, "hgp_synd_hx")):
+        want = np.unpackbits(golden[key], axis=1, bitorder="little")[:, :768]
+        assert np.array_equal(code.syndromes(errs, which), want)
+    rng = np.random.default_rng(16)
+    for shots, p in ((1, 0.5), (513, 0.5), (20000, 1e-3)):
+        errs = (rng.random((shots, 1600)) < p).astype(np.uint8)
+        for which, h in ((2, hz), (1, hx)):
+            assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(h, errs))
+
+
+def test_error_paths():
+    code, _ = pair("steane")
+    with pytest.raises(ValueError):
+        code.syndromes(np.zeros((4, 7), dtype=np.uint8), 3)
+    with pytest.raises(ValueError):
+        code.monte_carlo(1.5, 100)
+    with pytest.raises(ValueError):
+        code.monte_carlo(0.1, 128, first_shot=64)
+    hx, hz = codes.hgp1600()
+    with pytest.raises(_native.NativeLibraryError, match="lookup decode covers"):
+        SyndromeCode(hx, hz).device.decode_planes(planes.pack_planes(np.zeros((4, 1600), dtype=np.uint8)), 4, 1)

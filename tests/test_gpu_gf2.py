@@ -1,0 +1,100 @@
+"""GPU parity for K4 (batched GF(2) Gauss-Jordan) through the C ABI, against the oracle and the
+reference's captured outputs."""
+
+import numpy as np
+import pytest
+
+import bin_matrix
+import css_code
+from oracle import gf2 as ogf2
+from quantum_css_codes_b200 import codes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_kat():
+    """test/test_bin_matrix.py:8-20."""
+    mat = np.array([[1, 0, 1, 1, 0, 1, 0], [0, 1, 1, 0, 0, 1, 1], [1, 0, 1, 0, 1, 0, 1]], dtype='int')
+    want = np.array([[1, 0, 1, 0, 1, 0, 1], [0, 1, 1, 0, 0, 1, 1], [0, 0, 0, 1, 1, 1, 1]], dtype='int')
+    got = bin_matrix.reduced_row_echelon_form(mat)
+    assert np.array_equal(got, want) and got.dtype == mat.dtype
+    assert np.array_equal(mat[0], [1, 0, 1, 1, 0, 1, 0])            # input untouched
+
+
+def test_rref_golden(golden):
+    for i in range(int(golden["rref_count"])):
+        got = bin_matrix.reduced_row_echelon_form(golden[f"rref_in_{i}"])
+        assert np.array_equal(got, golden[f"rref_out_{i}"]), i
+    for tag in ("wide", "u8"):
+        got = bin_matrix.reduced_row_echelon_form(golden[f"rref_in_{tag}"])
+        assert got.dtype == golden[f"rref_out_{tag}"].dtype
+        assert np.array_equal(got, golden[f"rref_out_{tag}"])
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 200), (200, 1), (64, 64), (65, 129), (300, 100), (100, 300),
+                                 (512, 1024), (777, 1500)])
+def test_rref_random_shapes(m, n):
+    rng = np.random.default_rng(m * 1000 + n)
+    batch = 3
+    mats = rng.integers(0, 2, size=(batch, m, n), dtype=np.int64)
+    if m > 4:
+        mats[1, m - 1] = mats[1, 0] ^ mats[1, 2]                     # dependent row
+        mats[2, :, n // 3] = 0                                       # zero column
+        mats[2, m // 2] = 0                                          # zero row
+    out, rank, piv = bin_matrix.rref_batched(mats)
+    for b in range(batch):
+        packed, pv = ogf2.rref_packed(ogf2.pack_rows(mats[b].astype(np.uint8)), n)
+        assert np.array_equal(out[b], ogf2.unpack_rows(packed, n)), b
+        assert rank[b] == len(pv)
+        assert np.array_equal(piv[b, : rank[b]], pv) and np.all(piv[b, rank[b]:] == -1)
+
+
+def test_rref_c5_full_size():
+    """BASELINE config 5 shape: random 1024 x 2048 matrices, plus rank-deficient variants."""
+    packed = codes.random_matrices_c5(4).copy()
+    packed[1, 1000] = packed[1, 3] ^ packed[1, 5]
+    packed[2, :, 0] &= ~np.uint64(0xFFFF)                            # 16 zero columns
+    out, rank, piv = bin_matrix.rref_packed_batched(packed, 2048)
+    for b in range(4):
+        want, pv = ogf2.rref_packed(packed[b], 2048)
+        assert np.array_equal(out[b], want), b
+        assert rank[b] == len(pv) and np.array_equal(piv[b, : rank[b]], pv)
+    assert rank[0] == 1024 and rank[1] == 1023
+
+
+def test_rank_nullspace_solve():
+    rng = np.random.default_rng(8)
+    for m, n in [(5, 9), (12, 12), (20, 7), (40, 100), (130, 260)]:
+        a = rng.integers(0, 2, size=(m, n), dtype=np.int64)
+        if m > 3:
+            a[3] = (a[0] + a[1]) % 2
+        r = bin_matrix.rank(a)
+        assert r == ogf2.rank(a)
+        ns = bin_matrix.null_space(a)
+        assert np.array_equal(ns, ogf2.null_space(a))
+        assert not np.any((a @ ns.T) % 2)
+        x0 = rng.integers(0, 2, size=n, dtype=np.int64)
+        b = (a @ x0) % 2
+        x = bin_matrix.solve(a, b)
+        assert np.array_equal(x, ogf2.solve(a, b)) and np.array_equal((a @ x) % 2, b)
+    assert bin_matrix.solve(np.array([[1, 1], [1, 1]]), np.array([0, 1])) is None
+
+
+def test_codes_equal_and_transversal_gates(golden):
+    """css_code.py:182-201, 838-844 through the GPU RREF."""
+    assert css_code.codes_equal(golden["ce_a"], golden["ce_b"]) is True
+    assert css_code.codes_equal(golden["ce_a"], golden["ce_c"]) is False
+    assert css_code.codes_equal(golden["ce_a"], golden["ce_a"][:, :5]) is False
+    for name in ("steane", "qrm15", "golay23"):
+        code = css_code.CSSCode(*[np.array(h) for h in getattr(codes, name)()])
+        assert sorted(code._transversal_gates) == golden[f"{name}_gates"].tolist()
+    steane = css_code.CSSCode(*[np.array(h) for h in codes.steane()])
+    for gate in ('I', 'CNOT', 'H', 'CZ', 'S'):                       # test/test_css_code.py:24-26 ('S' is
+        assert steane.is_transversal(gate)                           # what css_code.py:199 registers)
+    assert not steane.is_transversal('T')
+
+
+def test_bool_rejected_and_empty():
+    with pytest.raises(TypeError):
+        bin_matrix.reduced_row_echelon_form(np.zeros((2, 2), dtype=bool))
+    assert bin_matrix.reduced_row_echelon_form(np.zeros((0, 5), dtype=int)).shape == (0, 5)

@@ -1,0 +1,153 @@
+"""CPU tests of the host-side drop-in surface (no GPU): constructor numerics against the
+reference's captured outputs, error behaviour, bit conventions, and that libqcss.so loads and
+exports every symbol include/qcss.h declares."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bin_matrix
+import css_code
+import errors
+from css_code import CSSCode
+from quantum_css_codes_b200 import codes, planes, _native
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_vec_int_reference_kats():
+    """test/test_bin_matrix.py:22-31."""
+    assert bin_matrix.vec_to_int(np.array([0, 1, 0, 1, 1])) == 11
+    assert np.array_equal(bin_matrix.int_to_vec(11, 5), np.array([0, 1, 0, 1, 1]))
+    with pytest.raises(ValueError, match="n is too small"):
+        bin_matrix.int_to_vec(11, 3)
+    assert isinstance(bin_matrix.vec_to_int(np.array([1, 0], dtype=np.int64)), np.int64)
+
+
+def test_vec_int_golden(golden):
+    for v, k, back in zip(golden["v2i_in"], golden["v2i_out"], golden["i2v_out"]):
+        assert bin_matrix.vec_to_int(v) == k
+        assert np.array_equal(bin_matrix.int_to_vec(int(k), 40), back)
+    assert np.array_equal(np.array(list(bin_matrix.weight_w_vectors(6, 3))), golden["wwv_6_3"])
+    assert np.array_equal(np.array(list(bin_matrix.weight_w_vectors(5, 0))), golden["wwv_5_0"])
+    assert np.array_equal(np.array(list(bin_matrix.weight_w_vectors(4, 4))), golden["wwv_4_4"])
+
+
+@pytest.mark.parametrize("name", ["steane", "qrm15", "golay23"])
+def test_constructor_matches_reference(golden, name):
+    h1, h2 = getattr(codes, name)()
+    code = CSSCode(np.array(h1), np.array(h2))
+    assert [code.n, code.k, code.t, code.r_1, code.r_2] == golden[f"{name}_nkt"].tolist()
+    assert np.array_equal(code.parity_check_c1, golden[f"{name}_h1"])
+    assert np.array_equal(code.parity_check_c2, golden[f"{name}_h2"])
+    assert np.array_equal(code.z_operator_matrix(), golden[f"{name}_lz"])
+    assert np.array_equal(code.x_operator_matrix(), golden[f"{name}_lx"])
+    for tab, tag in ((code._c1_syndromes, "c1"), (code._c2_syndromes, "c2")):
+        assert np.array_equal(np.array([int(k) for k in tab]), golden[f"{name}_{tag}_keys"])
+        assert np.array_equal(np.array(list(tab.values())), golden[f"{name}_{tag}_vals"])
+        assert all(isinstance(k, np.int64) for k in tab)
+        assert all(v.dtype == np.dtype('int') for v in tab.values())
+
+
+def test_steane_like_reference_tests():
+    """test/test_css_code.py:20-22, 28-30, 108-118 (the PauliTerm tests need pyquil)."""
+    steane = CSSCode(*[np.array(h) for h in codes.steane()])
+    for mat, off in ((steane.parity_check_c1, 0), (steane.parity_check_c2, 3)):
+        assert np.array_equal(mat[:, off:off + 3], np.identity(3))
+    t, table = css_code.syndrome_table(steane.parity_check_c1)
+    assert t == 1 and len(table) == 8
+    for s, e in table.items():
+        assert s == bin_matrix.vec_to_int(np.mod(np.matmul(steane.parity_check_c1, e), 2))
+    assert steane.z_operator_matrix().tolist() == [[0, 1, 1, 0, 0, 0, 1]]      # Z1 Z2 Z6
+    assert steane.x_operator_matrix().tolist() == [[0, 0, 0, 1, 1, 0, 1]]      # X3 X4 X6
+
+
+def test_is_doubly_even_reference_kats():
+    base = [[0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1, 0, 1, 1, 0], [1, 1, 1, 0, 0, 0, 0, 1], [1, 1, 1, 1, 1, 1, 1, 1]]
+    assert css_code.is_doubly_even(np.array(base))
+    bad = [r[:] for r in base]; bad[2][0] = 0
+    assert not css_code.is_doubly_even(np.array(bad))
+    bad = [r[:] for r in base]; bad[1][0] = 1
+    assert not css_code.is_doubly_even(np.array(bad))
+
+
+def test_module_functions(golden):
+    h = np.array(codes.hamming_7_4())
+    out, swaps = css_code.normalize_parity_check(h, 0)
+    assert np.array_equal(out, golden["norm_steane_out"])
+    assert np.array_equal(h, golden["norm_steane_mutated"])
+    assert np.array_equal(np.array(swaps).reshape(-1, 2), golden["norm_steane_swaps"])
+    m = np.arange(12).reshape(3, 4)
+    css_code.swap_columns(m, (0, 2))
+    assert m[:, 0].tolist() == [2, 6, 10] and m[:, 2].tolist() == [0, 4, 8]
+
+
+def test_constructor_errors_in_reference_order():
+    h = np.array(codes.hamming_7_4())
+    with pytest.raises(ValueError, match="C_1 and C_2 must have the same code word length"):
+        CSSCode(h, h[:, :6])
+    with pytest.raises(ValueError, match="C_1 parity check matrix must be binary"):
+        CSSCode(h * 2, h)
+    with pytest.raises(ValueError, match="C_2 parity check matrix must be binary"):
+        CSSCode(h, h + 2)
+    bad = h.copy(); bad[0, 0] = 1
+    with pytest.raises(ValueError, match="C_2 dual code must be a subspace of C_1"):
+        CSSCode(h, bad)
+    with pytest.raises(ValueError, match="not enough columns"):
+        css_code.normalize_parity_check(np.ones((3, 2), dtype='int'), 0)
+    with pytest.raises(errors.InvalidCodeError, match="rows are not independent"):
+        css_code.normalize_parity_check(np.array([[1, 1, 0], [1, 1, 0]]), 0)
+    # k != 1 is only rejected after all the tables are built (css_code.py:69-75)
+    four = np.array([[1, 1, 1, 1]])                                   # the [[4,2,2]] code: k = 2
+    with pytest.raises(errors.InvalidCodeError, match="single logical qubit"):
+        CSSCode(four, four)
+    hx, hz = codes.hgp1600()
+    with pytest.raises(errors.InvalidCodeError):
+        CSSCode(hx, hz)
+
+
+def test_plane_packing_roundtrip():
+    rng = np.random.default_rng(0)
+    for shots, n in ((1, 3), (64, 7), (65, 23), (1000, 40)):
+        v = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+        p = planes.pack_planes(v)
+        assert p.shape == (n, planes.stride_words(shots)) and p.shape[1] % 8 == 0
+        assert np.array_equal(planes.unpack_planes(p, shots), v)
+        assert (int(p[0, 0]) >> 0) & 1 == v[0, 0]                      # shot 0 is bit 0 of word 0
+    assert planes.pack_planes(np.array([[0], [1], [1]]))[0, 0] == 6
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "qcss.h")).read()
+    declared = set(re.findall(r"QCSS_API\s+(?:const\s+char\*|int)\s+(qcss_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+    lib = _native.load()                                               # builds nothing: must exist
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.qcss_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a device every numeric entry point fails loudly instead of computing on the host."""
+    from conftest import has_cuda
+    if has_cuda():
+        pytest.skip("GPU present")
+    steane = CSSCode(*[np.array(h) for h in codes.steane()])
+    with pytest.raises(_native.NativeLibraryError):
+        steane.syndromes(np.zeros((2, 7), dtype=np.uint8), 1)
+    with pytest.raises(_native.NativeLibraryError):
+        bin_matrix.reduced_row_echelon_form(np.eye(3, dtype=int))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "quantum_css_codes_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+    for f in ("bin_matrix.py", "css_code.py", "errors.py"):
+        assert "oracle" not in open(os.path.join(REPO, f)).read()

@@ -1,0 +1,177 @@
+"""CPU checks of the CUDA kernels' per-thread code through the host emulation (tests/hostemu):
+the same __host__ __device__ functions the sm_100a kernels call, run sequentially on the host and
+compared bit-for-bit with the oracle.  The GPU parity tests proper are in test_gpu_*.py."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu
+from oracle import css as ocss, montecarlo as omc, philox as ophilox
+from quantum_css_codes_b200 import codes, planes
+
+NAMED = {"steane": 0, "qrm15": 1, "golay23": 2}
+
+
+def build(name):
+    code = ocss.build_css(*[np.array(h) for h in getattr(codes, name)()])
+    sx = emu.Side(code.parity_check_c2, code.lz[0], code.c2_syndromes)
+    sz = emu.Side(code.parity_check_c1, code.lx[0], code.c1_syndromes)
+    return code, sx, sz
+
+
+def test_transpose32():
+    rng = np.random.default_rng(1)
+    w = rng.integers(0, 1 << 32, size=32, dtype=np.uint64).astype(np.uint32)
+    bits = ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.uint8)   # [i][k]
+    out = w.copy()
+    emu.lib().emu_transpose32(out.ctypes.data_as(ctypes.c_void_p))
+    obits = ((out[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.uint8)
+    assert np.array_equal(obits, bits.T)
+
+
+def test_philox_kat():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c = np.array(ctr, dtype=np.uint32); k = np.array(key, dtype=np.uint32); o = np.zeros(4, dtype=np.uint32)
+        emu.lib().emu_philox(c.ctypes.data_as(ctypes.c_void_p), k.ctypes.data_as(ctypes.c_void_p),
+                             o.ctypes.data_as(ctypes.c_void_p))
+        assert tuple(int(v) for v in o) == want
+        assert tuple(int(v) for v in ophilox.philox4x32_10(c, k)) == want
+
+
+def test_named_descriptors_match_reference_matrices(golden):
+    """The compiled-in descriptors are the reference's normalised matrices (golden fixtures)."""
+    for name, idx in NAMED.items():
+        for which_x, hkey, lkey in ((1, "h2", "lz"), (0, "h1", "lx")):
+            n, m, l = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint32()
+            rows = (ctypes.c_uint32 * 16)()
+            assert emu.lib().emu_named_side(idx, which_x, ctypes.byref(n), ctypes.byref(m), rows, ctypes.byref(l)) == 0
+            h = golden[f"{name}_{hkey}"]
+            assert (n.value, m.value) == (h.shape[1], h.shape[0])
+            for t in range(m.value):
+                assert rows[t] == sum(int(b) << j for j, b in enumerate(h[m.value - 1 - t]))
+            assert l.value == sum(int(b) << j for j, b in enumerate(golden[f"{name}_{lkey}"][0]))
+
+
+def check_against_oracle(code, sx, sz, ex, ez, named_id):
+    shots = ex.shape[0]
+    got = emu.decode(sx, sz, planes.pack_planes(ex), planes.pack_planes(ez), shots, named_id,
+                     want=("synd", "corr", "flip", "miss"))
+    for tag, which, errs in (("x", 2, ex), ("z", 1, ez)):
+        h, table, lop = ocss.pauli_side(code, which)
+        want = omc.decode_batch(h, table, lop, errs)
+        assert np.array_equal(planes.unpack_planes(got["synd_" + tag], shots), want["synd"]), tag
+        assert np.array_equal(planes.unpack_planes(got["corr_" + tag], shots), want["corr"]), tag
+        assert np.array_equal(planes.unpack_plane(got["flip_" + tag], shots), want["flip"]), tag
+        assert np.array_equal(planes.unpack_plane(got["miss_" + tag], shots), want["miss"]), tag
+    assert got["tally"] == omc.tally_xz(code, ex, ez)
+    # padding bits of every output plane stay zero
+    for key, val in got.items():
+        if key != "tally":
+            bits = np.unpackbits(np.atleast_2d(val).view(np.uint8), axis=1, bitorder="little")
+            assert not bits[:, shots:].any(), key
+
+
+@pytest.mark.parametrize("name", list(NAMED))
+@pytest.mark.parametrize("static", [True, False])
+@pytest.mark.parametrize("shots", [1, 31, 128, 1000])
+def test_decode_random_batches(name, static, shots):
+    code, sx, sz = build(name)
+    rng = np.random.default_rng(shots * 7 + len(name))
+    ex = (rng.random((shots, code.n)) < 0.15).astype(np.uint8)
+    ez = (rng.random((shots, code.n)) < 0.15).astype(np.uint8)
+    ex[0] = 0
+    ez[-1] = 1
+    check_against_oracle(code, sx, sz, ex, ez, NAMED[name] if static else -1)
+
+
+@pytest.mark.parametrize("name", list(NAMED))
+def test_weight_le_1_errors_decode_to_zero_residual(name):
+    """BASELINE config 1: every weight <= 1 X/Z error is corrected with no logical flip."""
+    code, sx, sz = build(name)
+    errs = np.vstack([np.zeros((1, code.n), dtype=np.uint8), np.eye(code.n, dtype=np.uint8)])
+    got = emu.decode(sx, sz, planes.pack_planes(errs), planes.pack_planes(errs), len(errs), NAMED[name],
+                     want=("corr", "flip", "miss"))
+    assert np.array_equal(planes.unpack_planes(got["corr_x"], len(errs)), errs)
+    assert np.array_equal(planes.unpack_planes(got["corr_z"], len(errs)), errs)
+    assert got["tally"] == dict(shots=len(errs), fail_x=0, fail_z=0, fail_any=0, miss_x=0, miss_z=0)
+
+
+@pytest.mark.parametrize("name,static", [("steane", True), ("steane", False), ("qrm15", True), ("qrm15", False)])
+def test_exhaustive_enumerators(name, static):
+    """All 2^n patterns of each Pauli type: failure counts equal SURVEY A.4."""
+    code, sx, sz = build(name)
+    pats = omc.all_patterns(code.n)
+    got = emu.decode(sx, sz, planes.pack_planes(pats), planes.pack_planes(pats), len(pats),
+                     NAMED[name] if static else -1)
+    want = omc.tally_xz(code, pats, pats)
+    assert got["tally"] == want
+    if name == "steane":
+        assert want["fail_x"] == 64 and want["fail_z"] == 64
+    else:
+        assert want["fail_x"] == 16384 and want["miss_x"] == 14336 and want["fail_z"] == 16384
+
+
+def test_golay_sample_of_patterns():
+    code, sx, sz = build("golay23")
+    rng = np.random.default_rng(23)
+    idx = rng.integers(0, 1 << 23, size=20000)
+    pats = ((idx[:, None] >> np.arange(23)[None, :]) & 1).astype(np.uint8)
+    check_against_oracle(code, sx, sz, pats, pats[::-1].copy(), NAMED["golay23"])
+    check_against_oracle(code, sx, sz, pats, pats[::-1].copy(), -1)
+
+
+@pytest.mark.parametrize("n,m1,m2", [(5, 2, 2), (12, 5, 4), (16, 8, 7), (20, 3, 12), (32, 16, 9), (9, 6, 1)])
+def test_generic_random_codes_with_partial_tables(n, m1, m2):
+    """Synthetic (H, L, table) triples, tables covering a random subset of the keys (misses)."""
+    rng = np.random.default_rng(n * 100 + m1)
+    sides = {}
+    for which, m in ((1, m1), (2, m2)):
+        h = rng.integers(0, 2, size=(m, n))
+        lrow = rng.integers(0, 2, size=n)
+        keys = rng.permutation(1 << m)[: max(1, (1 << m) * 2 // 3)]
+        table = {int(k): rng.integers(0, 2, size=n) for k in keys}
+        sides[which] = (h, table, lrow[None, :])
+    sx = emu.Side(sides[2][0], sides[2][2][0], sides[2][1])
+    sz = emu.Side(sides[1][0], sides[1][2][0], sides[1][1])
+    shots = 777
+    ex = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+    ez = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+    got = emu.decode(sx, sz, planes.pack_planes(ex), planes.pack_planes(ez), shots, -1,
+                     want=("synd", "corr", "flip", "miss"))
+    for tag, which, errs in (("x", 2, ex), ("z", 1, ez)):
+        want = omc.decode_batch(*sides[which], errs)
+        assert np.array_equal(planes.unpack_planes(got["synd_" + tag], shots), want["synd"])
+        assert np.array_equal(planes.unpack_planes(got["corr_" + tag], shots), want["corr"])
+        assert np.array_equal(planes.unpack_plane(got["flip_" + tag], shots), want["flip"])
+        assert np.array_equal(planes.unpack_plane(got["miss_" + tag], shots), want["miss"])
+
+
+@pytest.mark.parametrize("name", ["steane", "golay23"])
+@pytest.mark.parametrize("p", [1e-3, 0.05, 0.5, 0.0, 1.0])
+def test_fused_sampler_bit_exact(name, p):
+    """The fused sampler draws exactly the oracle sampler's bits and tallies them like the oracle."""
+    code, sx, sz = build(name)
+    shots, seed, first = 4000, 0x5EED1234ABCD, 128 * 7
+    thr = ophilox.threshold(p)
+    got = emu.decode(sx, sz, shots=shots, named_id=NAMED[name], sample=dict(seed=seed, first_shot=first, thr=thr))
+    ex, ez = ophilox.sample_bits(seed, first, shots, code.n, p)
+    assert np.array_equal(planes.unpack_planes(got["ex"], shots), ex)
+    assert np.array_equal(planes.unpack_planes(got["ez"], shots), ez)
+    assert got["tally"] == omc.tally_xz(code, ex, ez)
+    if p == 0.0:
+        assert not ex.any() and not ez.any()
+
+
+def test_sampler_statistics():
+    """Per-qubit X/Y/Z frequencies of the oracle sampler (which the kernel matches bit-for-bit)."""
+    p, shots = 0.3, 400000
+    ex, ez = ophilox.sample_bits(99, 0, shots, 3, p)
+    for freq in (np.mean(ex & ~ez & 1), np.mean(ez & ~ex & 1), np.mean(ex & ez)):
+        assert abs(freq - p / 3) < 5 * np.sqrt(p / 3 * (1 - p / 3) / (3 * shots))

@@ -87,7 +87,7 @@ PROTOTYPES = {
     "qcss_gf2_rref": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p, _c_i32p, _c_i32p]),
     "qcss_gf2_rref_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None

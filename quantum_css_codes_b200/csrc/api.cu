@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -64,7 +65,7 @@ struct qcss_code {
     uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
     uint32_t lmask_x = 0, lmask_z = 0;
     int named_id = -1;
-    DevBuf fm_x, fm_z, co_x, co_z;      // lookup tables
+    DevBuf fm_x, fm_z, co_x, co_z, e32_x, e32_z;      // lookup tables
     SparseRows sp1{}, sp2{};            // CSR of H1 / H2 for the tiled kernel
     DevBuf sp1_ptr, sp1_cols, sp2_ptr, sp2_cols;
     // host-buffer paths
@@ -94,7 +95,7 @@ int check_planes(const void* p, int64_t stride, int64_t shots, const char* what)
 // Build one side: masks, logical row, dense tables.
 int build_side(qcss_code* c, GenericSide& s, uint32_t* rows, uint32_t& lmask, int m, const uint8_t* H,
                const uint8_t* L, int64_t nk, const int64_t* keys, const uint8_t* corr, DevBuf& d_fm,
-               DevBuf& d_co) {
+               DevBuf& d_co, DevBuf& d_e32) {
     const int n = c->n;
     memset(&s, 0, sizeof(s));
     s.n = n;
@@ -141,6 +142,14 @@ int build_side(qcss_code* c, GenericSide& s, uint32_t* rows, uint32_t& lmask, in
     QCSS_CUDA(cudaMemcpy(d_co.p, co.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
     s.lut_fm = (const uint8_t*)d_fm.p;
     s.lut_corr = (const uint32_t*)d_co.p;
+    if (m > kSlicedM && m <= kMaxE32M) {
+        std::vector<uint32_t> e32(size);
+        for (size_t k = 0; k < size; ++k)
+            e32[k] = ((fm[k] & 1) ? 0x0000FFFFu : 0u) | ((fm[k] & 2) ? 0xFFFF0000u : 0u);
+        QCSS_CUDA(d_e32.reserve(size * sizeof(uint32_t)));
+        QCSS_CUDA(cudaMemcpy(d_e32.p, e32.data(), size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        s.lut_e32 = (const uint32_t*)d_e32.p;
+    }
     return QCSS_OK;
 }
 
@@ -363,9 +372,11 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
     c->small = (n <= kMaxN && m1 <= kMaxM && m2 <= kMaxM);
     int rc = QCSS_OK;
     if (c->small) {
-        rc = build_side(c, c->side_x, c->rows_x, c->lmask_x, m2, H2, Lz, n2, keys2, corr2, c->fm_x, c->co_x);
-        if (!rc) rc = build_side(c, c->side_z, c->rows_z, c->lmask_z, m1, H1, Lx, n1, keys1, corr1, c->fm_z, c->co_z);
+        rc = build_side(c, c->side_x, c->rows_x, c->lmask_x, m2, H2, Lz, n2, keys2, corr2, c->fm_x, c->co_x, c->e32_x);
+        if (!rc) rc = build_side(c, c->side_z, c->rows_z, c->lmask_z, m1, H1, Lx, n1, keys1, corr1, c->fm_z, c->co_z, c->e32_z);
         if (!rc) c->named_id = match_named(c->side_x, c->rows_x, c->lmask_x, c->side_z, c->rows_z, c->lmask_z);
+        // debugging / benchmarking knob: force the generic (runtime-H) kernels
+        if (getenv("QCSS_DISABLE_NAMED") != nullptr) c->named_id = -1;
     } else if ((keys1 && n1 > 0) || (keys2 && n2 > 0)) {
         // tables are accepted but unusable: decode entry points will report UNSUPPORTED
     }
@@ -382,6 +393,7 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
 QCSS_API int qcss_code_destroy(qcss_code* c) {
     if (!c) return QCSS_OK;
     c->fm_x.release(); c->fm_z.release(); c->co_x.release(); c->co_z.release();
+    c->e32_x.release(); c->e32_z.release();
     c->sp1_ptr.release(); c->sp1_cols.release(); c->sp2_ptr.release(); c->sp2_cols.release();
     for (int i = 0; i < kSlots; ++i) {
         c->slot_x[i].release();

@@ -21,6 +21,8 @@ namespace qcss {
 constexpr int kMaxN = 32;        // register-resident ("small code") kernels: n <= 32 qubits
 constexpr int kMaxM = 16;        // lookup decode: m <= 16 syndrome bits (table in shared memory)
 constexpr int kSlicedM = 5;      // fully bit-sliced decode when m <= 5
+constexpr int kMaxE32M = 13;     // tally kernels use 32-bit table entries (4 * 2^m bytes of smem)
+constexpr int kSparseMax = 3;    // <= this many non-zero syndromes per word: walk them one by one
 
 enum Mode : int32_t { kModeNone = 0, kModeSliced = 1, kModeLut = 2 };
 
@@ -34,6 +36,8 @@ struct GenericSide {
     uint32_t tt_corr[kMaxN];              // sliced mode: correction truth table of qubit j
     const uint8_t* lut_fm;                // lut mode: [2^m] bytes, bit0 = L.corr parity, bit1 = miss
     const uint32_t* lut_corr;             // lut mode: [2^m] correction bit masks (bit j = qubit j)
+    const uint32_t* lut_e32;              // lut mode, m <= kMaxE32M: [2^m] words, low half all-ones when
+                                          // L.corr is odd, high half all-ones on a miss (tally kernels)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -192,6 +196,104 @@ QCSS_HD void lut_flip_miss(uint32_t (&s)[MB], int has_miss, LutRead rd, uint32_t
             if (has_miss) miss |= ((ent >> 1) & 1u) << (b * MB + j);
         }
     }
+}
+
+// ---- tally-only lookup (FAST kernels), m <= kMaxE32M ------------------------------------------------
+QCSS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
+}
+
+QCSS_HD int ffs32(uint32_t v) {       // index of the lowest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+// True when `pred` holds for any lane of the warp (host emulation: for this thread).
+QCSS_HD bool warp_any(bool pred) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), pred) != 0;
+#else
+    return pred;
+#endif
+}
+
+// 16x16 transpose of both halves of 16 words; the distance-8 stage is two byte permutes per pair.
+QCSS_HD void transpose16(uint32_t (&w)[16]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t a = w[j], b = w[j + 8];
+        w[j] = prmt(a, b, 0x6240u);
+        w[j + 8] = prmt(a, b, 0x7351u);
+    }
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) {
+        const uint32_t mk = d == 4 ? 0x0F0F0F0Fu : (d == 2 ? 0x33333333u : 0x55555555u);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if ((j & d) == 0) {
+                const uint32_t a = w[j], b = w[j + d];
+                const uint32_t t = ((a >> d) ^ b) & mk;
+                w[j + d] = b ^ t;
+                w[j] = a ^ (t << d);
+            }
+        }
+    }
+}
+
+// Flip / miss words of one 32-shot word from the key planes s[0..M) (key-bit order), M <= 13.
+// rd32(byte_offset) reads the 32-bit entry at key = byte_offset / 4.  Two warp-uniform paths:
+//   sparse: at most kSparseMax shots of every lane have a non-zero syndrome (the usual case at
+//           physical error rates ~1e-3): gather each such shot's key bit by bit, one lookup each;
+//   dense : planes are placed two bit positions up so the 16x16 transpose yields key*4 directly,
+//           then 32 lookups whose all-ones entries are masked into place with one LOP3 each.
+template <int M, class Rd32>
+QCSS_HD void lut_tally_word(const uint32_t (&s)[M], bool has_miss, Rd32 rd32, uint32_t& fc, uint32_t& miss) {
+    static_assert(M <= kMaxE32M, "32-bit entry table needs m <= 13");
+    uint32_t nz = 0u;
+#pragma unroll
+    for (int t = 0; t < M; ++t) nz |= s[t];
+    const bool dense = warp_any(popc32(nz) > (uint32_t)kSparseMax);
+    if (!dense) {
+        const uint32_t e0 = rd32(0u);                   // every zero-syndrome shot shares key 0
+        fc = (e0 & 1u) ? ~nz : 0u;
+        miss = (e0 >> 16) ? ~nz : 0u;
+        while (nz != 0u) {
+            const int k = ffs32(nz);
+            nz &= nz - 1u;
+            uint32_t key4 = 0u;
+#pragma unroll
+            for (int t = M - 1; t >= 0; --t) key4 = (key4 << 1) | ((s[t] >> k) & 1u);
+            const uint32_t e = rd32(key4 << 2);
+            fc |= (e & 1u) << k;
+            miss |= (e >> 31) << k;
+        }
+        if (!has_miss) miss = 0u;
+        return;
+    }
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) w[t] = (t >= 2 && t - 2 < M) ? s[t - 2] : 0u;
+    transpose16(w);
+    uint32_t acc_lo = 0u, acc_hi = 0u;      // shots 0..15 / 16..31: low half flips, high half misses
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t e_lo = rd32(w[j] & 0xFFFFu);
+        const uint32_t e_hi = rd32(w[j] >> 16);
+        acc_lo |= e_lo & (0x00010001u << j);
+        acc_hi |= e_hi & (0x00010001u << j);
+    }
+    fc = prmt(acc_lo, acc_hi, 0x5410u);
+    miss = has_miss ? prmt(acc_lo, acc_hi, 0x7632u) : 0u;
 }
 
 // Same walk, but fetching the n-bit correction of every shot and re-slicing it into planes.

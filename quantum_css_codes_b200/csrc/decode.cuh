@@ -71,6 +71,25 @@ QCSS_HD void store_words(uint32_t* p, const uint32_t (&in)[VEC]) {
 #endif
 }
 
+// ---- lookup tables of one side as the kernels see them ------------------------------------------
+// fm / e32 point to shared memory on the device (staged by run_small), corr to global memory.
+struct SideLut {
+    const uint8_t* fm;        // [2^m] bytes: bit0 = L.corr parity, bit1 = miss
+    const uint32_t* corr;     // [2^m] correction masks
+    const uint8_t* e32;       // [2^m] 32-bit entries addressed by byte offset (tally kernels)
+    QCSS_HD uint32_t read_fm(uint32_t k) const { return (uint32_t)fm[k]; }
+    QCSS_HD uint32_t read_corr(uint32_t k) const {
+#if defined(__CUDA_ARCH__)
+        return __ldg(corr + k);
+#else
+        return corr[k];
+#endif
+    }
+    QCSS_HD uint32_t read_e32(uint32_t byte_off) const {
+        return *reinterpret_cast<const uint32_t*>(e32 + byte_off);
+    }
+};
+
 // ---- side policies ----------------------------------------------------------------------------
 // Generic: H, L and truth tables are runtime data (kernel parameters -> constant bank operands).
 //   MB == kSlicedM : fully bit-sliced decode (m <= 5)
@@ -79,7 +98,9 @@ template <int NB_, int MB_>
 struct GenericPolicy {
     static constexpr int NB = NB_, MB = MB_;
     static constexpr bool kSliced = (MB_ == kSlicedM);
+    static constexpr int kTallyM = kSliced ? 0 : (MB_ < kMaxE32M ? MB_ : kMaxE32M);   // lut_tally_word width
     const GenericSide* p;
+    QCSS_HD bool use_e32() const { return p->lut_e32 != nullptr; }
     QCSS_HD int n() const { return p->n; }
     QCSS_HD int m() const { return p->m; }
     QCSS_HD bool has_table() const { return p->mode != kModeNone; }
@@ -100,6 +121,8 @@ template <class D>
 struct StaticPolicy {
     static constexpr int NB = D::N, MB = D::MB;
     static constexpr bool kSliced = D::kSliced;
+    static constexpr int kTallyM = (!D::kSliced && D::M <= kMaxE32M) ? D::M : 0;
+    QCSS_HD bool use_e32() const { return kTallyM > 0; }
     QCSS_HD int n() const { return D::N; }
     QCSS_HD int m() const { return D::M; }
     QCSS_HD bool has_table() const { return true; }
@@ -116,58 +139,81 @@ struct StaticPolicy {
 };
 
 // ---- finish one word of one side ---------------------------------------------------------------
-template <class P, class LutFm, class LutCorr>
-QCSS_HD WordOut finish_side(const P& pol, uint32_t (&s)[P::MB], uint32_t le, LutFm lut_fm,
-                            LutCorr lut_corr, uint32_t* synd, int64_t s_stride, uint32_t* corr,
+// FAST = tally-only instantiation: no optional output planes, every bit of the word valid.
+template <bool FAST, class P>
+QCSS_HD WordOut finish_side(const P& pol, uint32_t (&s)[P::MB], uint32_t le, const SideLut& lut,
+                            uint32_t* synd, int64_t s_stride, uint32_t* corr,
                             int64_t c_stride, uint32_t* flip_p, uint32_t* miss_p, int64_t w,
                             uint32_t valid) {
     constexpr int MB = P::MB;
     const int m = pol.m(), n = pol.n();
     const bool in_range = valid != 0u;
-    if (synd != nullptr && in_range) {
+    if constexpr (!FAST) {
+        if (synd != nullptr && in_range) {
 #pragma unroll
-        for (int t = 0; t < MB; ++t)
-            if (t < m) synd[(int64_t)(m - 1 - t) * s_stride + w] = s[t] & valid;
+            for (int t = 0; t < MB; ++t)
+                if (t < m) synd[(int64_t)(m - 1 - t) * s_stride + w] = s[t] & valid;
+        }
     }
     WordOut o;
     o.flip = 0u;
     o.miss = 0u;
-    if (!pol.has_table()) return o;
+    if constexpr (!FAST) {
+        if (!pol.has_table()) return o;
+    }
     uint32_t fc = 0u;
     if constexpr (P::kSliced) {
         fc = eval_truth_table<MB>(s, pol.tt_flip());
         if (pol.has_miss()) o.miss = eval_truth_table<MB>(s, pol.tt_miss());
-        if (corr != nullptr && in_range) {
+        if constexpr (!FAST) {
+            if (corr != nullptr && in_range) {
 #pragma unroll
-            for (int j = 0; j < P::NB; ++j)
-                if (j < n)
-                    corr[(int64_t)j * c_stride + w] = eval_truth_table<MB>(s, pol.tt_corr(j)) & valid;
+                for (int j = 0; j < P::NB; ++j)
+                    if (j < n)
+                        corr[(int64_t)j * c_stride + w] = eval_truth_table<MB>(s, pol.tt_corr(j)) & valid;
+            }
         }
     } else {
-        lut_flip_miss<MB>(s, pol.has_miss() ? 1 : 0, lut_fm, fc, o.miss);
-        if (corr != nullptr && in_range) {
-            uint32_t planes[32];
-            lut_corrections<MB>(s, lut_corr, planes);
+        bool done = false;
+        if constexpr (FAST && P::kTallyM > 0) {
+            if (pol.use_e32()) {
+                lut_tally_word<P::kTallyM>(reinterpret_cast<const uint32_t(&)[P::kTallyM]>(s), pol.has_miss(),
+                                           [&lut](uint32_t off) { return lut.read_e32(off); }, fc, o.miss);
+                done = true;
+            }
+        }
+        if (!done)
+            lut_flip_miss<MB>(s, pol.has_miss() ? 1 : 0, [&lut](uint32_t k) { return lut.read_fm(k); }, fc,
+                              o.miss);
+        if constexpr (!FAST) {
+            if (corr != nullptr && in_range) {
+                uint32_t planes[32];
+                lut_corrections<MB>(s, [&lut](uint32_t k) { return lut.read_corr(k); }, planes);
 #pragma unroll
-            for (int j = 0; j < P::NB; ++j)
-                if (j < n) corr[(int64_t)j * c_stride + w] = planes[j] & valid;
+                for (int j = 0; j < P::NB; ++j)
+                    if (j < n) corr[(int64_t)j * c_stride + w] = planes[j] & valid;
+            }
         }
     }
     o.flip = le ^ fc;
-    if (flip_p != nullptr && in_range) flip_p[w] = o.flip & valid;
-    if (miss_p != nullptr && in_range) miss_p[w] = o.miss & valid;
+    if constexpr (!FAST) {
+        if (flip_p != nullptr && in_range) flip_p[w] = o.flip & valid;
+        if (miss_p != nullptr && in_range) miss_p[w] = o.miss & valid;
+    }
     return o;
 }
 
 // ---- one unit: VEC consecutive words of both sides -------------------------------------------
-template <class PX, class PZ, int VEC, bool SAMPLE, class LutFmX, class LutCorrX, class LutFmZ,
-          class LutCorrZ>
+// FAST units are the hot path of the Monte-Carlo tallies: both Pauli types present, all VEC words
+// fully inside the batch, nothing written but the counters.  Everything else (single-side calls,
+// output planes, the ragged tail of a batch) goes through the FAST = false instantiation.
+template <class PX, class PZ, int VEC, bool SAMPLE, bool FAST>
 QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_t unit,
-                          LutFmX fm_x, LutCorrX co_x, LutFmZ fm_z, LutCorrZ co_z, Counters& c) {
+                          const SideLut& lut_x, const SideLut& lut_z, Counters& c) {
     static_assert(PX::NB == PZ::NB, "sides share the qubit count");
     constexpr int NB = PX::NB;
     const int64_t w0 = unit * VEC;
-    const bool do_x = SAMPLE || (io.sides & 1), do_z = SAMPLE || (io.sides & 2);
+    const bool do_x = FAST || SAMPLE || (io.sides & 1), do_z = FAST || SAMPLE || (io.sides & 2);
     uint32_t sx[VEC][PX::MB], sz[VEC][PZ::MB], lex[VEC], lez[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -179,6 +225,8 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
         lez[v] = 0u;
     }
     const int n = px.n();
+    const uint32_t* ex_ptr = io.ex + w0;
+    const uint32_t* ez_ptr = io.ez + w0;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
         if (j < n) {
@@ -188,13 +236,15 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
                 for (int v = 0; v < VEC; ++v)
                     sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
                                      xe[v], ze[v]);
-                if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xe);
-                if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, ze);
+                if constexpr (!FAST) {
+                    if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xe);
+                    if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, ze);
+                }
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { xe[v] = 0u; ze[v] = 0u; }
-                if (do_x) load_words<VEC>(io.ex + (int64_t)j * io.e_stride + w0, xe);
-                if (do_z) load_words<VEC>(io.ez + (int64_t)j * io.e_stride + w0, ze);
+                if (do_x) load_words<VEC>(ex_ptr + (int64_t)j * io.e_stride, xe);
+                if (do_z) load_words<VEC>(ez_ptr + (int64_t)j * io.e_stride, ze);
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -206,16 +256,19 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         const int64_t w = w0 + v;
-        const bool in_range = w < io.words;
-        const uint32_t valid = in_range ? ((w == io.words - 1) ? io.tail_mask : 0xFFFFFFFFu) : 0u;
+        uint32_t valid = 0xFFFFFFFFu;
+        if constexpr (!FAST) {
+            const bool in_range = w < io.words;
+            valid = in_range ? ((w == io.words - 1) ? io.tail_mask : 0xFFFFFFFFu) : 0u;
+        }
         WordOut ox, oz;
         ox.flip = ox.miss = oz.flip = oz.miss = 0u;
         if (do_x)
-            ox = finish_side(px, sx[v], lex[v], fm_x, co_x, io.synd_x, io.s_stride, io.corr_x,
-                             io.c_stride, io.flip_x, io.miss_x, w, valid);
+            ox = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x,
+                                   io.c_stride, io.flip_x, io.miss_x, w, valid);
         if (do_z)
-            oz = finish_side(pz, sz[v], lez[v], fm_z, co_z, io.synd_z, io.s_stride, io.corr_z,
-                             io.c_stride, io.flip_z, io.miss_z, w, valid);
+            oz = finish_side<FAST>(pz, sz[v], lez[v], lut_z, io.synd_z, io.s_stride, io.corr_z,
+                                   io.c_stride, io.flip_z, io.miss_z, w, valid);
         c.fail_x += popc32(ox.flip & valid);
         c.fail_z += popc32(oz.flip & valid);
         c.fail_any += popc32((ox.flip | oz.flip) & valid);

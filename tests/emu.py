@@ -21,7 +21,7 @@ class GenericSide(ctypes.Structure):
                 ("has_miss", ctypes.c_int32), ("tt_flip", ctypes.c_uint32), ("tt_miss", ctypes.c_uint32),
                 ("lexp", ctypes.c_uint32 * MAX_N), ("mask", (ctypes.c_uint32 * MAX_N) * MAX_M),
                 ("tt_corr", ctypes.c_uint32 * MAX_N),
-                ("lut_fm", ctypes.c_void_p), ("lut_corr", ctypes.c_void_p)]
+                ("lut_fm", ctypes.c_void_p), ("lut_corr", ctypes.c_void_p), ("lut_e32", ctypes.c_void_p)]
 
 
 class DecodeIO(ctypes.Structure):
@@ -95,12 +95,15 @@ class Side:
                         s.tt_corr[j] |= ((int(self.co[k]) >> j) & 1) << k
             s.lut_fm = self.fm.ctypes.data
             s.lut_corr = self.co.ctypes.data
+            if 5 < m <= 13:
+                self.e32 = (np.where(self.fm & 1, 0x0000FFFF, 0) | np.where(self.fm & 2, 0xFFFF0000, 0)).astype(np.uint32)
+                s.lut_e32 = self.e32.ctypes.data
         self.c = s
         self.n, self.m = n, m
 
 
 def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1, want=(),
-           sample=None):
+           sample=None, fast=False):
     """Run the emulated kernel.  ex/ez planes: (n, stride) uint64.  want: subset of
     {'synd', 'corr', 'flip', 'miss'}.  sample: dict(seed, first_shot, p_thr) for the fused sampler.
     Returns dict with tally and requested planes."""
@@ -146,6 +149,10 @@ def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1,
                 out[f"{name}_{tag}"] = np.zeros(stride, dtype=np.uint64)
                 setattr(io, f"{name}_{tag}", out[f"{name}_{tag}"].ctypes.data)
     tally = np.zeros(6, dtype=np.uint64)
+    if fast:
+        assert shots % 128 == 0 and not want and io.sides == 3
+        io.ex_out = io.ez_out = None
+    L.emu_set_fast(int(fast))
     rc = L.emu_decode(ctypes.byref(side_x.c), ctypes.byref(side_z.c), ctypes.byref(io), named_id,
                       int(sample is not None), tally.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
     assert rc == 0

@@ -13,17 +13,21 @@ using namespace qcss;
 
 namespace {
 
+bool g_fast = false;
+
 template <class PX, class PZ, int VEC, bool SAMPLE>
-void run(const PX& px, const PZ& pz, const DecodeIO& io, const uint8_t* fmx, const uint32_t* cox,
-         const uint8_t* fmz, const uint32_t* coz, uint64_t* tally) {
-    auto fm_x = [fmx](uint32_t k) { return (uint32_t)fmx[k]; };
-    auto fm_z = [fmz](uint32_t k) { return (uint32_t)fmz[k]; };
-    auto co_x = [cox](uint32_t k) { return cox[k]; };
-    auto co_z = [coz](uint32_t k) { return coz[k]; };
+void run(const PX& px, const PZ& pz, const DecodeIO& io, const GenericSide* gx, const GenericSide* gz,
+         uint64_t* tally) {
+    // FAST instantiation when the caller asks for tallies only over whole units (mirrors
+    // small_common.cuh::launch_split for the part of the batch the FAST kernel would get)
+    const bool fast = g_fast;
+    const SideLut lut_x{gx->lut_fm, gx->lut_corr, (const uint8_t*)gx->lut_e32};
+    const SideLut lut_z{gz->lut_fm, gz->lut_corr, (const uint8_t*)gz->lut_e32};
     const int64_t units = (io.words + VEC - 1) / VEC;
     for (int64_t u = 0; u < units; ++u) {
         Counters c = {0, 0, 0, 0, 0};
-        process_unit<PX, PZ, VEC, SAMPLE>(px, pz, io, u, fm_x, co_x, fm_z, co_z, c);
+        if (fast) process_unit<PX, PZ, VEC, SAMPLE, true>(px, pz, io, u, lut_x, lut_z, c);
+        else process_unit<PX, PZ, VEC, SAMPLE, false>(px, pz, io, u, lut_x, lut_z, c);
         tally[1] += c.fail_x; tally[2] += c.fail_z; tally[3] += c.fail_any;
         tally[4] += c.miss_x; tally[5] += c.miss_z;
     }
@@ -32,16 +36,16 @@ void run(const PX& px, const PZ& pz, const DecodeIO& io, const uint8_t* fmx, con
 template <int NB, int MB, int VEC>
 void run_generic(const GenericSide* x, const GenericSide* z, const DecodeIO& io, int sample, uint64_t* tally) {
     GenericPolicy<NB, MB> px{x}, pz{z};
-    if (sample) run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, true>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
-    else run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, false>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+    if (sample) run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, true>(px, pz, io, x, z, tally);
+    else run<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, false>(px, pz, io, x, z, tally);
 }
 
 template <class DX, class DZ>
 void run_named(const GenericSide* x, const GenericSide* z, const DecodeIO& io, int sample, uint64_t* tally) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;
-    if (sample) run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, true>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
-    else run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, false>(px, pz, io, x->lut_fm, x->lut_corr, z->lut_fm, z->lut_corr, tally);
+    if (sample) run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, true>(px, pz, io, x, z, tally);
+    else run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, false>(px, pz, io, x, z, tally);
 }
 
 }  // namespace
@@ -50,6 +54,9 @@ extern "C" {
 
 __attribute__((visibility("default"))) int emu_sizeof_side(void) { return (int)sizeof(GenericSide); }
 __attribute__((visibility("default"))) int emu_sizeof_io(void) { return (int)sizeof(DecodeIO); }
+// 1: run the FAST (tally-only, whole-unit) instantiation; caller guarantees words % VEC == 0,
+// both sides present and no output planes.
+__attribute__((visibility("default"))) void emu_set_fast(int on) { g_fast = on != 0; }
 
 // named_id < 0: generic kernels with the launch_small bucket rule; else the static descriptor.
 __attribute__((visibility("default")))

@@ -175,3 +175,47 @@ def test_sampler_statistics():
     ex, ez = ophilox.sample_bits(99, 0, shots, 3, p)
     for freq in (np.mean(ex & ~ez & 1), np.mean(ez & ~ex & 1), np.mean(ex & ez)):
         assert abs(freq - p / 3) < 5 * np.sqrt(p / 3 * (1 - p / 3) / (3 * shots))
+
+
+@pytest.mark.parametrize("name", list(NAMED))
+@pytest.mark.parametrize("static", [True, False])
+@pytest.mark.parametrize("p", [0.003, 0.03, 0.2])
+def test_fast_instantiation_tallies(name, static, p):
+    """The tally-only FAST instantiation (the Monte-Carlo hot path) counts exactly like the oracle,
+    from loaded planes and from the fused sampler."""
+    code, sx, sz = build(name)
+    shots = 128 * 40
+    rng = np.random.default_rng(5)
+    ex = (rng.random((shots, code.n)) < p).astype(np.uint8)
+    ez = (rng.random((shots, code.n)) < p).astype(np.uint8)
+    nid = NAMED[name] if static else -1
+    got = emu.decode(sx, sz, planes.pack_planes(ex), planes.pack_planes(ez), shots, nid, fast=True)
+    assert got["tally"] == omc.tally_xz(code, ex, ez)
+    got = emu.decode(sx, sz, shots=shots, named_id=nid, fast=True,
+                     sample=dict(seed=77, first_shot=256, thr=ophilox.threshold(p)))
+    ox, oz = ophilox.sample_bits(77, 256, shots, code.n, p)
+    assert got["tally"] == omc.tally_xz(code, ox, oz)
+
+
+@pytest.mark.parametrize("n,m1,m2", [(12, 7, 8), (20, 13, 6), (32, 9, 11), (16, 14, 10)])
+@pytest.mark.parametrize("p", [0.004, 0.3])
+def test_fast_generic_partial_tables(n, m1, m2, p):
+    """FAST tallies of synthetic codes whose tables miss keys (incl. possibly key 0)."""
+    rng = np.random.default_rng(n + m1 * 31)
+    sides = {}
+    for which, m in ((1, m1), (2, m2)):
+        h = rng.integers(0, 2, size=(m, n))
+        lrow = rng.integers(0, 2, size=n)
+        keys = rng.permutation(1 << m)[: max(1, (1 << m) * 2 // 3)]
+        sides[which] = (h, {int(k): rng.integers(0, 2, size=n) for k in keys}, lrow[None, :])
+    sx = emu.Side(sides[2][0], sides[2][2][0], sides[2][1])
+    sz = emu.Side(sides[1][0], sides[1][2][0], sides[1][1])
+    shots = 128 * 30
+    ex = (rng.random((shots, n)) < p).astype(np.uint8)
+    ez = (rng.random((shots, n)) < p).astype(np.uint8)
+    got = emu.decode(sx, sz, planes.pack_planes(ex), planes.pack_planes(ez), shots, -1, fast=True)["tally"]
+    dx = omc.decode_batch(*sides[2], ex)
+    dz = omc.decode_batch(*sides[1], ez)
+    assert got["fail_x"] == int(dx["flip"].sum()) and got["fail_z"] == int(dz["flip"].sum())
+    assert got["fail_any"] == int((dx["flip"] | dz["flip"]).sum())
+    assert got["miss_x"] == int(dx["miss"].sum()) and got["miss_z"] == int(dz["miss"].sum())

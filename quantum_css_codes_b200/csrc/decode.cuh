@@ -207,6 +207,35 @@ QCSS_HD WordOut finish_side(const P& pol, uint32_t (&s)[P::MB], uint32_t le, con
 // FAST units are the hot path of the Monte-Carlo tallies: both Pauli types present, all VEC words
 // fully inside the batch, nothing written but the counters.  Everything else (single-side calls,
 // output planes, the ragged tail of a batch) goes through the FAST = false instantiation.
+//
+// Loaded batches are processed one Pauli type after the other (X planes -> X flips, then Z), which
+// halves the live syndrome registers; the fused sampler draws X and Z of a qubit from the same
+// random words, so there both sides advance together.
+template <class P, int VEC>
+QCSS_HD void zero_side(uint32_t (&s)[VEC][P::MB], uint32_t (&le)[VEC]) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+        for (int t = 0; t < P::MB; ++t) s[v][t] = 0u;
+        le[v] = 0u;
+    }
+}
+
+template <class P, int VEC>
+QCSS_HD void load_side(const P& pol, const uint32_t* base, int64_t stride, uint32_t (&s)[VEC][P::MB],
+                       uint32_t (&le)[VEC]) {
+    const int n = pol.n();
+#pragma unroll
+    for (int j = 0; j < P::NB; ++j) {
+        if (j < n) {
+            uint32_t e[VEC];
+            load_words<VEC>(base + (int64_t)j * stride, e);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pol.add(j, e[v], s[v], le[v]);
+        }
+    }
+}
+
 template <class PX, class PZ, int VEC, bool SAMPLE, bool FAST>
 QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_t unit,
                           const SideLut& lut_x, const SideLut& lut_z, Counters& c) {
@@ -214,24 +243,28 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
     constexpr int NB = PX::NB;
     const int64_t w0 = unit * VEC;
     const bool do_x = FAST || SAMPLE || (io.sides & 1), do_z = FAST || SAMPLE || (io.sides & 2);
-    uint32_t sx[VEC][PX::MB], sz[VEC][PZ::MB], lex[VEC], lez[VEC];
+    uint32_t valid[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-#pragma unroll
-        for (int t = 0; t < PX::MB; ++t) sx[v][t] = 0u;
-#pragma unroll
-        for (int t = 0; t < PZ::MB; ++t) sz[v][t] = 0u;
-        lex[v] = 0u;
-        lez[v] = 0u;
+        valid[v] = 0xFFFFFFFFu;
+        if constexpr (!FAST) {
+            const int64_t w = w0 + v;
+            valid[v] = (w < io.words) ? ((w == io.words - 1) ? io.tail_mask : 0xFFFFFFFFu) : 0u;
+        }
     }
-    const int n = px.n();
-    const uint32_t* ex_ptr = io.ex + w0;
-    const uint32_t* ez_ptr = io.ez + w0;
+    WordOut ox[VEC], oz[VEC];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        if (j < n) {
-            uint32_t xe[VEC], ze[VEC];
-            if constexpr (SAMPLE) {
+    for (int v = 0; v < VEC; ++v) ox[v].flip = ox[v].miss = oz[v].flip = oz[v].miss = 0u;
+
+    if constexpr (SAMPLE) {
+        uint32_t sx[VEC][PX::MB], sz[VEC][PZ::MB], lex[VEC], lez[VEC];
+        zero_side<PX, VEC>(sx, lex);
+        zero_side<PZ, VEC>(sz, lez);
+        const int n = px.n();
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            if (j < n) {
+                uint32_t xe[VEC], ze[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
                     sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
@@ -240,40 +273,47 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
                     if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xe);
                     if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, ze);
                 }
-            } else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { xe[v] = 0u; ze[v] = 0u; }
-                if (do_x) load_words<VEC>(ex_ptr + (int64_t)j * io.e_stride, xe);
-                if (do_z) load_words<VEC>(ez_ptr + (int64_t)j * io.e_stride, ze);
+                for (int v = 0; v < VEC; ++v) {
+                    px.add(j, xe[v], sx[v], lex[v]);
+                    pz.add(j, ze[v], sz[v], lez[v]);
+                }
             }
+        }
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                px.add(j, xe[v], sx[v], lex[v]);
-                pz.add(j, ze[v], sz[v], lez[v]);
-            }
+        for (int v = 0; v < VEC; ++v) {
+            ox[v] = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x, io.c_stride,
+                                      io.flip_x, io.miss_x, w0 + v, valid[v]);
+            oz[v] = finish_side<FAST>(pz, sz[v], lez[v], lut_z, io.synd_z, io.s_stride, io.corr_z, io.c_stride,
+                                      io.flip_z, io.miss_z, w0 + v, valid[v]);
+        }
+    } else {
+        if (do_x) {
+            uint32_t sx[VEC][PX::MB], lex[VEC];
+            zero_side<PX, VEC>(sx, lex);
+            load_side<PX, VEC>(px, io.ex + w0, io.e_stride, sx, lex);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                ox[v] = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x,
+                                          io.c_stride, io.flip_x, io.miss_x, w0 + v, valid[v]);
+        }
+        if (do_z) {
+            uint32_t sz[VEC][PZ::MB], lez[VEC];
+            zero_side<PZ, VEC>(sz, lez);
+            load_side<PZ, VEC>(pz, io.ez + w0, io.e_stride, sz, lez);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                oz[v] = finish_side<FAST>(pz, sz[v], lez[v], lut_z, io.synd_z, io.s_stride, io.corr_z,
+                                          io.c_stride, io.flip_z, io.miss_z, w0 + v, valid[v]);
         }
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        const int64_t w = w0 + v;
-        uint32_t valid = 0xFFFFFFFFu;
-        if constexpr (!FAST) {
-            const bool in_range = w < io.words;
-            valid = in_range ? ((w == io.words - 1) ? io.tail_mask : 0xFFFFFFFFu) : 0u;
-        }
-        WordOut ox, oz;
-        ox.flip = ox.miss = oz.flip = oz.miss = 0u;
-        if (do_x)
-            ox = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x,
-                                   io.c_stride, io.flip_x, io.miss_x, w, valid);
-        if (do_z)
-            oz = finish_side<FAST>(pz, sz[v], lez[v], lut_z, io.synd_z, io.s_stride, io.corr_z,
-                                   io.c_stride, io.flip_z, io.miss_z, w, valid);
-        c.fail_x += popc32(ox.flip & valid);
-        c.fail_z += popc32(oz.flip & valid);
-        c.fail_any += popc32((ox.flip | oz.flip) & valid);
-        c.miss_x += popc32(ox.miss & valid);
-        c.miss_z += popc32(oz.miss & valid);
+        c.fail_x += popc32(ox[v].flip & valid[v]);
+        c.fail_z += popc32(oz[v].flip & valid[v]);
+        c.fail_any += popc32((ox[v].flip | oz[v].flip) & valid[v]);
+        c.miss_x += popc32(ox[v].miss & valid[v]);
+        c.miss_z += popc32(oz[v].miss & valid[v]);
     }
 }
 

@@ -10,8 +10,11 @@
 //      bin_matrix.py:23-24 -- same row space, and the RREF is canonical so the bits agree);
 //   3. every other row with a 1 in column c gets the pivot row XORed in, word-parallel, starting
 //      at word c/64 (the pivot row is zero left of c).
-// Round-1 version: correct and batched; the blocked (four-Russians) variant comes next.
+// This is the general-shape kernel (any number of rows); matrices with <= 1024 rows take the
+// register-resident blocked kernel in gf2_fast.cu.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "launch.h"
 
@@ -102,6 +105,8 @@ k_gf2_rref(const uint64_t* __restrict__ in, int batch, int m, int n, uint64_t* _
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out, int32_t* rank,
                             int32_t* pivots, cudaStream_t stream) {
     if (batch <= 0 || m <= 0 || n <= 0) return cudaSuccess;
+    if (gf2_fast_supported(m, n) && getenv("QCSS_GF2_SIMPLE") == nullptr)
+        return launch_gf2_fast(in, batch, m, n, out, rank, pivots, stream);
     const int W = (n + 63) >> 6;
     const size_t bytes = (size_t)m * W * sizeof(uint64_t);
     int dev = 0, sms = 0;

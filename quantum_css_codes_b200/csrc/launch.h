@@ -34,5 +34,9 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes,
 // ---- batched GF(2) Gauss-Jordan (gf2_kernels.cu) --------------------------------------------
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);
+// register-resident blocked kernel (gf2_fast.cu), rows <= 1024
+bool gf2_fast_supported(int m, int n);
+cudaError_t launch_gf2_fast(const uint64_t* in, int batch, int m, int n, uint64_t* out,
+                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
 }  // namespace qcss

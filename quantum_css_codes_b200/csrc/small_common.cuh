@@ -109,7 +109,7 @@ __device__ __forceinline__ void run_small(const PX& px, const PZ& pz, const Deco
 }
 
 template <int NB, int MB, int VEC, bool SAMPLE, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FAST ? 2 : 1)
 k_small_generic(const __grid_constant__ GenericArgs a) {
     GenericPolicy<NB, MB> px{&a.x}, pz{&a.z};
     const SideTables tx{a.x.lut_fm, a.x.lut_corr, a.x.lut_e32}, tz{a.z.lut_fm, a.z.lut_corr, a.z.lut_e32};
@@ -117,7 +117,7 @@ k_small_generic(const __grid_constant__ GenericArgs a) {
 }
 
 template <class DX, class DZ, int VEC, bool SAMPLE, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FAST ? 2 : 1)
 k_small_named(const __grid_constant__ NamedArgs a) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;

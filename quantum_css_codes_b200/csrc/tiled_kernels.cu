@@ -1,11 +1,18 @@
-// K1 for codes of any size (hypergraph-product codes, n ~ 1600): sparse-row syndrome kernel.
+// K1 for codes of any size (hypergraph-product codes, n ~ 1600): sparse-row syndrome kernels.
 //
-// One CTA stages a tile of every error plane in shared memory -- TW consecutive 32-shot words
-// (TW*4 bytes) of each of the n planes, fetched once from HBM with 16-byte cp.async -- and then
-// forms every syndrome row as the XOR of the planes its CSR row names (css_code.py:728 with a
-// sparse H).  Each error bit is read from HBM exactly once although column j of H feeds
-// several rows; syndrome words go straight back to HBM with 16-byte stores.  Two CTAs fit per
-// SM for n = 1600 (102 KB each), so one CTA's loads overlap the other's XORs.
+// A CTA stages a tile of every error plane in shared memory -- TW consecutive 32-shot words
+// (TW*4 bytes) of each of the n planes -- and forms every syndrome row as the XOR of the planes
+// its CSR row names (css_code.py:728 with a sparse H).  Each error bit leaves HBM exactly once
+// although column j of H feeds several rows; syndrome words go back with 16-byte stores.
+//
+//  k_syndrome_tma   (main path): persistent CTA per SM, two-stage ring.  The planes are a 2-D
+//                   tensor (words x planes); one thread issues cp.async.bulk.tensor (TMA) box
+//                   loads of [rows_per_box planes][TW words] that complete on an mbarrier while
+//                   the whole CTA XORs the previous tile.  Out-of-range words / planes are
+//                   zero-filled by the TMA unit, so ragged tails need no special case on input.
+//  k_syndrome_tiled (large n): single-stage tile filled with 16-byte cp.async by all threads;
+//                   used when two TMA stages do not fit in shared memory.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "launch.h"
@@ -21,7 +28,123 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 
-// TW = words per plane per tile (multiple of 4).  smem layout: tile[n][TW] uint32.
+// XOR of the planes of every CSR row for one staged tile; thread (slot, q) owns 16 bytes of a row.
+template <int TW>
+__device__ __forceinline__ void xor_rows(const SparseRows& h, const uint32_t* tile, uint32_t* __restrict__ s,
+                                         int64_t s_stride, int64_t w0, int64_t words, uint32_t tail_mask) {
+    constexpr int kQ = TW / 4;
+    constexpr int kSlots = kTiledThreads / kQ;
+    const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
+    const int64_t wq = w0 + q * 4;
+    if (wq >= words) return;
+    const bool ragged = wq + 4 > words - 1;          // touches the tail word or runs past it
+    for (int i = slot; i < h.m; i += kSlots) {
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = beg; k < end; ++k) {
+            const int j = __ldg(h.cols + k);
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)j * TW + q * 4);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        uint32_t* dst = s + (int64_t)i * s_stride + wq;
+        if (!ragged) {
+            *reinterpret_cast<uint4*>(dst) = acc;
+        } else {
+            uint32_t out[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int64_t w = wq + v;
+                if (w >= words) out[v] = 0u;
+                else if (w == words - 1) out[v] &= tail_mask;
+            }
+            if (wq + 4 <= s_stride)
+                *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+            else
+                for (int v = 0; v < 4 && wq + v < s_stride; ++v) dst[v] = out[v];
+        }
+    }
+}
+
+// ---- TMA two-stage pipeline ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+struct TmaShape {
+    int box_rows;     // planes per TMA box (<= 256)
+    int boxes;        // boxes per tile; boxes * box_rows >= n
+};
+
+template <int TW>
+__global__ void __launch_bounds__(kTiledThreads, 1)
+k_syndrome_tma(const __grid_constant__ CUtensorMap map, SparseRows h, TmaShape shape,
+               uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    const size_t stage_words = (size_t)shape.boxes * shape.box_rows * TW;
+    uint32_t* stage_buf[2] = {reinterpret_cast<uint32_t*>(smem_raw),
+                              reinterpret_cast<uint32_t*>(smem_raw) + stage_words};
+    const unsigned stage_bytes = (unsigned)(stage_words * sizeof(uint32_t));
+    const int64_t tiles = (words + TW - 1) / TW;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int st) {
+        mbar_expect_tx(&full_bar[st], stage_bytes);
+        for (int b = 0; b < shape.boxes; ++b)
+            tma_load_2d(stage_buf[st] + (size_t)b * shape.box_rows * TW, &map, (int)(tile * TW),
+                        b * shape.box_rows, &full_bar[st]);
+    };
+
+    int64_t t = blockIdx.x;
+    int st = 0;
+    unsigned parity[2] = {0u, 0u};
+    if (threadIdx.x == 0 && t < tiles) issue(t, 0);
+    for (; t < tiles; t += gridDim.x) {
+        const int64_t next = t + gridDim.x;
+        // stage st^1 was drained by everyone before the __syncthreads that ended the last pass
+        if (threadIdx.x == 0 && next < tiles) issue(next, st ^ 1);
+        mbar_wait(&full_bar[st], parity[st]);
+        parity[st] ^= 1u;
+        xor_rows<TW>(h, stage_buf[st], s, s_stride, t * TW, words, tail_mask);
+        __syncthreads();
+        st ^= 1;
+    }
+}
+
+// ---- single-stage cp.async variant ---------------------------------------------------------
 template <int TW>
 __global__ void __launch_bounds__(kTiledThreads)
 k_syndrome_tiled(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride,
@@ -33,7 +156,6 @@ k_syndrome_tiled(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride,
 
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t w0 = t * TW;
-        // ---- stage: n * kQ chunks --------------------------------------------------------
         for (int idx = threadIdx.x; idx < h.n * kQ; idx += kTiledThreads) {
             const int j = idx / kQ, q = idx % kQ;
             const int64_t chunk = w0 / 4 + q;
@@ -44,36 +166,62 @@ k_syndrome_tiled(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride,
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // ---- rows: thread (slot, q) XORs 16 bytes of each named plane ---------------------
-        const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
-        constexpr int kSlots = kTiledThreads / kQ;
-        const int64_t wq = w0 + q * 4;
-        for (int i = slot; i < h.m; i += kSlots) {
-            const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
-            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-            for (int k = beg; k < end; ++k) {
-                const int j = __ldg(h.cols + k);
-                const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)j * TW + q * 4);
-                acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
-            }
-            if (wq < words) {
-                // mask the tail word and anything past it
-                uint32_t out[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int64_t w = wq + v;
-                    if (w >= words) out[v] = 0u;
-                    else if (w == words - 1) out[v] &= tail_mask;
-                }
-                if (wq + 4 <= s_stride)
-                    *reinterpret_cast<uint4*>(s + (int64_t)i * s_stride + wq) =
-                        make_uint4(out[0], out[1], out[2], out[3]);
-                else
-                    for (int v = 0; v < 4 && wq + v < s_stride; ++v) s[(int64_t)i * s_stride + wq + v] = out[v];
-            }
-        }
+        xor_rows<TW>(h, tile, s, s_stride, w0, words, tail_mask);
         __syncthreads();
     }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+cudaError_t device_info(int* sms) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    return cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+template <int TW>
+cudaError_t launch_tma(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
+                       int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) return cudaErrorNotSupported;
+    TmaShape shape;
+    shape.boxes = (h.n + 255) / 256;
+    shape.box_rows = (h.n + shape.boxes - 1) / shape.boxes;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)e_stride, (cuuint64_t)h.n};
+    const cuuint64_t strides[1] = {(cuuint64_t)e_stride * sizeof(uint32_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)TW, (cuuint32_t)shape.box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(e), dims, strides, box, elem,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const size_t smem = 2 * (size_t)shape.boxes * shape.box_rows * TW * sizeof(uint32_t);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_tma<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
+    const int64_t tiles = (words + TW - 1) / TW;
+    int64_t grid = sms < tiles ? sms : tiles;
+    if (grid < 1) grid = 1;
+    k_syndrome_tma<TW><<<(unsigned)grid, kTiledThreads, smem, stream>>>(map, h, shape, s, s_stride, words, tail_mask);
+    return cudaGetLastError();
 }
 
 template <int TW>
@@ -83,9 +231,8 @@ cudaError_t launch_tw(const SparseRows& h, const uint32_t* e, int64_t e_stride, 
     cudaError_t err = cudaFuncSetAttribute(k_syndrome_tiled<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return err;
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+    int sms = 0, per_sm = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_syndrome_tiled<TW>, kTiledThreads,
                                                              smem)) != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
@@ -98,14 +245,21 @@ cudaError_t launch_tw(const SparseRows& h, const uint32_t* e, int64_t e_stride, 
     return cudaGetLastError();
 }
 
+size_t tma_stage_bytes(int n, int tw) {
+    const int boxes = (n + 255) / 256;
+    const int rows = (n + boxes - 1) / boxes;
+    return (size_t)boxes * rows * tw * sizeof(uint32_t);
+}
+
 }  // namespace
 
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s,
                                   int64_t s_stride, int64_t words, uint32_t tail_mask,
                                   cudaStream_t stream) {
-    const size_t budget = 100 * 1024;                 // two CTAs per SM
-    if ((size_t)h.n * 16 * 4 <= budget) return launch_tw<16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if ((size_t)h.n * 8 * 4 <= budget) return launch_tw<8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    const size_t budget = 220 * 1024;                 // dynamic shared memory for the two TMA stages
+    if (2 * tma_stage_bytes(h.n, 16) <= budget) return launch_tma<16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (2 * tma_stage_bytes(h.n, 8) <= budget) return launch_tma<8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (2 * tma_stage_bytes(h.n, 4) <= budget) return launch_tma<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
     if ((size_t)h.n * 4 * 4 <= 200 * 1024) return launch_tw<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
     return cudaErrorInvalidValue;
 }

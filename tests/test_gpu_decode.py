@@ -217,6 +217,23 @@ def test_hgp1600_syndromes_golden_and_random(golden):
             assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(h, errs))
 
 
+@pytest.mark.parametrize("n,m,row_w,shots", [(40, 20, 5, 3000), (300, 130, 9, 1025), (3000, 900, 6, 700),
+                                             (6000, 64, 30, 130)])
+def test_tiled_syndromes_random_sparse(n, m, row_w, shots):
+    """Any-size sparse syndrome kernels (TMA two-stage for n <= 7040, cp.async tile beyond)."""
+    rng = np.random.default_rng(n + m)
+    mats = []
+    for _ in range(2):
+        h = np.zeros((m, n), dtype=np.int64)
+        for i in range(m):
+            h[i, rng.choice(n, size=row_w, replace=False)] = 1
+        mats.append(h)
+    code = SyndromeCode(mats[0], mats[1])
+    errs = (rng.random((shots, n)) < 0.3).astype(np.uint8)
+    for which in (1, 2):
+        assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(mats[which - 1], errs))
+
+
 def test_error_paths():
     code, _ = pair("steane")
     with pytest.raises(ValueError):

@@ -49,6 +49,33 @@ def test_rref_random_shapes(m, n):
         assert np.array_equal(piv[b, : rank[b]], pv) and np.all(piv[b, rank[b]:] == -1)
 
 
+@pytest.mark.parametrize("m,n", [(1024, 2048), (1000, 3000), (768, 1600), (1024, 100), (33, 4000)])
+def test_rref_structured(m, n):
+    """Sparse, identity-first and low-rank matrices: strips with few or no pivots, many slabs."""
+    rng = np.random.default_rng(m + n)
+    sparse = (rng.random((m, n)) < 0.004).astype(np.uint8)
+    ident = np.zeros((m, n), dtype=np.uint8)
+    ident[np.arange(min(m, n)), np.arange(min(m, n))] = 1
+    ident[:, min(m, n) - 1:] ^= (rng.random((m, n - min(m, n) + 1)) < 0.5).astype(np.uint8)
+    basis = rng.integers(0, 2, size=(7, n), dtype=np.uint8)
+    lowrank = ((rng.integers(0, 2, size=(m, 7), dtype=np.int64) @ basis.astype(np.int64)) % 2).astype(np.uint8)
+    mats = np.stack([sparse, ident, lowrank, np.zeros((m, n), dtype=np.uint8)])
+    out, rank, piv = bin_matrix.rref_batched(mats)
+    for b in range(len(mats)):
+        want, pv = ogf2.rref_packed(ogf2.pack_rows(mats[b]), n)
+        assert np.array_equal(out[b], ogf2.unpack_rows(want, n)), b
+        assert rank[b] == len(pv) and np.array_equal(piv[b, : rank[b]], pv)
+    assert rank[2] <= 7 and rank[3] == 0
+
+
+def test_rref_more_than_1024_rows_uses_general_kernel():
+    rng = np.random.default_rng(77)
+    mat = rng.integers(0, 2, size=(1100, 300), dtype=np.int64)
+    out, rank, piv = bin_matrix.rref_batched(mat[None])
+    want, pv = ogf2.rref_packed(ogf2.pack_rows(mat.astype(np.uint8)), 300)
+    assert np.array_equal(out[0], ogf2.unpack_rows(want, 300)) and rank[0] == len(pv)
+
+
 def test_rref_c5_full_size():
     """BASELINE config 5 shape: random 1024 x 2048 matrices, plus rank-deficient variants."""
     packed = codes.random_matrices_c5(4).copy()

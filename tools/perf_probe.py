@@ -125,8 +125,9 @@ def main():
     if only is None or "hgp" in only:
         probe_hgp(1 << 22 if args.quick else 100_000_000)
     if only is None or "gf2" in only:
-        probe_gf2(64 if args.quick else 512)
-        probe_gf2(256, 256, 512)
+        probe_gf2(64 if args.quick else 4096)
+        probe_gf2(4096, 256, 512)
+        probe_gf2(2048, 768, 1600)
 
 
 if __name__ == "__main__":

@@ -53,8 +53,9 @@ __host__ __device__ inline FastLayout make_layout(int m, int n) {
     L.off_rowpiv = off;  off += (size_t)L.mpad * sizeof(int16_t);
     off = (off + 3) & ~(size_t)3;
     L.off_pivcol = off;  off += (size_t)L.kmax * sizeof(int32_t);
+    off = (off + 7) & ~(size_t)7;
     L.off_cand = off;    off += 2 * 32 * sizeof(uint16_t);
-    L.off_lrow = off;    off += 8;
+    L.off_lrow = off;    off += 8;                      // 8-byte aligned: read as one uint2
     L.total = (off + 15) & ~(size_t)15;
     return L;
 }

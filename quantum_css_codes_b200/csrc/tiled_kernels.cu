@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "launch.h"
 
 namespace qcss {
@@ -45,6 +47,53 @@ __device__ __forceinline__ void xor_rows(const SparseRows& h, const uint32_t* ti
             const int j = __ldg(h.cols + k);
             const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)j * TW + q * 4);
             acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        uint32_t* dst = s + (int64_t)i * s_stride + wq;
+        if (!ragged) {
+            *reinterpret_cast<uint4*>(dst) = acc;
+        } else {
+            uint32_t out[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int64_t w = wq + v;
+                if (w >= words) out[v] = 0u;
+                else if (w == words - 1) out[v] &= tail_mask;
+            }
+            if (wq + 4 <= s_stride)
+                *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+            else
+                for (int v = 0; v < 4 && wq + v < s_stride; ++v) dst[v] = out[v];
+        }
+    }
+}
+
+// Same, with the row supports in shared memory in ELL form: ell[i][0..WP) are the plane indices of
+// row i (0xFFFF = padding), WP a multiple of 8 so one 16-byte read fetches 8 of them.  All the
+// plane reads of a row are independent, so the loop is shared-memory-bandwidth bound.
+template <int TW, int WP>
+__device__ __forceinline__ void xor_rows_ell(int m, const uint16_t* ell, const uint32_t* tile,
+                                             uint32_t* __restrict__ s, int64_t s_stride, int64_t w0, int64_t words,
+                                             uint32_t tail_mask) {
+    constexpr int kQ = TW / 4;
+    constexpr int kSlots = kTiledThreads / kQ;
+    const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
+    const int64_t wq = w0 + q * 4;
+    if (wq >= words) return;
+    const bool ragged = wq + 4 > words - 1;
+    for (int i = slot; i < m; i += kSlots) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int g = 0; g < WP / 8; ++g) {
+            const uint4 idx = *reinterpret_cast<const uint4*>(ell + (size_t)i * WP + g * 8);
+            const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t j = (iw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                if (j != 0xFFFFu) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)j * TW + q * 4);
+                    acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                }
+            }
         }
         uint32_t* dst = s + (int64_t)i * s_stride + wq;
         if (!ragged) {
@@ -101,31 +150,50 @@ struct TmaShape {
     int boxes;        // boxes per tile; boxes * box_rows >= n
 };
 
-template <int TW>
+// Boxes of equal height covering n planes.  The height is a multiple of 8 so that every box starts
+// on a 128-byte boundary of the stage buffer (TMA destination alignment) for any tile width >= 4.
+inline TmaShape tma_shape(int n) {
+    TmaShape sh;
+    sh.boxes = (n + 255) / 256;
+    sh.box_rows = (((n + sh.boxes - 1) / sh.boxes) + 7) & ~7;
+    return sh;
+}
+
+// WP = 0: row supports read from the CSR arrays in global memory; WP = 8 / 16: ELL copy in smem.
+template <int TW, int WP>
 __global__ void __launch_bounds__(kTiledThreads, 1)
-k_syndrome_tma(const __grid_constant__ CUtensorMap map, SparseRows h, TmaShape shape,
-               uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+k_syndrome_tma(const __grid_constant__ CUtensorMap map, const CUtensorMap* __restrict__ gmap, int dbg,
+               SparseRows h, TmaShape shape, uint32_t* __restrict__ s, int64_t s_stride, int64_t words,
+               uint32_t tail_mask) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
-    const size_t stage_words = (size_t)shape.boxes * shape.box_rows * TW;
-    uint32_t* stage_buf[2] = {reinterpret_cast<uint32_t*>(smem_raw),
-                              reinterpret_cast<uint32_t*>(smem_raw) + stage_words};
-    const unsigned stage_bytes = (unsigned)(stage_words * sizeof(uint32_t));
+    const unsigned stage_words = (unsigned)(shape.boxes * shape.box_rows * TW);
+    const unsigned stage_bytes = stage_words * (unsigned)sizeof(uint32_t);
+    uint32_t* const stage0 = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* const ell = reinterpret_cast<uint16_t*>(smem_raw + 2 * (size_t)stage_bytes);
     const int64_t tiles = (words + TW - 1) / TW;
+    const CUtensorMap* mp = (dbg & 2) ? gmap : &map;
+    if constexpr (WP > 0) {
+        for (int idx = threadIdx.x; idx < h.m * WP; idx += kTiledThreads) {
+            const int i = idx / WP, k = idx % WP;
+            const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+            ell[idx] = (beg + k < end) ? __ldg(h.cols + beg + k) : (uint16_t)0xFFFFu;
+        }
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+        if (!(dbg & 1)) asm volatile("prefetch.tensormap [%0];" ::"l"(mp) : "memory");
     }
     __syncthreads();
 
     auto issue = [&](int64_t tile, int st) {
         mbar_expect_tx(&full_bar[st], stage_bytes);
         for (int b = 0; b < shape.boxes; ++b)
-            tma_load_2d(stage_buf[st] + (size_t)b * shape.box_rows * TW, &map, (int)(tile * TW),
-                        b * shape.box_rows, &full_bar[st]);
+            tma_load_2d(stage0 + (size_t)st * stage_words + (size_t)b * shape.box_rows * TW, mp,
+                        (int)(tile * TW), b * shape.box_rows, &full_bar[st]);
     };
 
     int64_t t = blockIdx.x;
@@ -138,7 +206,10 @@ k_syndrome_tma(const __grid_constant__ CUtensorMap map, SparseRows h, TmaShape s
         if (threadIdx.x == 0 && next < tiles) issue(next, st ^ 1);
         mbar_wait(&full_bar[st], parity[st]);
         parity[st] ^= 1u;
-        xor_rows<TW>(h, stage_buf[st], s, s_stride, t * TW, words, tail_mask);
+        if constexpr (WP > 0)
+            xor_rows_ell<TW, WP>(h.m, ell, stage0 + (size_t)st * stage_words, s, s_stride, t * TW, words, tail_mask);
+        else
+            xor_rows<TW>(h, stage0 + (size_t)st * stage_words, s, s_stride, t * TW, words, tail_mask);
         __syncthreads();
         st ^= 1;
     }
@@ -195,14 +266,12 @@ cudaError_t device_info(int* sms) {
     return cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
-template <int TW>
+template <int TW, int WP>
 cudaError_t launch_tma(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
                        int64_t words, uint32_t tail_mask, cudaStream_t stream) {
     EncodeTiledFn encode = encode_tiled_fn();
     if (encode == nullptr) return cudaErrorNotSupported;
-    TmaShape shape;
-    shape.boxes = (h.n + 255) / 256;
-    shape.box_rows = (h.n + shape.boxes - 1) / shape.boxes;
+    const TmaShape shape = tma_shape(h.n);
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)e_stride, (cuuint64_t)h.n};
     const cuuint64_t strides[1] = {(cuuint64_t)e_stride * sizeof(uint32_t)};
@@ -212,15 +281,29 @@ cudaError_t launch_tma(const SparseRows& h, const uint32_t* e, int64_t e_stride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const size_t smem = 2 * (size_t)shape.boxes * shape.box_rows * TW * sizeof(uint32_t);
-    cudaError_t err = cudaFuncSetAttribute(k_syndrome_tma<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = 2 * (size_t)shape.boxes * shape.box_rows * TW * sizeof(uint32_t) +
+                        (size_t)h.m * WP * sizeof(uint16_t);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_tma<TW, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int sms = 0;
     if ((err = device_info(&sms)) != cudaSuccess) return err;
     const int64_t tiles = (words + TW - 1) / TW;
     int64_t grid = sms < tiles ? sms : tiles;
     if (grid < 1) grid = 1;
-    k_syndrome_tma<TW><<<(unsigned)grid, kTiledThreads, smem, stream>>>(map, h, shape, s, s_stride, words, tail_mask);
+    // debugging knob QCSS_TMA_DBG: bit0 = no descriptor prefetch, bit1 = descriptor read from global memory
+    static int dbg = -1;
+    static CUtensorMap* d_map = nullptr;
+    if (dbg < 0) {
+        const char* v = getenv("QCSS_TMA_DBG");
+        dbg = v ? atoi(v) : 0;
+    }
+    if (dbg & 2) {
+        if (d_map == nullptr && (err = cudaMalloc((void**)&d_map, sizeof(CUtensorMap))) != cudaSuccess) return err;
+        if ((err = cudaMemcpyAsync(d_map, &map, sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+            return err;
+    }
+    k_syndrome_tma<TW, WP><<<(unsigned)grid, kTiledThreads, smem, stream>>>(map, d_map, dbg, h, shape, s, s_stride,
+                                                                          words, tail_mask);
     return cudaGetLastError();
 }
 
@@ -246,9 +329,8 @@ cudaError_t launch_tw(const SparseRows& h, const uint32_t* e, int64_t e_stride, 
 }
 
 size_t tma_stage_bytes(int n, int tw) {
-    const int boxes = (n + 255) / 256;
-    const int rows = (n + boxes - 1) / boxes;
-    return (size_t)boxes * rows * tw * sizeof(uint32_t);
+    const TmaShape sh = tma_shape(n);
+    return (size_t)sh.boxes * sh.box_rows * tw * sizeof(uint32_t);
 }
 
 }  // namespace
@@ -257,9 +339,25 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e, int64_
                                   int64_t s_stride, int64_t words, uint32_t tail_mask,
                                   cudaStream_t stream) {
     const size_t budget = 220 * 1024;                 // dynamic shared memory for the two TMA stages
-    if (2 * tma_stage_bytes(h.n, 16) <= budget) return launch_tma<16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if (2 * tma_stage_bytes(h.n, 8) <= budget) return launch_tma<8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if (2 * tma_stage_bytes(h.n, 4) <= budget) return launch_tma<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (getenv("QCSS_TILED_NO_TMA") != nullptr) {
+        if ((size_t)h.n * 16 * 4 <= 100 * 1024) return launch_tw<16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+        return launch_tw<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    }
+    // ELL copy of the row supports in shared memory when it fits next to the two stages
+    const size_t total = 226 * 1024;
+    auto ell_fits = [&](int tw, int wp) {
+        return h.max_row_weight <= wp && 2 * tma_stage_bytes(h.n, tw) + (size_t)h.m * wp * 2 <= total;
+    };
+#define QCSS_TMA_CASE(TWV)                                                                                     \
+    if (2 * tma_stage_bytes(h.n, TWV) <= budget) {                                                             \
+        if (ell_fits(TWV, 8)) return launch_tma<TWV, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);   \
+        if (ell_fits(TWV, 16)) return launch_tma<TWV, 16>(h, e, e_stride, s, s_stride, words, tail_mask, stream); \
+        return launch_tma<TWV, 0>(h, e, e_stride, s, s_stride, words, tail_mask, stream);                       \
+    }
+    QCSS_TMA_CASE(16)
+    QCSS_TMA_CASE(8)
+    QCSS_TMA_CASE(4)
+#undef QCSS_TMA_CASE
     if ((size_t)h.n * 4 * 4 <= 200 * 1024) return launch_tw<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
     return cudaErrorInvalidValue;
 }

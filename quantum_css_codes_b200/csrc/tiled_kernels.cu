@@ -70,12 +70,12 @@ __device__ __forceinline__ void xor_rows(const SparseRows& h, const uint32_t* ti
 // Same, with the row supports in shared memory in ELL form: ell[i][0..WP) are the plane indices of
 // row i (0xFFFF = padding), WP a multiple of 8 so one 16-byte read fetches 8 of them.  All the
 // plane reads of a row are independent, so the loop is shared-memory-bandwidth bound.
-template <int TW, int WP>
+template <int TW, int WP, int THREADS = kTiledThreads>
 __device__ __forceinline__ void xor_rows_ell(int m, const uint16_t* ell, const uint32_t* tile,
                                              uint32_t* __restrict__ s, int64_t s_stride, int64_t w0, int64_t words,
                                              uint32_t tail_mask) {
     constexpr int kQ = TW / 4;
-    constexpr int kSlots = kTiledThreads / kQ;
+    constexpr int kSlots = THREADS / kQ;
     const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
     const int64_t wq = w0 + q * 4;
     if (wq >= words) return;
@@ -196,14 +196,20 @@ k_syndrome_tma(const __grid_constant__ CUtensorMap map, const CUtensorMap* __res
                         (int)(tile * TW), b * shape.box_rows, &full_bar[st]);
     };
 
-    int64_t t = blockIdx.x;
+    // tile -> CTA mapping: interleaved (CTA b takes b, b+grid, ...) or, with dbg bit 16, a contiguous
+    // range per CTA (consecutive tiles of one CTA then share 256-byte L2 lines)
+    const bool contig = (dbg & 16) != 0;
+    const int64_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+    int64_t t = contig ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
+    const int64_t t_end = contig ? (t + per_cta < tiles ? t + per_cta : tiles) : tiles;
+    const int64_t t_step = contig ? 1 : (int64_t)gridDim.x;
     int st = 0;
     unsigned parity[2] = {0u, 0u};
-    if (threadIdx.x == 0 && t < tiles) issue(t, 0);
-    for (; t < tiles; t += gridDim.x) {
-        const int64_t next = t + gridDim.x;
+    if (threadIdx.x == 0 && t < t_end) issue(t, 0);
+    for (; t < t_end; t += t_step) {
+        const int64_t next = t + t_step;
         // stage st^1 was drained by everyone before the __syncthreads that ended the last pass
-        if (threadIdx.x == 0 && next < tiles) issue(next, st ^ 1);
+        if (threadIdx.x == 0 && next < t_end) issue(next, st ^ 1);
         mbar_wait(&full_bar[st], parity[st]);
         parity[st] ^= 1u;
         if constexpr (WP > 0)
@@ -242,6 +248,184 @@ k_syndrome_tiled(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride,
     }
 }
 
+// ---- wide single-stage tiles with L2 prefetch (default path) ---------------------------------------
+// The widest tile that fits one CTA per SM (TW = 32 words = one 128-byte line per plane for n <= 1640)
+// is staged with 16-byte cp.async by all 1024 threads.  While the CTA XORs tile t it has already asked
+// L2 to fetch tile t+grid (one prefetch per 128-byte line), so the next staging pass is served from
+// L2 and the DRAM latency hides behind the XOR phase.  Measured on B200 (HGP-1600, 5e7 shots): 128-byte
+// rows reach 1.5x the bandwidth of the 64-byte-row TMA ring, whose per-row request rate is the limit.
+constexpr int kWideThreads = 1024;
+
+template <int TW, int WP>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_syndrome_wide(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride, uint32_t* __restrict__ s,
+                int64_t s_stride, int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* const tile = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* const ell = reinterpret_cast<uint16_t*>(smem_raw + (size_t)h.n * TW * sizeof(uint32_t));
+    constexpr int kQ = TW / 4;                       // 16-byte chunks per plane row
+    const int64_t tiles = (words + TW - 1) / TW;
+    const int64_t e_chunks = e_stride / 4;
+    for (int idx = threadIdx.x; idx < h.m * WP; idx += kWideThreads) {
+        const int i = idx / WP, k = idx % WP;
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        ell[idx] = (beg + k < end) ? __ldg(h.cols + beg + k) : (uint16_t)0xFFFFu;
+    }
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t w0 = t * TW;
+        for (int idx = threadIdx.x; idx < h.n * kQ; idx += kWideThreads) {
+            const int j = idx / kQ, q = idx % kQ;
+            const int64_t chunk = w0 / 4 + q;
+            uint32_t* dst = tile + (size_t)j * TW + q * 4;
+            if (chunk < e_chunks) cp_async16(dst, e + (int64_t)j * e_stride + chunk * 4);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int64_t next = t + gridDim.x;
+        if (next < tiles) {
+            constexpr int kLines = (TW * 4 + 127) / 128;         // 128-byte lines per plane row
+            const int64_t nw0 = next * TW;
+            for (int idx = threadIdx.x; idx < h.n * kLines; idx += kWideThreads) {
+                const int j = idx / kLines, l = idx % kLines;
+                const int64_t w = nw0 + l * 32;
+                if (w < e_stride)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(e + (int64_t)j * e_stride + w));
+            }
+        }
+        xor_rows_ell<TW, WP, kWideThreads>(h.m, ell, tile, s, s_stride, w0, words, tail_mask);
+        __syncthreads();
+    }
+}
+
+template <int TW, int WP>
+cudaError_t launch_wide(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
+                        int64_t words, uint32_t tail_mask, cudaStream_t stream);
+
+// ---- plane-split accumulate pipeline (default path for n x 128 B > one stage) -----------------------
+// 128-byte plane rows are what the memory system likes (64-byte rows run at about half the L2 request
+// rate), but n = 1600 planes x 128 B is a whole SM's shared memory, leaving no second stage.  So the
+// planes are split into P parts of <= pp planes; a tile is processed as P "part-tiles" that flow
+// through a two-stage cp.async ring, and every thread keeps the partial syndromes of its RPT row
+// chunks in registers across the parts of a tile (row i, 16-byte chunk q <-> thread (i % 128) * 8 + q).
+// Loads of part-tile k+1 are in flight while part-tile k is XORed.
+constexpr int kSplitTW = 32;                  // words per plane row per tile: one 128-byte line
+constexpr int kSplitSlots = kWideThreads / 8; // 128 row slots x 8 chunks
+
+struct SplitShape {
+    int parts;        // P
+    int pp;           // planes per part
+    int blocked;      // experiment: input stored tile-major [tile][plane][32 words]
+};
+
+template <int RPT, int WP>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_syndrome_split(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, int64_t e_stride,
+                 uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int TW = kSplitTW, kQ = TW / 4;
+    const size_t stage_words = (size_t)shape.pp * TW;
+    uint32_t* const stage0 = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* const ell = reinterpret_cast<uint16_t*>(smem_raw + 2 * stage_words * sizeof(uint32_t));
+    const int64_t tiles = (words + TW - 1) / TW;
+    const int64_t e_chunks = e_stride / 4;
+    for (int idx = threadIdx.x; idx < h.m * WP; idx += kWideThreads) {
+        const int i = idx / WP, k = idx % WP;
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        ell[idx] = (beg + k < end) ? __ldg(h.cols + beg + k) : (uint16_t)0xFFFFu;
+    }
+    const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
+    const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t steps = my_tiles * shape.parts;
+
+    auto issue = [&](int64_t step) {
+        const int64_t t = blockIdx.x + (step / shape.parts) * gridDim.x;
+        const int part = (int)(step % shape.parts);
+        const int lo = part * shape.pp;
+        const int cnt = (h.n - lo) < shape.pp ? (h.n - lo) : shape.pp;
+        uint32_t* buf = stage0 + (size_t)(step & 1) * stage_words;
+        const int64_t c0 = t * (TW / 4);
+        for (int idx = threadIdx.x; idx < cnt * kQ; idx += kWideThreads) {
+            const int j = idx / kQ, qq = idx % kQ;
+            uint32_t* dst = buf + (size_t)j * TW + qq * 4;
+            if (shape.blocked) cp_async16(dst, e + ((int64_t)t * h.n + lo + j) * TW + qq * 4);
+            else if (c0 + qq < e_chunks) cp_async16(dst, e + (int64_t)(lo + j) * e_stride + (c0 + qq) * 4);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint4 acc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = make_uint4(0u, 0u, 0u, 0u);
+    if (steps > 0) issue(0);
+    for (int64_t step = 0; step < steps; ++step) {
+        if (step + 1 < steps) {
+            issue(step + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int part = (int)(step % shape.parts);
+        const uint32_t lo = (uint32_t)(part * shape.pp), cnt = (uint32_t)shape.pp;
+        const uint32_t* buf = stage0 + (size_t)(step & 1) * stage_words;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = slot + r * kSplitSlots;
+            if (i < h.m) {
+#pragma unroll
+                for (int g = 0; g < WP / 8; ++g) {
+                    const uint4 idx = *reinterpret_cast<const uint4*>(ell + (size_t)i * WP + g * 8);
+                    const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t j = ((iw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) - lo;
+                        if (j < cnt) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(buf + (size_t)j * TW + q * 4);
+                            acc[r].x ^= v.x; acc[r].y ^= v.y; acc[r].z ^= v.z; acc[r].w ^= v.w;
+                        }
+                    }
+                }
+            }
+        }
+        if (part == shape.parts - 1) {
+            const int64_t t = blockIdx.x + (step / shape.parts) * gridDim.x;
+            const int64_t wq = t * TW + q * 4;
+            const bool ragged = wq + 4 > words - 1;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int i = slot + r * kSplitSlots;
+                if (i < h.m && wq < words) {
+                    uint32_t* dst = s + (int64_t)i * s_stride + wq;
+                    if (!ragged) {
+                        *reinterpret_cast<uint4*>(dst) = acc[r];
+                    } else {
+                        uint32_t out[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int64_t w = wq + v;
+                            if (w >= words) out[v] = 0u;
+                            else if (w == words - 1) out[v] &= tail_mask;
+                        }
+                        if (wq + 4 <= s_stride)
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+                        else
+                            for (int v = 0; v < 4 && wq + v < s_stride; ++v) dst[v] = out[v];
+                    }
+                }
+                acc[r] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int RPT, int WP>
+cudaError_t launch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                         int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream);
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -277,8 +461,17 @@ cudaError_t launch_tma(const SparseRows& h, const uint32_t* e, int64_t e_stride,
     const cuuint64_t strides[1] = {(cuuint64_t)e_stride * sizeof(uint32_t)};
     const cuuint32_t box[2] = {(cuuint32_t)TW, (cuuint32_t)shape.box_rows};
     const cuuint32_t elem[2] = {1, 1};
+    static int promo = -1;
+    if (promo < 0) {
+        const char* v = getenv("QCSS_TMA_PROMO");
+        promo = v ? atoi(v) : 128;
+    }
+    const CUtensorMapL2promotion l2p = promo >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : (promo >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                      : (promo >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                                     : CU_TENSOR_MAP_L2_PROMOTION_NONE));
     CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(e), dims, strides, box, elem,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     const size_t smem = 2 * (size_t)shape.boxes * shape.box_rows * TW * sizeof(uint32_t) +
@@ -328,6 +521,51 @@ cudaError_t launch_tw(const SparseRows& h, const uint32_t* e, int64_t e_stride, 
     return cudaGetLastError();
 }
 
+template <int TW, int WP>
+cudaError_t launch_wide(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
+                        int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    const size_t smem = (size_t)h.n * TW * sizeof(uint32_t) + (size_t)h.m * WP * sizeof(uint16_t);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_wide<TW, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+    if (err != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
+    const int64_t tiles = (words + TW - 1) / TW;
+    int64_t grid = sms < tiles ? sms : tiles;
+    if (grid < 1) grid = 1;
+    k_syndrome_wide<TW, WP><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, e, e_stride, s, s_stride, words,
+                                                                          tail_mask);
+    return cudaGetLastError();
+}
+
+template <int RPT, int WP>
+cudaError_t launch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                         int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    const size_t smem = 2 * (size_t)shape.pp * kSplitTW * sizeof(uint32_t) + (size_t)h.m * WP * sizeof(uint16_t);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_split<RPT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+    if (err != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
+    const int64_t tiles = (words + kSplitTW - 1) / kSplitTW;
+    int64_t grid = sms < tiles ? sms : tiles;
+    if (grid < 1) grid = 1;
+    k_syndrome_split<RPT, WP><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, shape, e, e_stride, s, s_stride,
+                                                                            words, tail_mask);
+    return cudaGetLastError();
+}
+
+template <int WP>
+cudaError_t dispatch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                           int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    const int rpt = (h.m + kSplitSlots - 1) / kSplitSlots;
+    if (rpt <= 2) return launch_split<2, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 4) return launch_split<4, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 6) return launch_split<6, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 8) return launch_split<8, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    return launch_split<12, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+}
+
 size_t tma_stage_bytes(int n, int tw) {
     const TmaShape sh = tma_shape(n);
     return (size_t)sh.boxes * sh.box_rows * tw * sizeof(uint32_t);
@@ -338,8 +576,42 @@ size_t tma_stage_bytes(int n, int tw) {
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s,
                                   int64_t s_stride, int64_t words, uint32_t tail_mask,
                                   cudaStream_t stream) {
+    // default: plane-split accumulate pipeline (128-byte rows, two-stage ring, partial sums in registers)
+    if (getenv("QCSS_TILED_TMA") == nullptr && getenv("QCSS_TILED_NO_TMA") == nullptr &&
+        getenv("QCSS_TILED_WIDE") == nullptr && h.max_row_weight <= 16 && h.m <= 12 * kSplitSlots) {
+        const int wp = h.max_row_weight <= 8 ? 8 : 16;
+        const size_t cap = 226 * 1024, ell_bytes = (size_t)h.m * wp * 2;
+        for (int parts = 1; parts <= 64; ++parts) {
+            const int pp = (h.n + parts - 1) / parts;
+            if (2 * (size_t)pp * kSplitTW * 4 + ell_bytes <= cap) {
+                const SplitShape shape{parts, pp, getenv("QCSS_TILED_BLOCKED") != nullptr ? 1 : 0};
+                if (wp == 8) return dispatch_split<8>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+                return dispatch_split<16>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+            }
+        }
+    }
+    // widest single-stage tile with the ELL supports next to it in shared memory
+    if (getenv("QCSS_TILED_TMA") == nullptr && getenv("QCSS_TILED_NO_TMA") == nullptr) {
+        const size_t cap = 226 * 1024;
+        const int wp = h.max_row_weight <= 8 ? 8 : (h.max_row_weight <= 16 ? 16 : 0);
+        if (wp != 0) {
+            const size_t ell_bytes = (size_t)h.m * wp * 2;
+#define QCSS_WIDE_CASE(TWV)                                                                                   \
+    if ((size_t)h.n * TWV * 4 + ell_bytes <= cap) {                                                           \
+        if (wp == 8) return launch_wide<TWV, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);        \
+        return launch_wide<TWV, 16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);                    \
+    }
+            QCSS_WIDE_CASE(32)
+            QCSS_WIDE_CASE(16)
+            QCSS_WIDE_CASE(8)
+            QCSS_WIDE_CASE(4)
+#undef QCSS_WIDE_CASE
+        }
+    }
     const size_t budget = 220 * 1024;                 // dynamic shared memory for the two TMA stages
     if (getenv("QCSS_TILED_NO_TMA") != nullptr) {
+        if (atoi(getenv("QCSS_TILED_NO_TMA")) == 32 && (size_t)h.n * 32 * 4 <= 220 * 1024)
+            return launch_tw<32>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
         if ((size_t)h.n * 16 * 4 <= 100 * 1024) return launch_tw<16>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
         return launch_tw<4>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
     }

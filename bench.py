@@ -32,6 +32,10 @@ sys.path.insert(0, REPO)
 P_ERR = 1e-3
 SEED = 0x5EED
 CPU_SAMPLE_SHOTS = 1 << 22        # per worker per step of the CPU baseline
+# dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per shot, from the committed
+# `ncu --set full` capture of this very command (profiles/r01_steane_bench_ncu_summary.txt:
+# 17.500021 GB read + 3.6 MB written for 1e10 shots).  Algorithmic bytes are 1.75 B/shot.
+NCU_TRAFFIC_BYTES_PER_SHOT = {"steane": 1.7503621}
 
 
 def parse_args():
@@ -263,7 +267,10 @@ def run_b200(args):
                        "l2_policy": "inputs (%.1f GB) larger than L2, no flush" % (2 * n * stride * 8 / 1e9),
                        "kernel": dev.kernel_name(), "parallelism": f"shots sharded over {world} GPU(s), weak"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": (NCU_TRAFFIC_BYTES_PER_SHOT[args.code] * shots
+                                     if args.code in NCU_TRAFFIC_BYTES_PER_SHOT else None),
+                         "traffic_source": "profiles/r01_steane_bench_ncu_summary.txt (ncu --set full, bytes/shot x shots)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_shot": bytes_per_shot, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,

@@ -107,10 +107,17 @@ k_gf2_fast(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
         // Applies pivots [t0, t0+k) to the slab held in r[].
         uint32_t r[32];
         auto apply = [&](int t0, int k) {
-            // A1: owners publish the pivot rows' words of this slab
-            for (int u = 0; u < k; ++u) {
-                const int p = pivrow[t0 + u];
-                if ((p >> 5) == warp) P[u * kSlabWords + lane] = select_reg(r, p & 31);
+            // A1: owners publish the pivot rows' words of this slab.  Lane l looks at row 32*warp+l;
+            // a ballot tells the warp which of its rows (usually none or one) are pivots of the block.
+            {
+                const int pk = (int)rowpiv[tid] - t0;
+                unsigned mine = __ballot_sync(0xFFFFFFFFu, (unsigned)pk < (unsigned)k);
+                while (mine != 0u) {
+                    const int i = __ffs(mine) - 1;
+                    mine &= mine - 1u;
+                    const int u = __shfl_sync(0xFFFFFFFFu, pk, i);
+                    P[u * kSlabWords + lane] = select_reg(r, i);
+                }
             }
             // A2: warp 0 unwinds the order dependence between the block's pivots
             const int byte0 = t0 >> 3, off = t0 & 7;

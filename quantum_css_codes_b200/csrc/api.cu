@@ -68,6 +68,8 @@ struct qcss_code {
     DevBuf fm_x, fm_z, co_x, co_z, e32_x, e32_z;      // lookup tables
     SparseRows sp1{}, sp2{};            // CSR of H1 / H2 for the tiled kernel
     DevBuf sp1_ptr, sp1_cols, sp2_ptr, sp2_cols;
+    DevBuf hq1, hq2;                    // dense H1 / H2 in tensor-core operand layout (dense codes only)
+    bool dense1 = false, dense2 = false;
     // host-buffer paths
     cudaStream_t stream = nullptr;
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
@@ -174,6 +176,26 @@ int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, 
     sp.max_row_weight = maxw;
     sp.row_ptr = (const int32_t*)d_ptr.p;
     sp.cols = (const uint16_t*)d_cols.p;
+    return QCSS_OK;
+}
+
+// A check matrix goes to the tensor-core kernel when it is big and dense enough for the contraction
+// to be a real GEMM (QCSS_DENSE=1 / 0 forces the choice, for the parity tests and the comparison runs).
+bool wants_dense(int m, int n, const uint8_t* H) {
+    const char* force = getenv("QCSS_DENSE");
+    if (force != nullptr) return atoi(force) != 0;
+    if ((size_t)m * n < (size_t)256 * 512) return false;
+    size_t nnz = 0;
+    for (size_t i = 0; i < (size_t)m * n; ++i) nnz += H[i] & 1;
+    return nnz * 8 >= (size_t)m * n;                       // density >= 1/8
+}
+
+int build_dense(int m, int n, const uint8_t* H, DevBuf& d_hq) {
+    const size_t bytes = dense_h_bytes(m, n);
+    std::vector<uint8_t> hq(bytes);
+    dense_h_layout(m, n, H, hq.data());
+    QCSS_CUDA(d_hq.reserve(bytes));
+    QCSS_CUDA(cudaMemcpy(d_hq.p, hq.data(), bytes, cudaMemcpyHostToDevice));
     return QCSS_OK;
 }
 
@@ -308,6 +330,13 @@ int launch_syndrome(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stri
         QCSS_CUDA(launch_small(l, stream));
         return QCSS_OK;
     }
+    if ((which == 1) ? c->dense1 : c->dense2) {
+        const DevBuf& hq = (which == 1) ? c->hq1 : c->hq2;
+        QCSS_CUDA(launch_syndrome_mma((const uint8_t*)hq.p, (which == 1) ? c->m1 : c->m2, c->n, (const uint32_t*)d_e,
+                                      e_stride * 2, (uint32_t*)d_s, s_stride * 2, (shots + 31) / 32,
+                                      tail_mask_for(shots), stream));
+        return QCSS_OK;
+    }
     const SparseRows& sp = (which == 1) ? c->sp1 : c->sp2;
     cudaError_t e = launch_syndrome_tiled(sp, (const uint32_t*)d_e, e_stride * 2, (uint32_t*)d_s,
                                           s_stride * 2, (shots + 31) / 32, tail_mask_for(shots), stream);
@@ -382,6 +411,12 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
     }
     if (!rc) rc = build_sparse(m1, n, H1, c->sp1, c->sp1_ptr, c->sp1_cols);
     if (!rc) rc = build_sparse(m2, n, H2, c->sp2, c->sp2_ptr, c->sp2_cols);
+    if (!rc && !c->small) {
+        c->dense1 = wants_dense(m1, n, H1);
+        c->dense2 = wants_dense(m2, n, H2);
+        if (c->dense1) rc = build_dense(m1, n, H1, c->hq1);
+        if (!rc && c->dense2) rc = build_dense(m2, n, H2, c->hq2);
+    }
     if (rc) {
         qcss_code_destroy(c);
         return rc;
@@ -395,6 +430,7 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
     c->fm_x.release(); c->fm_z.release(); c->co_x.release(); c->co_z.release();
     c->e32_x.release(); c->e32_z.release();
     c->sp1_ptr.release(); c->sp1_cols.release(); c->sp2_ptr.release(); c->sp2_cols.release();
+    c->hq1.release(); c->hq2.release();
     for (int i = 0; i < kSlots; ++i) {
         c->slot_x[i].release();
         c->slot_z[i].release();
@@ -409,7 +445,9 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
 
 QCSS_API int qcss_code_kernel_name(const qcss_code* c, char* buf, int buflen) {
     if (!c || !buf || buflen <= 0) return fail(QCSS_ERR_INVALID, "bad arguments");
-    if (!c->small)
+    if (!c->small && (c->dense1 || c->dense2))
+        snprintf(buf, buflen, "dense-tcgen05(n=%d%s%s)", c->n, c->dense1 ? ",c1" : "", c->dense2 ? ",c2" : "");
+    else if (!c->small)
         snprintf(buf, buflen, "tiled-sparse(n=%d)", c->n);
     else if (c->named_id >= 0)
         snprintf(buf, buflen, "small-static(%s)", named_name(c->named_id));

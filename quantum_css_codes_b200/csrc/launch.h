@@ -31,6 +31,13 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes,
                                   uint32_t* s_planes, int64_t s_stride, int64_t words,
                                   uint32_t tail_mask, cudaStream_t stream);
 
+// ---- dense syndrome on tensor cores (dense_kernels.cu) ---------------------------------------
+size_t dense_h_bytes(int m, int n);
+void dense_h_layout(int m, int n, const uint8_t* H, uint8_t* out);      // host-side operand layout
+cudaError_t launch_syndrome_mma(const uint8_t* hq, int m, int n, const uint32_t* e_planes, int64_t e_stride,
+                                uint32_t* s_planes, int64_t s_stride, int64_t words, uint32_t tail_mask,
+                                cudaStream_t stream);
+
 // ---- batched GF(2) Gauss-Jordan (gf2_kernels.cu) --------------------------------------------
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);

@@ -234,6 +234,26 @@ def test_tiled_syndromes_random_sparse(n, m, row_w, shots):
         assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(mats[which - 1], errs))
 
 
+@pytest.mark.parametrize("m,n,shots", [(300, 700, 1000), (1024, 2048, 4096), (130, 4100, 257), (256, 512, 33)])
+def test_dense_syndromes_tensor_core_and_lop3_paths(m, n, shots, monkeypatch):
+    """Dense random H: the tcgen05 int8 MMA kernel (K1') and the bit-sliced kernel give the reference's
+    np.mod(np.matmul(H, e), 2) bit for bit."""
+    rng = np.random.default_rng(m * 7 + n)
+    h1 = rng.integers(0, 2, size=(m, n))
+    h2 = rng.integers(0, 2, size=(m // 2 + 1, n))
+    errs = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+    want = {1: omc.syndromes_batch(h1, errs), 2: omc.syndromes_batch(h2, errs)}
+    for force, prefix in (("1", "dense-tcgen05"), ("0", "tiled-sparse")):
+        monkeypatch.setenv("QCSS_DENSE", force)
+        code = SyndromeCode(h1, h2)
+        assert code.device.kernel_name().startswith(prefix)
+        for which in (1, 2):
+            assert np.array_equal(code.syndromes(errs, which), want[which]), (force, which)
+    monkeypatch.delenv("QCSS_DENSE")
+    auto = SyndromeCode(h1, h2)
+    assert auto.device.kernel_name().startswith("dense-tcgen05" if m * n >= 256 * 512 else "tiled-sparse")
+
+
 def test_error_paths():
     code, _ = pair("steane")
     with pytest.raises(ValueError):

@@ -89,6 +89,33 @@ def probe_hgp(shots):
     torch.cuda.empty_cache()
 
 
+def probe_dense(shots, m=1024, n=2048):
+    """C4-dense: H = a random dense 1024 x 2048 matrix; tcgen05 int8 MMA vs the bit-sliced kernel."""
+    rng = np.random.default_rng(5)
+    h = rng.integers(0, 2, size=(m, n))
+    stride = ((shots + 127) // 128) * 2
+    stream = torch.cuda.current_stream().cuda_stream
+    e = torch.randint(-2**62, 2**62, (n, stride), dtype=torch.int64, device="cuda")
+    s = torch.empty((m, stride), dtype=torch.int64, device="cuda")
+    ref = None
+    for force in ("1", "0"):
+        os.environ["QCSS_DENSE"] = force
+        dev = SyndromeCode(h, h[:8]).device
+        n_shots = shots if force == "1" else min(shots, 1 << 18)
+        med, best = timed(lambda: dev.syndrome_dev(1, e.data_ptr(), stride, n_shots, s.data_ptr(), stride, stream),
+                          warmup=1, iters=3)
+        chk = int(s[:, : n_shots // 64].sum().item())
+        if ref is None:
+            ref = s[:, : (1 << 18) // 64].clone()
+            same = None
+        else:
+            same = bool(torch.equal(ref[:, : n_shots // 64], s[:, : n_shots // 64]))
+        emit(probe="dense_syndrome", kernel=dev.kernel_name(), m=m, n=n, shots=n_shots, ms=med, ms_best=best,
+             shots_per_s=n_shots / (med / 1e3), int_ops_per_s=2.0 * m * n * n_shots / (med / 1e3),
+             matches_other_path=same, checksum=chk)
+    del os.environ["QCSS_DENSE"]
+
+
 def probe_gf2(batch, m=1024, n=2048):
     lib = _native.load()
     words = n // 64
@@ -124,6 +151,8 @@ def main():
             probe_decode(name, big // 4, p=0.05)
     if only is None or "hgp" in only:
         probe_hgp(1 << 22 if args.quick else 100_000_000)
+    if only is None or "dense" in only:
+        probe_dense(1 << 18 if args.quick else 1 << 21)
     if only is None or "gf2" in only:
         probe_gf2(64 if args.quick else 4096)
         probe_gf2(4096, 256, 512)

@@ -96,25 +96,41 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
 
     // expansion role of this thread: qubit kq of the chunk, shot words 2*wp, 2*wp+1 of the tile
     const int kq = tid % kKC, wp = tid / kKC;                 // 64 x 4
+    constexpr int kAhead = 2;                                 // H blocks are fetched two chunks ahead
 
-    for (int kc = 0; kc < kchunks; ++kc) {
-        const int st = kc % kStages, use = kc / kStages;
-        uint8_t* sA = smem + (size_t)st * kStageBytes;
-        uint8_t* sB = sA + kABytes;
+    auto issue_a = [&](int c) {                               // contiguous 16 KB block of the pre-laid-out H
+        const int st = c % kStages, use = c / kStages;
         if (use > 0) mbar_wait_parity(&free_bar[st], (unsigned)((use - 1) & 1));
-        // ---- A: contiguous 16 KB block of the pre-laid-out H ------------------------------------
-        const uint8_t* asrc = hq + ((size_t)mg * kchunks + kc) * kABytes;
+        uint8_t* sA = smem + (size_t)st * kStageBytes;
+        const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
         for (int i = tid; i < kABytes / 16; i += kMmaThreads) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
         }
+    };
+    auto load_bits = [&](int c) {                             // 64 shots of qubit c*64+kq
+        const int j = c * kKC + kq;
+        const int64_t w = w0 + 2 * wp;
+        uint2 bits = make_uint2(0u, 0u);
+        if (c < kchunks && j < n && w < e_stride) bits = __ldg(reinterpret_cast<const uint2*>(e + (int64_t)j * e_stride + w));
+        return bits;
+    };
+
+    for (int c = 0; c < kAhead && c < kchunks; ++c) {
+        issue_a(c);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        // ---- B: expand 64 shots of qubit kc*64+kq to bytes --------------------------------------
+    }
+    uint2 bits_next = load_bits(0);
+    for (int kc = 0; kc < kchunks; ++kc) {
+        const int st = kc % kStages;
+        uint8_t* sA = smem + (size_t)st * kStageBytes;
+        uint8_t* sB = sA + kABytes;
+        if (kc + kAhead < kchunks) issue_a(kc + kAhead);
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per iteration (possibly empty)
+        const uint2 bits = bits_next;
+        bits_next = load_bits(kc + 1);
+        // ---- B: expand 64 shots of qubit kc*64+kq to bytes (stage st was freed when its A was issued) ----
         {
-            const int j = kc * kKC + kq;
-            uint2 bits = make_uint2(0u, 0u);
-            const int64_t w = w0 + 2 * wp;
-            if (j < n && w < e_stride) bits = *reinterpret_cast<const uint2*>(e + (int64_t)j * e_stride + w);
             const uint32_t wv[2] = {bits.x, bits.y};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {                     // 4 groups of 16 shots
@@ -125,7 +141,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
                 *reinterpret_cast<uint4*>(sB + (size_t)(kq / 8) * (kNT / 16) * 128 + nb * 128 + (kq % 8) * 16) = bytes;
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");     // chunk kc's H block has landed
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         // ---- MMAs of this chunk: 2 row tiles x 2 K-steps of 32 ------------------------------------

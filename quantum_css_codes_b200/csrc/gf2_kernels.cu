@@ -105,8 +105,12 @@ k_gf2_rref(const uint64_t* __restrict__ in, int batch, int m, int n, uint64_t* _
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out, int32_t* rank,
                             int32_t* pivots, cudaStream_t stream) {
     if (batch <= 0 || m <= 0 || n <= 0) return cudaSuccess;
-    if (gf2_fast_supported(m, n) && getenv("QCSS_GF2_SIMPLE") == nullptr)
-        return launch_gf2_fast(in, batch, m, n, out, rank, pivots, stream);
+    if (getenv("QCSS_GF2_SIMPLE") == nullptr) {
+        // QCSS_GF2_V1 selects the first-generation blocked kernel (kept for A/B measurements)
+        if (gf2_m4r_supported(m, n) && getenv("QCSS_GF2_V1") == nullptr)
+            return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);
+        if (gf2_fast_supported(m, n)) return launch_gf2_fast(in, batch, m, n, out, rank, pivots, stream);
+    }
     const int W = (n + 63) >> 6;
     const size_t bytes = (size_t)m * W * sizeof(uint64_t);
     int dev = 0, sms = 0;

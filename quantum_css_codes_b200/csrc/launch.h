@@ -46,4 +46,9 @@ bool gf2_fast_supported(int m, int n);
 cudaError_t launch_gf2_fast(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
+// second generation (gf2_m4r.cu): one-warp bit-sliced panel, packed combination bytes; the default
+bool gf2_m4r_supported(int m, int n);
+cudaError_t launch_gf2_m4r(const uint64_t* in, int batch, int m, int n, uint64_t* out,
+                           int32_t* rank, int32_t* pivots, cudaStream_t stream);
+
 }  // namespace qcss

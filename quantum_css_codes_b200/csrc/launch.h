@@ -46,9 +46,14 @@ bool gf2_fast_supported(int m, int n);
 cudaError_t launch_gf2_fast(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
-// second generation (gf2_m4r.cu): one-warp bit-sliced panel, packed combination bytes; the default
+// second generation (gf2_m4r.cu): one-warp bit-sliced panel, packed combination bytes; QCSS_GF2_V2=1
 bool gf2_m4r_supported(int m, int n);
 cudaError_t launch_gf2_m4r(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
+
+// third generation (gf2_m4r2.cu): 512-column slabs, two matrices per SM, replay bytes through L2
+bool gf2_m4r2_supported(int m, int n);
+cudaError_t launch_gf2_m4r2(const uint64_t* in, int batch, int m, int n, uint64_t* out,
+                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
 }  // namespace qcss

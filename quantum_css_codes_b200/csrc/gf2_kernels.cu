@@ -106,9 +106,10 @@ cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_
                             int32_t* pivots, cudaStream_t stream) {
     if (batch <= 0 || m <= 0 || n <= 0) return cudaSuccess;
     if (getenv("QCSS_GF2_SIMPLE") == nullptr) {
-        // QCSS_GF2_V1 / QCSS_GF2_V2 select the earlier generations (kept for A/B measurements)
+        // QCSS_GF2_V1 / QCSS_GF2_V2 select the earlier generations (kept for A/B measurements and tests)
         const bool v1 = getenv("QCSS_GF2_V1") != nullptr, v2 = getenv("QCSS_GF2_V2") != nullptr;
-        if (gf2_m4r2_supported(m, n) && !v1 && !v2)
+        const bool v3 = getenv("QCSS_GF2_V3") != nullptr && m <= 1024;      // force the third generation
+        if ((gf2_m4r2_supported(m, n) || v3) && !v1 && !v2)
             return launch_gf2_m4r2(in, batch, m, n, out, rank, pivots, stream);
         if (gf2_m4r_supported(m, n) && !v1)
             return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);

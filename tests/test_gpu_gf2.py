@@ -68,6 +68,25 @@ def test_rref_structured(m, n):
     assert rank[2] <= 7 and rank[3] == 0
 
 
+@pytest.mark.parametrize("knob", ["QCSS_GF2_V1", "QCSS_GF2_V2", "QCSS_GF2_V3", "QCSS_GF2_SIMPLE"])
+def test_rref_every_kernel_generation(knob, monkeypatch):
+    """The dispatcher picks a kernel by shape; the knobs force each generation (gf2_fast, gf2_m4r,
+    gf2_m4r2, the general kernel) over small, ragged, rank-deficient and full-size shapes."""
+    monkeypatch.setenv(knob, "1")
+    rng = np.random.default_rng(len(knob))
+    for m, n in [(1, 1), (7, 70), (33, 31), (64, 200), (130, 1100), (300, 100), (640, 640), (1024, 1100)]:
+        mats = rng.integers(0, 2, size=(3, m, n), dtype=np.int64)
+        if m > 4:
+            mats[1, m - 1] = mats[1, 0] ^ mats[1, 2]
+            mats[2, :, n // 2] = 0
+            mats[2] *= (rng.random((m, n)) < 0.05)                   # sparse: strips with few pivots
+        out, rank, piv = bin_matrix.rref_batched(mats)
+        for b in range(3):
+            packed, pv = ogf2.rref_packed(ogf2.pack_rows(mats[b].astype(np.uint8)), n)
+            assert np.array_equal(out[b], ogf2.unpack_rows(packed, n)), (knob, m, n, b)
+            assert rank[b] == len(pv) and np.array_equal(piv[b, : rank[b]], pv)
+
+
 def test_rref_more_than_1024_rows_uses_general_kernel():
     rng = np.random.default_rng(77)
     mat = rng.integers(0, 2, size=(1100, 300), dtype=np.int64)

@@ -174,6 +174,7 @@ int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, 
     sp.m = m;
     sp.n = n;
     sp.max_row_weight = maxw;
+    sp.nnz = ptr[m];
     sp.row_ptr = (const int32_t*)d_ptr.p;
     sp.cols = (const uint16_t*)d_cols.p;
     return QCSS_OK;

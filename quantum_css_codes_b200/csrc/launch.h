@@ -23,7 +23,7 @@ int small_bucket_m(int mx, int mz);
 
 // ---- any-size sparse syndrome (tiled_kernels.cu) --------------------------------------------
 struct SparseRows {            // CSR of one parity-check matrix, device pointers
-    int m, n, max_row_weight;
+    int m, n, max_row_weight, nnz;
     const int32_t* row_ptr;    // [m + 1]
     const uint16_t* cols;      // [nnz]
 };

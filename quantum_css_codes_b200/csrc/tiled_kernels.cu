@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include <cstdlib>
 
 #include "launch.h"
@@ -303,55 +305,145 @@ template <int TW, int WP>
 cudaError_t launch_wide(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
                         int64_t words, uint32_t tail_mask, cudaStream_t stream);
 
-// ---- plane-split accumulate pipeline (default path for n x 128 B > one stage) -----------------------
+// ---- plane-split accumulate ring (default path for n x 128 B > one stage) --------------------------
 // 128-byte plane rows are what the memory system likes (64-byte rows run at about half the L2 request
-// rate), but n = 1600 planes x 128 B is a whole SM's shared memory, leaving no second stage.  So the
-// planes are split into P parts of <= pp planes; a tile is processed as P "part-tiles" that flow
-// through a two-stage cp.async ring, and every thread keeps the partial syndromes of its RPT row
-// chunks in registers across the parts of a tile (row i, 16-byte chunk q <-> thread (i % 128) * 8 + q).
-// Loads of part-tile k+1 are in flight while part-tile k is XORed.
+// rate), but n = 1600 planes x 128 B is a whole SM's shared memory.  So the planes are split into P
+// parts of <= pp planes; a tile is processed as P "part-tiles" that flow through an NST-deep cp.async
+// ring (NST - 1 part-tiles in flight while one is XORed, ONE block barrier per part-tile), and every
+// thread keeps the partial syndromes of its RPT row chunks in registers across the parts of a tile
+// (row i, 16-byte chunk q <-> thread (i % 128) * 8 + q).
+//
+// The XOR loop touches exactly the support: at kernel start the CSR rows are re-bucketed per part
+// into shared memory (poff[part][row] -> pent[], entries = local plane index * 8 = the plane row's
+// byte offset >> 4), so a part-tile costs one 128-byte shared-memory wavefront per support entry.
+// History (HGP-1600, B200): testing every entry against the part bounds in every part (two-stage
+// ring) 59 % of the HBM copy peak with 77 % of the tile time spent issuing instructions; sentinel-
+// padded per-part ELL, same ring: 61 % -- fewer instructions but 1.7x the shared-memory wavefronts.
+// With the XOR loop switched off (QCSS_RING_DBG=1: loads + stores only) the kernel runs at 4.29 TB/s,
+// with the loads switched off (QCSS_RING_DBG=2) at 6.24 TB/s-equivalent: the limit is the memory side
+// of n = 1600 separate 128-byte streams per SM, not the XOR work (profiles/r01_hgp_ring_ncu_summary.txt).
 constexpr int kSplitTW = 32;                  // words per plane row per tile: one 128-byte line
 constexpr int kSplitSlots = kWideThreads / 8; // 128 row slots x 8 chunks
 
 struct SplitShape {
     int parts;        // P
     int pp;           // planes per part
-    int blocked;      // experiment: input stored tile-major [tile][plane][32 words]
+    int nnz;          // support entries (capacity of pent)
+    int dbg;          // experiments: 1 = skip the XOR loop, 2 = skip the loads
 };
 
-template <int RPT, int WP>
+inline size_t split_csr_bytes(int m, SplitShape shape) {
+    return (((size_t)shape.parts * m + 2) * sizeof(uint16_t) + (size_t)(shape.nnz + 2) * sizeof(uint16_t) + 15) & ~(size_t)15;
+}
+inline size_t split_smem_bytes(int m, int nst, SplitShape shape) {
+    return (size_t)nst * shape.pp * kSplitTW * sizeof(uint32_t) + split_csr_bytes(m, shape);
+}
+
+template <int RPT, int NST>
 __global__ void __launch_bounds__(kWideThreads, 1)
-k_syndrome_split(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, int64_t e_stride,
-                 uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
+k_syndrome_ring(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, int64_t e_stride,
+                uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int wsum[32];
     constexpr int TW = kSplitTW, kQ = TW / 4;
-    const size_t stage_words = (size_t)shape.pp * TW;
-    uint32_t* const stage0 = reinterpret_cast<uint32_t*>(smem_raw);
-    uint16_t* const ell = reinterpret_cast<uint16_t*>(smem_raw + 2 * stage_words * sizeof(uint32_t));
+    const int pp = shape.pp, parts = shape.parts, m = h.m;
+    const uint32_t stage_bytes = (uint32_t)pp * TW * sizeof(uint32_t);
+    uint16_t* const poff = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NST * stage_bytes);   // [parts * m + 1]
+    uint16_t* const pent = poff + (size_t)parts * m + 2;                                         // [nnz]
     const int64_t tiles = (words + TW - 1) / TW;
     const int64_t e_chunks = e_stride / 4;
-    for (int idx = threadIdx.x; idx < h.m * WP; idx += kWideThreads) {
-        const int i = idx / WP, k = idx % WP;
-        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
-        ell[idx] = (beg + k < end) ? __ldg(h.cols + beg + k) : (uint16_t)0xFFFFu;
-    }
-    const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
-    const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t steps = my_tiles * shape.parts;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // ---- one-time setup: supports bucketed by part (count, scan, fill) ---------------------------
+    if (tid == 0) poff[0] = 0;
+    for (int i = tid; i < m; i += kWideThreads) {
+        int cnt[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) cnt[p] = 0;
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        for (int t = beg; t < end; ++t) {
+            const int p = __ldg(h.cols + t) / pp;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) cnt[u] += (u == p);
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if (p < parts) poff[1 + p * m + i] = (uint16_t)cnt[p];
+    }
+    __syncthreads();
+    {
+        const int L = parts * m, per = (L + kWideThreads - 1) / kWideThreads;
+        const int beg = tid * per < L ? tid * per : L, end = beg + per < L ? beg + per : L;
+        int sum = 0;
+        for (int x = beg; x < end; ++x) sum += poff[1 + x];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += t;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        int run = incl - sum + (warp ? wsum[warp - 1] : 0);
+        for (int x = beg; x < end; ++x) {
+            run += poff[1 + x];
+            poff[1 + x] = (uint16_t)run;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += kWideThreads) {
+        int fill[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) fill[p] = 0;
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        for (int t = beg; t < end; ++t) {
+            const int c = __ldg(h.cols + t);
+            const int p = c / pp;
+            int pos = 0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (u == p) pos = fill[u]++;
+            pent[poff[p * m + i] + pos] = (uint16_t)((c - p * pp) * (TW * 4 / 16));
+        }
+    }
+
+    const int q = tid % kQ, slot = tid / kQ;
+    const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t steps = my_tiles * parts;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    // issue: thread (slot, q) copies chunk q of planes slot, slot + 128, ... of part-tile `step`
     auto issue = [&](int64_t step) {
-        const int64_t t = blockIdx.x + (step / shape.parts) * gridDim.x;
-        const int part = (int)(step % shape.parts);
-        const int lo = part * shape.pp;
-        const int cnt = (h.n - lo) < shape.pp ? (h.n - lo) : shape.pp;
-        uint32_t* buf = stage0 + (size_t)(step & 1) * stage_words;
-        const int64_t c0 = t * (TW / 4);
-        for (int idx = threadIdx.x; idx < cnt * kQ; idx += kWideThreads) {
-            const int j = idx / kQ, qq = idx % kQ;
-            uint32_t* dst = buf + (size_t)j * TW + qq * 4;
-            if (shape.blocked) cp_async16(dst, e + ((int64_t)t * h.n + lo + j) * TW + qq * 4);
-            else if (c0 + qq < e_chunks) cp_async16(dst, e + (int64_t)(lo + j) * e_stride + (c0 + qq) * 4);
-            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        if (step < steps && shape.dbg != 2) {
+            const int64_t t = blockIdx.x + (step / parts) * gridDim.x;
+            const int part = (int)(step % parts);
+            const int lo = part * pp;
+            const int cnt = (h.n - lo) < pp ? (h.n - lo) : pp;
+            const uint32_t off0 = (uint32_t)(step % NST) * stage_bytes + (uint32_t)slot * (TW * 4) + q * 16;
+            const int64_t chunk = t * (TW / 4) + q;
+            if (chunk < e_chunks) {
+                const uint32_t* src = e + (int64_t)(lo + slot) * e_stride + chunk * 4;
+                const int64_t src_step = (int64_t)kSplitSlots * e_stride;
+                uint32_t dst = smem_base + off0;
+                for (int j = slot; j < cnt; j += kSplitSlots) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    src += src_step;
+                    dst += kSplitSlots * TW * 4;
+                }
+            } else {
+                for (int j = slot; j < cnt; j += kSplitSlots)
+                    *reinterpret_cast<uint4*>(smem_raw + off0 + (size_t)(j - slot) * TW * 4) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -359,45 +451,34 @@ k_syndrome_split(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e,
     uint4 acc[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) acc[r] = make_uint4(0u, 0u, 0u, 0u);
-    if (steps > 0) issue(0);
+#pragma unroll
+    for (int st = 0; st < NST - 1; ++st) issue(st);
     for (int64_t step = 0; step < steps; ++step) {
-        if (step + 1 < steps) {
-            issue(step + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const int part = (int)(step % shape.parts);
-        const uint32_t lo = (uint32_t)(part * shape.pp), cnt = (uint32_t)shape.pp;
-        const uint32_t* buf = stage0 + (size_t)(step & 1) * stage_words;
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");   // part-tile `step` has landed
+        __syncthreads();                       // ... for every thread; part-tile step - 1 is consumed (and pent is ready)
+        issue(step + NST - 1);                 // refill the slot consumed in the previous step
+        const int part = (int)(step % parts);
+        const uint8_t* buf = smem_raw + (size_t)(step % NST) * stage_bytes + q * 16;
+        const uint16_t* po = poff + (size_t)part * m;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int i = slot + r * kSplitSlots;
-            if (i < h.m) {
-#pragma unroll
-                for (int g = 0; g < WP / 8; ++g) {
-                    const uint4 idx = *reinterpret_cast<const uint4*>(ell + (size_t)i * WP + g * 8);
-                    const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t j = ((iw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) - lo;
-                        if (j < cnt) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(buf + (size_t)j * TW + q * 4);
-                            acc[r].x ^= v.x; acc[r].y ^= v.y; acc[r].z ^= v.z; acc[r].w ^= v.w;
-                        }
-                    }
+            if (i < m && shape.dbg != 1) {
+                const int o0 = po[i], o1 = po[i + 1];
+                for (int k = o0; k < o1; ++k) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(buf + ((uint32_t)pent[k] << 4));
+                    acc[r].x ^= v.x; acc[r].y ^= v.y; acc[r].z ^= v.z; acc[r].w ^= v.w;
                 }
             }
         }
-        if (part == shape.parts - 1) {
-            const int64_t t = blockIdx.x + (step / shape.parts) * gridDim.x;
+        if (part == parts - 1) {
+            const int64_t t = blockIdx.x + (step / parts) * gridDim.x;
             const int64_t wq = t * TW + q * 4;
             const bool ragged = wq + 4 > words - 1;
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const int i = slot + r * kSplitSlots;
-                if (i < h.m && wq < words) {
+                if (i < m && wq < words) {
                     uint32_t* dst = s + (int64_t)i * s_stride + wq;
                     if (!ragged) {
                         *reinterpret_cast<uint4*>(dst) = acc[r];
@@ -418,13 +499,84 @@ k_syndrome_split(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e,
                 acc[r] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int RPT, int NST>
+cudaError_t launch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                        int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream);
+
+// ---- L1-resident gather (experiment, QCSS_TILED_L1=1) ----------------------------------------------
+// No staging at all: thread (row slot, 16-byte chunk q) gathers the chunk of every plane in its rows'
+// supports straight from global memory with cached loads and relies on the SM's L1 (configured to its
+// maximum, ~200+ KB) to serve the 3-4 rows that share a plane; no barriers, no cp.async bookkeeping.
+template <int RPT, int WP>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_syndrome_l1(SparseRows h, const uint32_t* __restrict__ e, int64_t e_stride, uint32_t* __restrict__ s,
+              int64_t s_stride, int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_l1[];
+    uint16_t* const ell = reinterpret_cast<uint16_t*>(smem_l1);          // [m][WP]
+    constexpr int TW = kSplitTW, kQ = TW / 4;
+    for (int idx = threadIdx.x; idx < h.m * WP; idx += kWideThreads) {
+        const int i = idx / WP, k = idx % WP;
+        const int beg = __ldg(h.row_ptr + i), end = __ldg(h.row_ptr + i + 1);
+        ell[idx] = (beg + k < end) ? __ldg(h.cols + beg + k) : (uint16_t)0xFFFFu;
+    }
+    __syncthreads();
+    const int q = threadIdx.x % kQ, slot = threadIdx.x / kQ;
+    const int64_t tiles = (words + TW - 1) / TW;
+    const int64_t e_chunks = e_stride / 4;
+    const uint4* const e4 = reinterpret_cast<const uint4*>(e);
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t chunk = t * kQ + q;
+        const bool in = chunk < e_chunks;
+        const int64_t wq = t * TW + q * 4;
+        const bool ragged = wq + 4 > words - 1;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = slot + r * kSplitSlots;
+            if (i < h.m) {
+                uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int g = 0; g < WP / 8; ++g) {
+                    const uint4 idx = *reinterpret_cast<const uint4*>(ell + (size_t)i * WP + g * 8);
+                    const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t c = (iw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                        if (c != 0xFFFFu && in) {
+                            const uint4 v = __ldg(e4 + (int64_t)c * e_chunks + chunk);
+                            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+                        }
+                    }
+                }
+                if (wq < words) {
+                    uint32_t* dst = s + (int64_t)i * s_stride + wq;
+                    if (!ragged) {
+                        __stcs(reinterpret_cast<uint4*>(dst), acc);
+                    } else {
+                        uint32_t out[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int64_t w = wq + v;
+                            if (w >= words) out[v] = 0u;
+                            else if (w == words - 1) out[v] &= tail_mask;
+                        }
+                        if (wq + 4 <= s_stride)
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+                        else
+                            for (int v = 0; v < 4 && wq + v < s_stride; ++v) dst[v] = out[v];
+                    }
+                }
+            }
+        }
     }
 }
 
 template <int RPT, int WP>
-cudaError_t launch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
-                         int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream);
+cudaError_t launch_l1(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
+                      int64_t words, uint32_t tail_mask, cudaStream_t stream);
 
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -538,11 +690,11 @@ cudaError_t launch_wide(const SparseRows& h, const uint32_t* e, int64_t e_stride
     return cudaGetLastError();
 }
 
-template <int RPT, int WP>
-cudaError_t launch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
-                         int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
-    const size_t smem = 2 * (size_t)shape.pp * kSplitTW * sizeof(uint32_t) + (size_t)h.m * WP * sizeof(uint16_t);
-    cudaError_t err = cudaFuncSetAttribute(k_syndrome_split<RPT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int RPT, int NST>
+cudaError_t launch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                        int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    const size_t smem = split_smem_bytes(h.m, NST, shape);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_ring<RPT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return err;
     int sms = 0;
@@ -550,20 +702,36 @@ cudaError_t launch_split(const SparseRows& h, SplitShape shape, const uint32_t* 
     const int64_t tiles = (words + kSplitTW - 1) / kSplitTW;
     int64_t grid = sms < tiles ? sms : tiles;
     if (grid < 1) grid = 1;
-    k_syndrome_split<RPT, WP><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, shape, e, e_stride, s, s_stride,
-                                                                            words, tail_mask);
+    k_syndrome_ring<RPT, NST><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, shape, e, e_stride, s, s_stride,
+                                                                           words, tail_mask);
     return cudaGetLastError();
 }
 
-template <int WP>
-cudaError_t dispatch_split(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
-                           int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+template <int NST>
+cudaError_t dispatch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
+                          int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
     const int rpt = (h.m + kSplitSlots - 1) / kSplitSlots;
-    if (rpt <= 2) return launch_split<2, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if (rpt <= 4) return launch_split<4, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if (rpt <= 6) return launch_split<6, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
-    if (rpt <= 8) return launch_split<8, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
-    return launch_split<12, WP>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 2) return launch_ring<2, NST>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 4) return launch_ring<4, NST>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    if (rpt <= 6) return launch_ring<6, NST>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+    return launch_ring<8, NST>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+}
+
+template <int RPT, int WP>
+cudaError_t launch_l1(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s, int64_t s_stride,
+                      int64_t words, uint32_t tail_mask, cudaStream_t stream) {
+    const size_t smem = (size_t)h.m * WP * sizeof(uint16_t);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_l1<RPT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_syndrome_l1<RPT, WP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxL1)) != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
+    const int64_t tiles = (words + kSplitTW - 1) / kSplitTW;
+    int64_t grid = sms < tiles ? sms : tiles;
+    if (grid < 1) grid = 1;
+    k_syndrome_l1<RPT, WP><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, e, e_stride, s, s_stride, words, tail_mask);
+    return cudaGetLastError();
 }
 
 size_t tma_stage_bytes(int n, int tw) {
@@ -576,17 +744,37 @@ size_t tma_stage_bytes(int n, int tw) {
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s,
                                   int64_t s_stride, int64_t words, uint32_t tail_mask,
                                   cudaStream_t stream) {
-    // default: plane-split accumulate pipeline (128-byte rows, two-stage ring, partial sums in registers)
+    if (getenv("QCSS_TILED_L1") != nullptr && h.max_row_weight <= 8 && h.m <= 8 * kSplitSlots) {
+        const int rpt = (h.m + kSplitSlots - 1) / kSplitSlots;
+        if (rpt <= 2) return launch_l1<2, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+        if (rpt <= 4) return launch_l1<4, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+        if (rpt <= 6) return launch_l1<6, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+        return launch_l1<8, 8>(h, e, e_stride, s, s_stride, words, tail_mask, stream);
+    }
+    // default: plane-split accumulate ring (128-byte rows, NST-deep cp.async ring, partial sums in registers)
     if (getenv("QCSS_TILED_TMA") == nullptr && getenv("QCSS_TILED_NO_TMA") == nullptr &&
-        getenv("QCSS_TILED_WIDE") == nullptr && h.max_row_weight <= 16 && h.m <= 12 * kSplitSlots) {
-        const int wp = h.max_row_weight <= 8 ? 8 : 16;
-        const size_t cap = 226 * 1024, ell_bytes = (size_t)h.m * wp * 2;
-        for (int parts = 1; parts <= 64; ++parts) {
-            const int pp = (h.n + parts - 1) / parts;
-            if (2 * (size_t)pp * kSplitTW * 4 + ell_bytes <= cap) {
-                const SplitShape shape{parts, pp, getenv("QCSS_TILED_BLOCKED") != nullptr ? 1 : 0};
-                if (wp == 8) return dispatch_split<8>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
-                return dispatch_split<16>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+        getenv("QCSS_TILED_WIDE") == nullptr && h.m <= 8 * kSplitSlots && h.nnz <= 65000) {
+        const size_t cap = 226 * 1024;
+        const char* knob = getenv("QCSS_RING");            // "NST,parts" (experiments)
+        int want_nst = 0, want_parts = 0;
+        if (knob != nullptr) sscanf(knob, "%d,%d", &want_nst, &want_parts);
+        // Fewest, largest part-tiles win: measured on HGP-1600 (5e7 shots) NST,parts = 2,2: 4.03 TB/s,
+        // 3,3: 3.71, 4,4: 3.50, 4,8: 2.49 -- the per-part-tile barrier and row bookkeeping cost more than
+        // the extra part-tiles in flight buy.  Bulk L2 prefetch of the next round in per-plane runs
+        // (cp.async.bulk.prefetch.L2) was tried and lost 15 %.
+        const int nsts[3] = {2, 3, 4};
+        for (int a = 0; a < 3; ++a) {
+            const int nst = nsts[a];
+            if (want_nst != 0 && nst != want_nst) continue;
+            for (int parts = (want_parts ? want_parts : nst); parts <= 16; ++parts) {
+                const int pp = (h.n + parts - 1) / parts;
+                const SplitShape shape{parts, pp, h.nnz, getenv("QCSS_RING_DBG") ? atoi(getenv("QCSS_RING_DBG")) : 0};
+                if (pp * 8 <= 0xFFFF && split_smem_bytes(h.m, nst, shape) <= cap) {
+                    if (nst == 4) return dispatch_ring<4>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+                    if (nst == 3) return dispatch_ring<3>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+                    return dispatch_ring<2>(h, shape, e, e_stride, s, s_stride, words, tail_mask, stream);
+                }
+                if (want_parts) break;
             }
         }
     }

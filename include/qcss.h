@@ -143,6 +143,24 @@ QCSS_API int qcss_gf2_rref(const uint64_t* mats, int batch, int m, int n, uint64
 QCSS_API int qcss_gf2_rref_dev(const uint64_t* d_mats, int batch, int m, int n, uint64_t* d_out,
                       int32_t* d_rank, int32_t* d_pivots, void* stream);
 
+/* ---- K4 derived: batched null space and solve (no reference counterpart: bin_matrix.py stops at
+ *      the RREF; BASELINE config 5 names the null space).
+ *      nullspace: basis[batch][max_basis_rows][ceil(n/64)]; matrix b gets n - rank[b] basis vectors,
+ *      one per free column f in increasing order (x[f] = 1, x[pivot_i] = RREF[i][f], other free
+ *      variables 0), zero rows after them.  The host form fails with QCSS_ERR_INVALID when a matrix
+ *      needs more than max_basis_rows; the device form drops the extra rows and writes the needed
+ *      count to *d_overflow (device int, may be NULL; 0 = everything fitted).
+ *      solve: rhs[batch][ceil(m/64)] packed right-hand sides, x[batch][ceil(n/64)]; consistent[b] =
+ *      1 and x = the solution with every free variable 0, or consistent[b] = 0 and x = 0. -------- */
+QCSS_API int qcss_gf2_nullspace(const uint64_t* mats, int batch, int m, int n, int max_basis_rows, uint64_t* basis,
+                       int32_t* rank);
+QCSS_API int qcss_gf2_nullspace_dev(const uint64_t* d_mats, int batch, int m, int n, int max_basis_rows,
+                           uint64_t* d_basis, int32_t* d_rank, int32_t* d_overflow, void* stream);
+QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch, int m, int n, uint64_t* x,
+                   int32_t* consistent);
+QCSS_API int qcss_gf2_solve_dev(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
+                       int32_t* d_consistent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

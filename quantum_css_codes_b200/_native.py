@@ -88,6 +88,14 @@ PROTOTYPES = {
                                      ctypes.c_void_p, _c_i32p, _c_i32p]),
     "qcss_gf2_rref_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_gf2_nullspace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, _c_i32p]),
+    "qcss_gf2_nullspace_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_gf2_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, _c_i32p]),
+    "qcss_gf2_solve_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -298,6 +306,53 @@ def gf2_rref_bits(mats_u8):
     out, rank, piv = gf2_rref_packed(packed, n)
     bits = np.unpackbits(out.view(np.uint8).reshape(batch, m, words * 8), axis=2, bitorder="little")
     return np.ascontiguousarray(bits[:, :, :n]), rank, piv
+
+
+def pack_bits(bits_u8):
+    """(..., n) uint8 0/1 -> (..., ceil(n/64)) uint64, bit j of word w = element 64w + j."""
+    bits_u8 = np.asarray(bits_u8, dtype=np.uint8)
+    n = bits_u8.shape[-1]
+    words = (n + 63) // 64
+    padded = np.zeros(bits_u8.shape[:-1] + (words * 64,), dtype=np.uint8)
+    padded[..., :n] = bits_u8
+    return np.packbits(padded, axis=-1, bitorder="little").view(np.uint64).reshape(bits_u8.shape[:-1] + (words,))
+
+
+def unpack_bits(packed, n):
+    """Inverse of pack_bits."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    bits = np.unpackbits(packed.view(np.uint8).reshape(packed.shape[:-1] + (packed.shape[-1] * 8,)), axis=-1,
+                         bitorder="little")
+    return np.ascontiguousarray(bits[..., :n])
+
+
+def gf2_nullspace_packed(packed, n, max_basis_rows=None):
+    """(batch, m, words) packed matrices -> (basis (batch, rows, words), rank (batch,)): matrix b has
+    n - rank[b] basis vectors (free columns in increasing order), zero rows after them."""
+    lib = load()
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    batch, m, words = packed.shape
+    if words != (n + 63) // 64:
+        raise ValueError("words must be ceil(n / 64)")
+    rows = n if max_basis_rows is None else int(max_basis_rows)
+    basis = np.zeros((batch, rows, words), dtype=np.uint64)
+    rank = np.zeros(batch, dtype=np.int32)
+    check(lib.qcss_gf2_nullspace(_ptr(packed), batch, m, n, rows, _ptr(basis), rank.ctypes.data_as(_c_i32p)))
+    return basis, rank
+
+
+def gf2_solve_packed(packed, rhs_packed, n):
+    """(batch, m, words) matrices and (batch, ceil(m/64)) right-hand sides -> (x (batch, words), ok (batch,))."""
+    lib = load()
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    rhs_packed = np.ascontiguousarray(rhs_packed, dtype=np.uint64)
+    batch, m, words = packed.shape
+    if words != (n + 63) // 64 or rhs_packed.shape != (batch, (m + 63) // 64):
+        raise ValueError("bad packed shapes")
+    x = np.zeros((batch, words), dtype=np.uint64)
+    ok = np.zeros(batch, dtype=np.int32)
+    check(lib.qcss_gf2_solve(_ptr(packed), _ptr(rhs_packed), batch, m, n, _ptr(x), ok.ctypes.data_as(_c_i32p)))
+    return x, ok
 
 
 def host_alloc(nbytes):

@@ -97,31 +97,48 @@ def rank(mat):
 
 def null_space(mat):
     """Basis of {x : mat.x = 0 mod 2}, shape (n - rank, n): one vector per free column f in
-    increasing order, with x[f] = 1 and x[pivot_i] = RREF[i, f]."""
+    increasing order, with x[f] = 1 and x[pivot_i] = RREF[i, f] (built on the device,
+    ``qcss_gf2_nullspace``)."""
     mat = np.asarray(mat)
     m, n = mat.shape
-    out, rk, piv = _native.gf2_rref_bits(np.mod(mat, 2).astype(np.uint8)[None, :, :])
-    r = int(rk[0])
-    pivots = piv[0, :r]
-    free = np.setdiff1d(np.arange(n), pivots)
-    basis = np.zeros((len(free), n), dtype=np.int64)
-    basis[np.arange(len(free)), free] = 1
-    if r:
-        basis[:, pivots] = out[0][:r][:, free].T
-    return basis
+    basis, rk = null_space_batched(mat[None, :, :])
+    return basis[0][: n - int(rk[0])]
+
+
+def null_space_batched(mats):
+    """(batch, m, n) 0/1 integer array -> (basis (batch, n, n) int64, rank (batch,)); matrix b's basis is
+    ``basis[b, : n - rank[b]]``, the remaining rows are zero."""
+    mats = np.asarray(mats)
+    if mats.ndim != 3:
+        raise ValueError("expected a (batch, m, n) array")
+    n = mats.shape[2]
+    packed = _native.pack_bits(np.mod(mats, 2).astype(np.uint8))
+    basis, rk = _native.gf2_nullspace_packed(packed, n)
+    return _native.unpack_bits(basis, n).astype(np.int64), rk
+
+
+def null_space_packed_batched(packed, n, max_basis_rows=None):
+    """Packed form of ``null_space_batched`` (the C5 benchmark shape): (batch, m, ceil(n/64)) uint64 ->
+    (basis (batch, rows, ceil(n/64)) uint64, rank); ``rows`` defaults to n."""
+    return _native.gf2_nullspace_packed(packed, n, max_basis_rows)
 
 
 def solve(mat, rhs):
     """One solution of mat.x = rhs (mod 2) with every free variable 0, or None when the
-    system is inconsistent (RREF of the augmented matrix)."""
+    system is inconsistent (RREF of the augmented matrix on the device, ``qcss_gf2_solve``)."""
     mat = np.asarray(mat)
     m, n = mat.shape
-    aug = np.concatenate([np.mod(mat, 2), np.mod(np.asarray(rhs).reshape(m, 1), 2)], axis=1)
-    out, rk, piv = _native.gf2_rref_bits(aug.astype(np.uint8)[None, :, :])
-    r = int(rk[0])
-    pivots = piv[0, :r]
-    if r and pivots[-1] == n:
-        return None
-    x = np.zeros(n, dtype=np.int64)
-    x[pivots] = out[0][:r, n]
-    return x
+    x, ok = solve_batched(mat[None, :, :], np.asarray(rhs).reshape(1, m))
+    return x[0] if ok[0] else None
+
+
+def solve_batched(mats, rhs):
+    """(batch, m, n) matrices and (batch, m) right-hand sides -> (x (batch, n) int64, ok (batch,) bool)."""
+    mats = np.asarray(mats)
+    rhs = np.asarray(rhs)
+    if mats.ndim != 3 or rhs.shape != mats.shape[:2]:
+        raise ValueError("expected (batch, m, n) matrices and (batch, m) right-hand sides")
+    n = mats.shape[2]
+    packed = _native.pack_bits(np.mod(mats, 2).astype(np.uint8))
+    x, ok = _native.gf2_solve_packed(packed, _native.pack_bits(np.mod(rhs, 2).astype(np.uint8)), n)
+    return _native.unpack_bits(x, n).astype(np.int64), ok.astype(bool)

@@ -673,4 +673,79 @@ QCSS_API int qcss_gf2_rref(const uint64_t* mats, int batch, int m, int n, uint64
     return rc;
 }
 
+QCSS_API int qcss_gf2_nullspace_dev(const uint64_t* d_mats, int batch, int m, int n, int max_basis_rows,
+                           uint64_t* d_basis, int32_t* d_rank, int32_t* d_overflow, void* stream) {
+    if (batch < 0 || m < 0 || n < 0 || max_basis_rows < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!d_mats || (!d_basis && max_basis_rows > 0)) return fail(QCSS_ERR_INVALID, "NULL matrices");
+    QCSS_CUDA(launch_gf2_nullspace(d_mats, batch, m, n, max_basis_rows, d_basis, d_rank, d_overflow,
+                                   (cudaStream_t)stream));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_gf2_nullspace(const uint64_t* mats, int batch, int m, int n, int max_basis_rows, uint64_t* basis,
+                       int32_t* rank) {
+    if (batch < 0 || m < 0 || n < 0 || max_basis_rows < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!mats || (!basis && max_basis_rows > 0)) return fail(QCSS_ERR_INVALID, "NULL matrices");
+    const size_t W = (size_t)(n + 63) / 64, in_bytes = (size_t)batch * m * W * 8;
+    const size_t out_bytes = (size_t)batch * max_basis_rows * W * 8;
+    void *d_in = nullptr, *d_out = nullptr;
+    int32_t* d_rank = nullptr;
+    int32_t need = 0;
+    int rc = QCSS_OK;
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_rank, ((size_t)batch + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, mats, in_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = launch_gf2_nullspace((const uint64_t*)d_in, batch, m, n, max_basis_rows, (uint64_t*)d_out, d_rank,
+                                 d_rank + batch, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(&need, d_rank + batch, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_bytes) e = cudaMemcpy(basis, d_out, out_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rank) e = cudaMemcpy(rank, d_rank, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+        rc = fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "gf2_nullspace: %s", cudaGetErrorString(e));
+    else if (need > max_basis_rows)
+        rc = fail(QCSS_ERR_INVALID, "gf2_nullspace: a matrix needs %d basis rows, capacity is %d", need, max_basis_rows);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_rank);
+    return rc;
+}
+
+QCSS_API int qcss_gf2_solve_dev(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
+                       int32_t* d_consistent, void* stream) {
+    if (batch < 0 || m < 0 || n < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!d_mats || !d_rhs || !d_x) return fail(QCSS_ERR_INVALID, "NULL operands");
+    QCSS_CUDA(launch_gf2_solve(d_mats, d_rhs, batch, m, n, d_x, d_consistent, (cudaStream_t)stream));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch, int m, int n, uint64_t* x,
+                   int32_t* consistent) {
+    if (batch < 0 || m < 0 || n < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (batch == 0 || m == 0 || n == 0) return QCSS_OK;
+    if (!mats || !rhs || !x) return fail(QCSS_ERR_INVALID, "NULL operands");
+    const size_t W = (size_t)(n + 63) / 64, Wr = (size_t)(m + 63) / 64;
+    const size_t in_bytes = (size_t)batch * m * W * 8, rhs_bytes = (size_t)batch * Wr * 8, x_bytes = (size_t)batch * W * 8;
+    void *d_in = nullptr, *d_rhs = nullptr, *d_x = nullptr;
+    int32_t* d_ok = nullptr;
+    int rc = QCSS_OK;
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_rhs, rhs_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_x, x_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_ok, (size_t)batch * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, mats, in_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rhs, rhs, rhs_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = launch_gf2_solve((const uint64_t*)d_in, (const uint64_t*)d_rhs, batch, m, n, (uint64_t*)d_x, d_ok, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(x, d_x, x_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && consistent) e = cudaMemcpy(consistent, d_ok, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+        rc = fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "gf2_solve: %s", cudaGetErrorString(e));
+    cudaFree(d_in); cudaFree(d_rhs); cudaFree(d_x); cudaFree(d_ok);
+    return rc;
+}
+
 }  // extern "C"
+

@@ -56,4 +56,10 @@ bool gf2_m4r2_supported(int m, int n);
 cudaError_t launch_gf2_m4r2(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
+// null space / solve on top of the RREF (gf2_derive.cu)
+cudaError_t launch_gf2_nullspace(const uint64_t* d_mats, int batch, int m, int n, int max_rows, uint64_t* d_basis,
+                                 int32_t* d_rank, int32_t* d_overflow, cudaStream_t stream);
+cudaError_t launch_gf2_solve(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
+                             int32_t* d_consistent, cudaStream_t stream);
+
 }  // namespace qcss

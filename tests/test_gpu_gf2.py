@@ -126,6 +126,52 @@ def test_rank_nullspace_solve():
     assert bin_matrix.solve(np.array([[1, 1], [1, 1]]), np.array([0, 1])) is None
 
 
+@pytest.mark.parametrize("m,n", [(1, 1), (3, 70), (70, 3), (64, 128), (100, 333), (333, 100), (640, 1300)])
+def test_nullspace_and_solve_batched(m, n):
+    """Device null space / solve (qcss_gf2_nullspace, qcss_gf2_solve) against the oracle's RREF-derived
+    restatement: same basis vectors in the same order, H.N^T = 0, dim = n - rank, A.x = b."""
+    rng = np.random.default_rng(31 * m + n)
+    batch = 4
+    mats = rng.integers(0, 2, size=(batch, m, n), dtype=np.int64)
+    mats[1] *= (rng.random((m, n)) < 0.08)                           # sparse: scattered pivots
+    if m > 3:
+        mats[2, m - 1] = mats[2, 0] ^ mats[2, 1]
+    mats[3, :, : n // 2] = 0                                         # leading zero columns
+    basis, rank = bin_matrix.null_space_batched(mats)
+    for b in range(batch):
+        want = ogf2.null_space(mats[b])
+        assert rank[b] == ogf2.rank(mats[b])
+        assert np.array_equal(basis[b, : n - rank[b]], want), (m, n, b)
+        assert not basis[b, n - rank[b]:].any()
+        assert not np.any((mats[b] @ basis[b].T) % 2)
+    x0 = rng.integers(0, 2, size=(batch, n), dtype=np.int64)
+    rhs = np.einsum('bij,bj->bi', mats, x0) % 2
+    rhs_bad = rhs.copy()
+    x, ok = bin_matrix.solve_batched(mats, rhs)
+    for b in range(batch):
+        assert ok[b] and np.array_equal((mats[b] @ x[b]) % 2, rhs[b])
+        assert np.array_equal(x[b], ogf2.solve(mats[b], rhs[b]))
+    if m > 3:                                                        # row m-1 = row 0 + row 1: flip one side only
+        rhs_bad[2, m - 1] ^= 1
+        x, ok = bin_matrix.solve_batched(mats, rhs_bad)
+        assert not ok[2] and not x[2].any() and ok[0]
+        assert ogf2.solve(mats[2], rhs_bad[2]) is None
+
+
+def test_nullspace_capacity_error_and_c5_shape():
+    packed = codes.random_matrices_c5(2).copy()
+    packed[1, 7] = packed[1, 3] ^ packed[1, 4]                       # rank 1023 -> 1025 basis vectors
+    with pytest.raises(ValueError):
+        bin_matrix.null_space_packed_batched(packed, 2048, max_basis_rows=1024)
+    basis, rank = bin_matrix.null_space_packed_batched(packed, 2048, max_basis_rows=1025)
+    assert rank.tolist() == [1024, 1023]
+    for b in range(2):
+        bits = ogf2.unpack_rows(basis[b], 2048).astype(np.int64)
+        mat = ogf2.unpack_rows(packed[b], 2048).astype(np.int64)
+        assert not np.any((mat @ bits.T) % 2)
+        assert np.array_equal(bits[: 2048 - rank[b]], ogf2.null_space(mat))
+
+
 def test_codes_equal_and_transversal_gates(golden):
     """css_code.py:182-201, 838-844 through the GPU RREF."""
     assert css_code.codes_equal(golden["ce_a"], golden["ce_b"]) is True

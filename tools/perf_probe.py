@@ -134,6 +134,25 @@ def probe_gf2(batch, m=1024, n=2048):
          xor_word_ops_per_s=word_ops / (med / 1e3), full_rank=int((rank == min(m, n)).sum().item()))
 
 
+def probe_gf2_nullspace(batch, m=1024, n=2048):
+    lib = _native.load()
+    words = n // 64
+    rows = n - m + 8
+    mats = torch.randint(-2**62, 2**62, (batch, m, words), dtype=torch.int64, device="cuda")
+    basis = torch.empty((batch, rows, words), dtype=torch.int64, device="cuda")
+    rank = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _native.check(lib.qcss_gf2_nullspace_dev(mats.data_ptr(), batch, m, n, rows, basis.data_ptr(), rank.data_ptr(),
+                                                 ovf.data_ptr(), stream))
+    med, best = timed(run, warmup=1, iters=3)
+    emit(probe="gf2_nullspace", batch=batch, m=m, n=n, ms=med, ms_best=best, matrices_per_s=batch / (med / 1e3),
+         includes="RREF + rank + basis (n - m + 8 rows per matrix)", overflow=int(ovf.item()),
+         full_rank=int((rank == min(m, n)).sum().item()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -157,6 +176,7 @@ def main():
         probe_gf2(64 if args.quick else 4096)
         probe_gf2(4096, 256, 512)
         probe_gf2(2048, 768, 1600)
+        probe_gf2_nullspace(64 if args.quick else 4096)
 
 
 if __name__ == "__main__":

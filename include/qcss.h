@@ -46,6 +46,7 @@ extern "C" {
 #define QCSS_ERR_NOMEM       -4
 
 typedef struct qcss_code qcss_code;
+typedef struct qcss_table qcss_table;
 
 /* Tallies of one run: fail_x counts Lz.(e_x ^ c_x) = 1, fail_z counts
  * Lx.(e_z ^ c_z) = 1, fail_any their union, miss_* syndromes absent from the table. */
@@ -160,6 +161,19 @@ QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch
                    int32_t* consistent);
 QCSS_API int qcss_gf2_solve_dev(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
                        int32_t* d_consistent, void* stream);
+
+/* ---- GPU-assisted syndrome table: replaces the weight-layer search of css_code.syndrome_table
+ *      (css_code.py:715-735; bin_matrix.weight_w_vectors order, bin_matrix.py:57-72).
+ *      H: row-major 0/1 bytes of an m x n parity check, n <= 64, m <= 62.  Layers w = 0, 1, ... are
+ *      enumerated on the device; the first layer containing a repeated syndrome stops the search:
+ *      *t = w - 1 and the layer is discarded, exactly as the reference does.  *n_entries = table
+ *      size (fails with QCSS_ERR_NOMEM when it would exceed max_entries).  qcss_table_read copies
+ *      the entries out in the reference's insertion order (weight, then lexicographic support):
+ *      keys[i] = bin_matrix.vec_to_int(H.e mod 2) (big-endian), supports[i] = bit j set <=> e[j] = 1. */
+QCSS_API int qcss_table_build(int n, int m, const uint8_t* H, int64_t max_entries, qcss_table** out, int* t,
+                     int64_t* n_entries);
+QCSS_API int qcss_table_read(const qcss_table* table, int64_t* keys, uint64_t* supports);
+QCSS_API int qcss_table_destroy(qcss_table* table);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,11 @@ PROTOTYPES = {
                                      ctypes.c_void_p, _c_i32p, _c_i32p]),
     "qcss_gf2_rref_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_table_build": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_u8p, ctypes.c_int64,
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                        ctypes.POINTER(ctypes.c_int64)]),
+    "qcss_table_read": (ctypes.c_int, [ctypes.c_void_p, _c_i64p, ctypes.c_void_p]),
+    "qcss_table_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "qcss_gf2_nullspace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p, _c_i32p]),
     "qcss_gf2_nullspace_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -353,6 +358,26 @@ def gf2_solve_packed(packed, rhs_packed, n):
     ok = np.zeros(batch, dtype=np.int32)
     check(lib.qcss_gf2_solve(_ptr(packed), _ptr(rhs_packed), batch, m, n, _ptr(x), ok.ctypes.data_as(_c_i32p)))
     return x, ok
+
+
+def syndrome_table_arrays(parity_check_u8, max_entries=1 << 28):
+    """Device weight-layer search (qcss_table_build): returns (t, keys int64[count], supports uint64[count])
+    in the reference's insertion order."""
+    lib = load()
+    h = np.ascontiguousarray(parity_check_u8, dtype=np.uint8)
+    m, n = h.shape
+    handle = ctypes.c_void_p()
+    t = ctypes.c_int()
+    count = ctypes.c_int64()
+    check(lib.qcss_table_build(n, m, h.ctypes.data_as(_c_u8p), int(max_entries), ctypes.byref(handle),
+                               ctypes.byref(t), ctypes.byref(count)))
+    try:
+        keys = np.zeros(max(count.value, 1), dtype=np.int64)
+        supports = np.zeros(max(count.value, 1), dtype=np.uint64)
+        check(lib.qcss_table_read(handle, keys.ctypes.data_as(_c_i64p), _ptr(supports)))
+    finally:
+        lib.qcss_table_destroy(handle)
+    return t.value, keys[: count.value], supports[: count.value]
 
 
 def host_alloc(nbytes):

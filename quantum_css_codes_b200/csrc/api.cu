@@ -747,5 +747,37 @@ QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch
     return rc;
 }
 
+// ---- GPU-assisted syndrome table -----------------------------------------------
+
+QCSS_API int qcss_table_build(int n, int m, const uint8_t* H, int64_t max_entries, qcss_table** out, int* t,
+                     int64_t* n_entries) {
+    if (!H || !out || !t || !n_entries) return fail(QCSS_ERR_INVALID, "NULL argument");
+    if (n < 1 || n > 64) return fail(QCSS_ERR_UNSUPPORTED, "syndrome table on the device needs 1 <= n <= 64 (got %d)", n);
+    if (m < 1 || m > 62) return fail(QCSS_ERR_UNSUPPORTED, "syndrome table on the device needs 1 <= m <= 62 (got %d)", m);
+    if (max_entries < 1) return fail(QCSS_ERR_INVALID, "max_entries must be positive");
+    TableBuild* tb = nullptr;
+    const char* why = "";
+    const cudaError_t e = table_build(n, m, H, max_entries, &tb, &why);
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "table_build: %s %s",
+                    cudaGetErrorString(e), why);
+    *out = reinterpret_cast<qcss_table*>(tb);
+    *t = table_t(tb);
+    *n_entries = table_count(tb);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_table_read(const qcss_table* table, int64_t* keys, uint64_t* supports) {
+    if (!table || !keys || !supports) return fail(QCSS_ERR_INVALID, "NULL argument");
+    QCSS_CUDA(table_read(reinterpret_cast<const TableBuild*>(table), keys, supports));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_table_destroy(qcss_table* table) {
+    table_free(reinterpret_cast<TableBuild*>(table));
+    return QCSS_OK;
+}
+
 }  // extern "C"
+
 

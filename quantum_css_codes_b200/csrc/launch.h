@@ -62,4 +62,12 @@ cudaError_t launch_gf2_nullspace(const uint64_t* d_mats, int batch, int m, int n
 cudaError_t launch_gf2_solve(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
                              int32_t* d_consistent, cudaStream_t stream);
 
+// GPU-assisted syndrome table (table_kernels.cu)
+struct TableBuild;
+cudaError_t table_build(int n, int m, const uint8_t* H, int64_t max_entries, TableBuild** out, const char** why);
+int table_t(const TableBuild* tb);
+int64_t table_count(const TableBuild* tb);
+cudaError_t table_read(const TableBuild* tb, int64_t* keys, uint64_t* supports);
+void table_free(TableBuild* tb);
+
 }  // namespace qcss

@@ -121,6 +121,19 @@ def syndrome_table(parity_check):
     return n, table
 
 
+def syndrome_table_gpu(parity_check, max_entries=1 << 28):
+    """``syndrome_table`` with the weight layers enumerated and checked for collisions on the GPU
+    (``qcss_table_build``): same ``(t, table)``, same ``np.int64`` big-endian keys, same
+    insertion order (weight, then lexicographic support), values fresh dtype='int' vectors.  Needs
+    n <= 64 and m <= 62 (the reference's keys wrap at 64 bits anyway); raises ``NativeLibraryError``
+    without the CUDA library -- there is no silent fallback inside this function."""
+    parity_check = np.asarray(parity_check)
+    _, n = parity_check.shape
+    t, keys, supports = _native.syndrome_table_arrays(np.mod(parity_check, 2).astype(np.uint8), max_entries)
+    vecs = ((supports[:, None] >> np.arange(n, dtype=np.uint64)[None, :]) & np.uint64(1)).astype('int')
+    return t, dict(zip(keys, vecs))
+
+
 def codes_equal(parity_check_1, parity_check_2) -> bool:
     """Two parity checks span the same code iff their RREFs agree (css_code.py:838-844).
     Both RREFs run on the GPU in one batched call."""
@@ -146,11 +159,17 @@ class CSSCode:
     sampling -- runs in CUDA kernels on bit-plane batches through ``libqcss.so``.
     """
 
-    def __init__(self, parity_check_c1, parity_check_c2):
+    def __init__(self, parity_check_c1, parity_check_c2, table_builder=None):
+        """``table_builder`` (extension, not in the reference): ``"gpu"`` builds both syndrome tables
+        with the device weight-layer search (``syndrome_table_gpu``); the default is the host search
+        (``syndrome_table``), which needs no GPU.  Both give identical tables."""
         r_1, n_1 = parity_check_c1.shape
         r_2, n_2 = parity_check_c2.shape
         if n_1 != n_2:
             raise ValueError("C_1 and C_2 must have the same code word length")
+        if table_builder not in (None, "host", "gpu"):
+            raise ValueError("table_builder must be None, 'host' or 'gpu'")
+        build_table = syndrome_table_gpu if table_builder == "gpu" else syndrome_table
 
         h_1 = np.mod(np.array(parity_check_c1, dtype='int'), 2)
         h_2 = np.mod(np.array(parity_check_c2, dtype='int'), 2)
@@ -178,8 +197,8 @@ class CSSCode:
         self.r_2 = r_2
         self.parity_check_c1 = h_1
         self.parity_check_c2 = h_2
-        t_1, self._c1_syndromes = syndrome_table(h_1)
-        t_2, self._c2_syndromes = syndrome_table(h_2)
+        t_1, self._c1_syndromes = build_table(h_1)
+        t_2, self._c2_syndromes = build_table(h_2)
         self._t = min(t_1, t_2)
         self._transversal_cache = None
         self._device_code = None

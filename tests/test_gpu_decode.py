@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import css as ocss, montecarlo as omc, philox as ophilox
+import css_code
 from quantum_css_codes_b200 import CSSCode, SyndromeCode, codes, planes, _native
 
 pytestmark = pytest.mark.gpu
@@ -265,3 +266,41 @@ def test_error_paths():
     hx, hz = codes.hgp1600()
     with pytest.raises(_native.NativeLibraryError, match="lookup decode covers"):
         SyndromeCode(hx, hz).device.decode_planes(planes.pack_planes(np.zeros((4, 1600), dtype=np.uint8)), 4, 1)
+
+
+# ---- GPU-assisted syndrome table -------------------------------------------------
+
+def _same_table(a, b):
+    (ta, da), (tb, db) = a, b
+    assert ta == tb and len(da) == len(db)
+    for (ka, va), (kb, vb) in zip(da.items(), db.items()):           # insertion order matters
+        assert type(ka) is type(kb) is np.int64 and ka == kb
+        assert va.dtype == vb.dtype and np.array_equal(va, vb)
+
+
+@pytest.mark.parametrize("name", ["steane", "qrm15", "golay23"])
+def test_syndrome_table_gpu_named_codes(name, golden):
+    """Device weight-layer search == host search == the reference's captured tables
+    (css_code.py:715-735), including dict order and key type."""
+    host = css_code.CSSCode(*[np.array(h) for h in getattr(codes, name)()])
+    dev = css_code.CSSCode(*[np.array(h) for h in getattr(codes, name)()], table_builder="gpu")
+    assert dev.t == host.t == int(golden[f"{name}_nkt"][2])
+    for which, tag in (("_c1_syndromes", "c1"), ("_c2_syndromes", "c2")):
+        _same_table((host.t, getattr(host, which)), (dev.t, getattr(dev, which)))
+        table = getattr(dev, which)
+        assert np.array_equal(np.array(list(table.keys())), golden[f"{name}_{tag}_keys"])
+        assert np.array_equal(np.array(list(table.values())), golden[f"{name}_{tag}_vals"])
+    for h in (host.parity_check_c1, host.parity_check_c2):
+        _same_table(css_code.syndrome_table(h), css_code.syndrome_table_gpu(h))
+
+
+def test_syndrome_table_gpu_larger_codes():
+    rng = np.random.default_rng(2026)
+    cases = [rng.integers(0, 2, size=(18, 40)), rng.integers(0, 2, size=(30, 52)),
+             np.concatenate([np.eye(24, dtype=np.int64), rng.integers(0, 2, size=(24, 12))], axis=1),
+             np.ones((1, 5), dtype=np.int64), np.eye(6, dtype=np.int64)]
+    for h in cases:
+        _same_table(css_code.syndrome_table(h), css_code.syndrome_table_gpu(h))
+    assert css_code.syndrome_table_gpu(np.eye(6, dtype=np.int64))[0] == 6        # no collision at all: t = n
+    with pytest.raises(MemoryError):
+        css_code.syndrome_table_gpu(np.eye(20, dtype=np.int64), max_entries=1000)

@@ -99,6 +99,18 @@ QCSS_API int qcss_code_destroy(qcss_code* code);
 /* Human-readable name of the kernel family the code dispatches to (tests). */
 QCSS_API int qcss_code_kernel_name(const qcss_code* code, char* buf, int buflen);
 
+/* Kernel specialisation for one code: the static kernel family (H, L and the m <= 5 decode truth tables
+ * as compile-time constants -- what runs at the HBM roofline) for ANY decodable code, not only the
+ * descriptors built into the library.  qcss_code_spec_source writes the CUDA translation unit (*needed
+ * = bytes incl. the terminator; call with buf = NULL to size it); compile it for sm_100a with
+ *     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr
+ *          -Xcompiler -fPIC -shared -I <quantum_css_codes_b200/csrc> spec.cu -o spec.so
+ * and hand the shared object to qcss_code_load_specialized; the code's decode / Monte-Carlo launches
+ * then use it (qcss_code_kernel_name reports "small-static(jit:<tag>)").  Results are bit-identical to
+ * the generic kernels. */
+QCSS_API int qcss_code_spec_source(const qcss_code* code, char* buf, int64_t cap, int64_t* needed);
+QCSS_API int qcss_code_load_specialized(qcss_code* code, const char* so_path, const char* tag);
+
 /* ---- K1 syndrome: replaces np.mod(np.matmul(parity_check, e), 2), css_code.py:728 ------- */
 QCSS_API int qcss_syndrome(qcss_code* code, int which, const uint64_t* e_planes, int64_t e_stride,
                   int64_t shots, uint64_t* s_planes, int64_t s_stride);

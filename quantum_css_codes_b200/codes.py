@@ -84,3 +84,38 @@ def random_matrices_c5(count, m=1024, n=2048, seed=5, offset=0):
             left -= step
     raw = rng.integers(0, 256, size=(count, m, n // 8), dtype=np.uint8)
     return raw.view(np.uint64).reshape(count, m, n // 64)
+
+
+def shor9():
+    """Shor [[9,1,3]] as a CSS code: H1 (X-type generators, 2 rows of weight 6), H2 (Z-type pairs, 6 rows)."""
+    hx = np.zeros((2, 9), dtype=np.int64)
+    hx[0, 0:6] = 1
+    hx[1, 3:9] = 1
+    hz = np.zeros((6, 9), dtype=np.int64)
+    for b in range(3):
+        hz[2 * b, [3 * b, 3 * b + 1]] = 1
+        hz[2 * b + 1, [3 * b + 1, 3 * b + 2]] = 1
+    return hx, hz
+
+
+def rotated_surface(d):
+    """Rotated surface code [[d^2, 1, d]] (d odd): (d^2 - 1)/2 X-type and Z-type checks, weight 4 in the bulk
+    and weight 2 on the boundary.  Returns (HX, HZ) for ``CSSCode(HX, HZ)``."""
+    if d % 2 == 0 or d < 3:
+        raise ValueError("d must be odd and >= 3")
+    hx, hz = [], []
+    for i in range(-1, d):
+        for j in range(-1, d):
+            cells = [(a, b) for a in (i, i + 1) for b in (j, j + 1) if 0 <= a < d and 0 <= b < d]
+            x_type = (i + j) % 2 == 0
+            if len(cells) == 2:
+                horizontal_edge = i in (-1, d - 1)              # top / bottom boundary
+                if horizontal_edge != x_type:
+                    continue
+            elif len(cells) != 4:
+                continue
+            row = np.zeros(d * d, dtype=np.int64)
+            for a, b in cells:
+                row[a * d + b] = 1
+            (hx if x_type else hz).append(row)
+    return np.array(hx), np.array(hz)

@@ -1,6 +1,7 @@
 // C ABI of libqcss.so (include/qcss.h): code objects, argument checking, launches, and the
 // host-buffer entry points that stream caller memory through the GPU.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -8,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/qcss.h"
@@ -65,6 +67,10 @@ struct qcss_code {
     uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
     uint32_t lmask_x = 0, lmask_z = 0;
     int named_id = -1;
+    // kernels compiled for THIS code (qcss_code_spec_source -> nvcc -> qcss_code_load_specialized)
+    void* spec_dl = nullptr;
+    int (*spec_launch)(const void* small_launch, void* stream) = nullptr;
+    char spec_tag[32] = "";
     DevBuf fm_x, fm_z, co_x, co_z, e32_x, e32_z;      // lookup tables
     SparseRows sp1{}, sp2{};            // CSR of H1 / H2 for the tiled kernel
     DevBuf sp1_ptr, sp1_cols, sp2_ptr, sp2_cols;
@@ -79,6 +85,12 @@ struct qcss_code {
 };
 
 namespace {
+
+// static kernels of a matching descriptor, kernels compiled for this code, or the generic ones
+cudaError_t launch_small_any(const qcss_code* c, const SmallLaunch& l, cudaStream_t stream) {
+    if (c->spec_launch != nullptr && l.named_id < 0) return (cudaError_t)c->spec_launch(&l, stream);
+    return launch_small(l, stream);
+}
 
 uint32_t tail_mask_for(int64_t shots) {
     const int r = (int)(shots & 31);
@@ -268,7 +280,7 @@ int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStr
     l.io = make_io(io, shots);
     l.named_id = c->named_id;
     l.sample = false;
-    QCSS_CUDA(launch_small(l, stream));
+    QCSS_CUDA(launch_small_any(c, l, stream));
     return QCSS_OK;
 }
 
@@ -303,7 +315,7 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
     l.io.thr = thr;
     l.named_id = c->named_id;
     l.sample = true;
-    QCSS_CUDA(launch_small(l, stream));
+    QCSS_CUDA(launch_small_any(c, l, stream));
     return QCSS_OK;
 }
 
@@ -328,7 +340,7 @@ int launch_syndrome(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stri
         l.io = make_io(&io, shots);
         l.named_id = c->named_id;
         l.sample = false;
-        QCSS_CUDA(launch_small(l, stream));
+        QCSS_CUDA(launch_small_any(c, l, stream));
         return QCSS_OK;
     }
     if ((which == 1) ? c->dense1 : c->dense2) {
@@ -440,6 +452,7 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
     c->buf_a.release(); c->buf_b.release(); c->buf_c.release(); c->buf_d.release(); c->buf_e.release();
     c->tally.release();
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->spec_dl) dlclose(c->spec_dl);
     delete c;
     return QCSS_OK;
 }
@@ -452,6 +465,8 @@ QCSS_API int qcss_code_kernel_name(const qcss_code* c, char* buf, int buflen) {
         snprintf(buf, buflen, "tiled-sparse(n=%d)", c->n);
     else if (c->named_id >= 0)
         snprintf(buf, buflen, "small-static(%s)", named_name(c->named_id));
+    else if (c->spec_launch != nullptr)
+        snprintf(buf, buflen, "small-static(jit:%s)", c->spec_tag);
     else
         snprintf(buf, buflen, "small-generic(nb=%d,mb=%d)", c->n <= 16 ? 16 : 32,
                  small_bucket_m(c->side_x.m, c->side_z.m));
@@ -780,4 +795,72 @@ QCSS_API int qcss_table_destroy(qcss_table* table) {
 
 }  // extern "C"
 
+// ---- per-code kernel specialisation -------------------------------------------------------------
+// The static kernel family (H, L and the m <= 5 truth tables as compile-time constants) is not limited
+// to the three descriptors built into the library: qcss_code_spec_source writes the translation unit
+// for THIS code (the same descriptor layout tools/gen_named_codes.py emits), the host compiles it with
+// nvcc for sm_100a into a shared object, and qcss_code_load_specialized routes the code's launches to it.
 
+namespace {
+
+void emit_side(std::string& out, const char* name, const GenericSide& s, const uint32_t* rows, uint32_t lmask) {
+    const bool sliced = s.m <= kSlicedM;
+    const int mb = sliced ? s.m : (s.m <= 8 ? 8 : 16);
+    char line[256];
+    out += "struct "; out += name; out += " {\n";
+    snprintf(line, sizeof(line), "    static constexpr int N = %d, M = %d, MB = %d;\n", s.n, s.m, mb); out += line;
+    snprintf(line, sizeof(line), "    static constexpr bool kSliced = %s, kHasMiss = %s;\n", sliced ? "true" : "false",
+             s.has_miss ? "true" : "false"); out += line;
+    snprintf(line, sizeof(line), "    static constexpr uint32_t kL = 0x%xu, kTtFlip = 0x%xu, kTtMiss = 0x%xu;\n", lmask,
+             sliced ? s.tt_flip : 0u, sliced ? s.tt_miss : 0u); out += line;
+    out += "    QCSS_HD static constexpr uint32_t row(int t) {\n        constexpr uint32_t r[MB] = {";
+    for (int t = 0; t < mb; ++t) { snprintf(line, sizeof(line), "%s0x%xu", t ? ", " : "", t < s.m ? rows[t] : 0u); out += line; }
+    out += "};\n        return r[t];\n    }\n";
+    out += "    QCSS_HD static constexpr uint32_t tt_corr(int j) {\n        constexpr uint32_t r[N] = {";
+    for (int j = 0; j < s.n; ++j) { snprintf(line, sizeof(line), "%s0x%xu", j ? ", " : "", sliced ? s.tt_corr[j] : 0u); out += line; }
+    out += "};\n        return r[j];\n    }\n};\n\n";
+}
+
+}  // namespace
+
+extern "C" {
+
+QCSS_API int qcss_code_spec_source(const qcss_code* c, char* buf, int64_t cap, int64_t* needed) {
+    if (!c || !needed) return fail(QCSS_ERR_INVALID, "bad arguments");
+    if (!c->small || c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
+        return fail(QCSS_ERR_UNSUPPORTED, "specialisation needs a decodable code (n <= %d, m <= %d, both tables)", kMaxN, kMaxM);
+    std::string out = "// GENERATED by qcss_code_spec_source -- kernels specialised for one code.\n"
+                      "#include \"small_common.cuh\"\n\nnamespace qcss {\nnamespace spec {\nnamespace {   // internal linkage: "
+                      "several specialised objects can live in one process\n\n";
+    emit_side(out, "Spec_X", c->side_x, c->rows_x, c->lmask_x);
+    emit_side(out, "Spec_Z", c->side_z, c->rows_z, c->lmask_z);
+    out += "}  // namespace\n}  // namespace spec\n}  // namespace qcss\n\n"
+           "extern \"C\" __attribute__((visibility(\"default\"))) int qcss_spec_abi(void) {\n"
+           "    return (int)sizeof(qcss::SmallLaunch) * 1000 + (int)(sizeof(qcss::GenericSide) % 1000);\n}\n"
+           "extern \"C\" __attribute__((visibility(\"default\"))) int qcss_spec_launch(const void* l, void* stream) {\n"
+           "    return (int)qcss::small::launch_named<qcss::spec::Spec_X, qcss::spec::Spec_Z>(\n"
+           "        *static_cast<const qcss::SmallLaunch*>(l), static_cast<cudaStream_t>(stream));\n}\n";
+    *needed = (int64_t)out.size() + 1;
+    if (buf != nullptr && cap >= *needed) memcpy(buf, out.c_str(), out.size() + 1);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_code_load_specialized(qcss_code* c, const char* so_path, const char* tag) {
+    if (!c || !so_path) return fail(QCSS_ERR_INVALID, "bad arguments");
+    void* dl = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return fail(QCSS_ERR_INVALID, "cannot load %s: %s", so_path, dlerror());
+    auto abi = reinterpret_cast<int (*)(void)>(dlsym(dl, "qcss_spec_abi"));
+    auto fn = reinterpret_cast<int (*)(const void*, void*)>(dlsym(dl, "qcss_spec_launch"));
+    const int want = (int)sizeof(SmallLaunch) * 1000 + (int)(sizeof(GenericSide) % 1000);
+    if (!abi || !fn || abi() != want) {
+        dlclose(dl);
+        return fail(QCSS_ERR_INVALID, "%s was not built against this library's headers", so_path);
+    }
+    if (c->spec_dl) dlclose(c->spec_dl);
+    c->spec_dl = dl;
+    c->spec_launch = fn;
+    snprintf(c->spec_tag, sizeof(c->spec_tag), "%s", tag ? tag : "");
+    return QCSS_OK;
+}
+
+}  // extern "C"

@@ -270,8 +270,12 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
                     sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
                                      xe[v], ze[v]);
                 if constexpr (!FAST) {
-                    if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xe);
-                    if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, ze);
+                    // padding bits (past the last shot) are written as zero, whatever the unit width
+                    uint32_t xo[VEC], zo[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { xo[v] = xe[v] & valid[v]; zo[v] = ze[v] & valid[v]; }
+                    if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xo);
+                    if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, zo);
                 }
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {

@@ -285,6 +285,13 @@ class CSSCode:
                 self._c1_syndromes, self._c2_syndromes)
         return self._device_code
 
+    def specialize(self):
+        """Compile and attach decode kernels specialised for this code (``specialize.py``): the static
+        family that runs Steane / QRM-15 / Golay-23 at the HBM roofline, for any code with n <= 32 and
+        m <= 16.  One nvcc run per distinct code, cached on disk.  Returns the kernel family name."""
+        from . import specialize as _spec
+        return _spec.specialize(self.device)
+
     def syndromes(self, errors, which):
         """Batched ``np.mod(np.matmul(parity_check, e), 2)`` (css_code.py:728) for a
         (shots, n) 0/1 array; returns (shots, m) uint8."""

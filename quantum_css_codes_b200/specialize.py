@@ -1,0 +1,71 @@
+"""
+Per-code kernel specialisation: compile the static decode kernels (H, L and the m <= 5 truth tables as
+compile-time constants) for ONE code and attach them to its device object.
+
+    code = CSSCode(h1, h2); code.specialize()           # "small-static(jit:<hash>)"
+
+The library writes the translation unit (``qcss_code_spec_source``), nvcc builds it for sm_100a into
+``quantum_css_codes_b200/jit/qcss_spec_<hash>.so`` (cached by the hash of the source and of the kernel
+headers), and ``qcss_code_load_specialized`` routes the code's launches to it.  The three descriptors built
+into the library (Steane, QRM-15, Golay-23) are the same mechanism run ahead of time.
+"""
+
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+
+from . import _native
+from . import build as _build
+
+JIT_DIR = os.path.join(_build.HERE, "jit")
+_HEADERS = ("small_common.cuh", "decode.cuh", "core.cuh", "launch.h")
+
+
+def spec_source(handle):
+    lib = _native.load()
+    needed = ctypes.c_int64()
+    _native.check(lib.qcss_code_spec_source(handle, None, 0, ctypes.byref(needed)))
+    buf = ctypes.create_string_buffer(needed.value)
+    _native.check(lib.qcss_code_spec_source(handle, buf, needed.value, ctypes.byref(needed)))
+    return buf.value.decode()
+
+
+def _headers_digest():
+    h = hashlib.sha1()
+    for name in _HEADERS:
+        with open(os.path.join(_build.CSRC, name), "rb") as fh:
+            h.update(fh.read())
+    return h
+
+
+def build_spec(source):
+    """Compile one specialised translation unit; returns (path of the shared object, tag)."""
+    digest = _headers_digest()
+    digest.update(source.encode())
+    tag = digest.hexdigest()[:12]
+    os.makedirs(JIT_DIR, exist_ok=True)
+    so_path = os.path.join(JIT_DIR, f"qcss_spec_{tag}.so")
+    if os.path.exists(so_path):
+        return so_path, tag
+    with tempfile.TemporaryDirectory(dir=JIT_DIR) as tmp:
+        src = os.path.join(tmp, "spec.cu")
+        with open(src, "w") as fh:
+            fh.write(source)
+        out = os.path.join(tmp, "spec.so")
+        cmd = [_build.nvcc(), *_build.ARCH, "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+               "-shared", "-I", _build.CSRC, src, "-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for the specialised kernels:\n{res.stdout}\n{res.stderr}")
+        os.replace(out, so_path)                       # atomic: concurrent builders race benignly
+    return so_path, tag
+
+
+def specialize(device_code):
+    """Build (or reuse) and attach the specialised kernels; returns the kernel family name."""
+    lib = _native.load()
+    so_path, tag = build_spec(spec_source(device_code.handle))
+    _native.check(lib.qcss_code_load_specialized(device_code.handle, so_path.encode(), tag.encode()))
+    return device_code.kernel_name()

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (libqcss.so via ctypes),
 against the oracle on the same inputs.  Bit-exact everywhere (integer work)."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -148,6 +150,66 @@ def test_generic_kernels_partial_tables(n, m1, m2):
     got = dev.decode_xz_planes(planes.pack_planes(ex), planes.pack_planes(ez), shots)
     assert got["fail_any"] == int((tall[2]["flip"] | tall[1]["flip"]).sum())
     assert got["miss_x"] == int(tall[2]["miss"].sum()) and got["miss_z"] == int(tall[1]["miss"].sum())
+
+
+@pytest.mark.parametrize("n,m1,m2", [(5, 2, 2), (12, 5, 4), (20, 3, 12), (32, 16, 9), (17, 8, 8)])
+def test_specialized_kernels_match_generic_and_oracle(n, m1, m2):
+    """qcss_code_spec_source -> nvcc -> qcss_code_load_specialized: kernels compiled for one code must give
+    the oracle's bits on every output (shared inputs) and the generic kernels' tallies on the fused
+    Philox run (which has no oracle for random tables beyond the sampler itself)."""
+    from quantum_css_codes_b200 import specialize
+    rng = np.random.default_rng(n * 100 + m1)
+    sides = {}
+    for which, m in ((1, m1), (2, m2)):
+        h = rng.integers(0, 2, size=(m, n))
+        lrow = rng.integers(0, 2, size=n)
+        keys = rng.permutation(1 << m)[: max(1, (1 << m) * 2 // 3)]
+        sides[which] = (h, {int(k): rng.integers(0, 2, size=n) for k in keys}, lrow[None, :])
+    make = lambda: _native.DeviceCode(n, sides[1][0], sides[2][0], sides[1][2][0], sides[2][2][0], sides[1][1], sides[2][1])
+    generic, dev = make(), make()
+    assert specialize.specialize(dev).startswith("small-static(jit:")
+    assert generic.kernel_name().startswith("small-generic")
+    for shots in (1, 127, 5000, 128 * 300 + 5):
+        ex = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
+        ez = (rng.random((shots, n)) < 0.05).astype(np.uint8)
+        tall = {}
+        for which, errs in ((2, ex), (1, ez)):
+            want = omc.decode_batch(*sides[which], errs)
+            e_planes = planes.pack_planes(errs)
+            corr, flip, miss, tally = dev.decode_planes(e_planes, shots, which)
+            assert np.array_equal(planes.unpack_planes(corr, shots), want["corr"])
+            assert np.array_equal(planes.unpack_plane(flip, shots), want["flip"])
+            assert np.array_equal(planes.unpack_plane(miss, shots), want["miss"])
+            tall[which] = want
+        got = dev.decode_xz_planes(planes.pack_planes(ex), planes.pack_planes(ez), shots)
+        assert got == generic.decode_xz_planes(planes.pack_planes(ex), planes.pack_planes(ez), shots)
+        assert got["fail_x"] == int(tall[2]["flip"].sum()) and got["fail_z"] == int(tall[1]["flip"].sum())
+        assert got["fail_any"] == int((tall[2]["flip"] | tall[1]["flip"]).sum())
+    for p_err in (1e-3, 0.2):
+        assert dev.mc_run(p_err, 1 << 20, seed=5, first_shot=256) == generic.mc_run(p_err, 1 << 20, seed=5, first_shot=256)
+        sx, sz = dev.mc_sample(p_err, 3000, seed=9)
+        gx, gz = generic.mc_sample(p_err, 3000, seed=9)
+        assert np.array_equal(sx, gx) and np.array_equal(sz, gz)
+
+
+def test_specialize_through_csscode_and_cache():
+    """CSSCode.specialize() on codes the library has no descriptor for; the second build of the same
+    code reuses the cached shared object."""
+    from quantum_css_codes_b200 import specialize
+    hx, hz = codes.shor9()
+    code, again = CSSCode(hx, hz), CSSCode(hx, hz)
+    ref = ocss.build_css(hx, hz)
+    assert code.device.kernel_name().startswith("small-generic")
+    name = code.specialize()
+    assert name.startswith("small-static(jit:") and again.specialize() == name
+    so = [f for f in os.listdir(specialize.JIT_DIR) if name[len("small-static(jit:"):-1] in f]
+    assert len(so) == 1
+    rng = np.random.default_rng(9)
+    ex, ez = omc.sample_depolarizing(rng, 20000, code.n, 0.1)
+    assert code.decode_xz(ex, ez) == omc.tally_xz(ref, ex, ez)
+    got = code.monte_carlo(0.05, 1 << 16, seed=3)
+    sx, sz = ophilox.sample_bits(3, 0, 1 << 16, code.n, 0.05)
+    assert got == omc.tally_xz(ref, sx, sz)
 
 
 # ---- fused Philox sampler -----------------------------------------------------------------------

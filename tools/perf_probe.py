@@ -71,6 +71,31 @@ def probe_decode(name, shots, p=1e-3):
     torch.cuda.empty_cache()
 
 
+def probe_specialized(shots, p=1e-3):
+    """A code the library has no built-in descriptor for (Shor [[9,1,3]]): generic kernels vs kernels
+    compiled for the code (CSSCode.specialize)."""
+    hx, hz = codes.shor9()
+    for jit in (False, True):
+        code = CSSCode(hx, hz)
+        if jit:
+            code.specialize()
+        dev = code.device
+        n = code.n
+        stride = ((shots + 127) // 128) * 2
+        stream = torch.cuda.current_stream().cuda_stream
+        ex = torch.empty((n, stride), dtype=torch.int64, device="cuda")
+        ez = torch.empty((n, stride), dtype=torch.int64, device="cuda")
+        tally = torch.zeros(6, dtype=torch.int64, device="cuda")
+        dev.mc_sample_dev(p, shots, 1, 0, ex.data_ptr(), ez.data_ptr(), stride, stream)
+        med, best = timed(lambda: dev.decode_dev(shots, stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride,
+                                                 tally=tally.data_ptr()))
+        gbs = 2 * n / 8 * shots / (med / 1e3) / 1e9
+        emit(probe="decode_resident", code="shor9", kernel=dev.kernel_name(), shots=shots, p=p, ms=med, ms_best=best,
+             shots_per_s=shots / (med / 1e3), gbs=gbs, hbm_frac=gbs / HBM_PEAK)
+        del ex, ez
+        torch.cuda.empty_cache()
+
+
 def probe_hgp(shots):
     hx, hz = codes.hgp1600()
     code = SyndromeCode(hx, hz)
@@ -168,6 +193,8 @@ def main():
             probe_decode(name, big)
         for name in ("qrm15", "golay23"):
             probe_decode(name, big // 4, p=0.05)
+    if only is None or "jit" in only:
+        probe_specialized(big)
     if only is None or "hgp" in only:
         probe_hgp(1 << 22 if args.quick else 100_000_000)
     if only is None or "dense" in only:

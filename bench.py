@@ -220,6 +220,10 @@ def run_b200(args):
     sampler.start()
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # align the ranks' streams on the device (host threads leave the barrier milliseconds apart): an
+        # untimed one-word allreduce completes at the same moment everywhere, the start event follows it
+        dist.all_reduce(torch.zeros(1, dtype=torch.int64, device="cuda"))
     start.record()
     tallies = run(args.steps, True)
     stop.record()

@@ -131,8 +131,9 @@ QCSS_API int qcss_decode_xz(qcss_code* code, const uint64_t* ex_planes, const ui
 QCSS_API int qcss_decode_dev(qcss_code* code, const qcss_decode_io* io, int64_t shots, void* stream);
 
 /* ---- K3 fused Philox sampler + K1 + K2 (no reference counterpart).
- *      Depolarising noise: each qubit of each shot gets X, Y or Z with probability p/3 each,
- *      p quantised to floor(p * 2^32) / 2^32.  Streams are keyed by (seed, global shot word,
+ *      Depolarising noise: each qubit of each shot gets X, Y or Z with probability p/3 each.  For
+ *      p >= 1/128 the per-shot error probability is exactly floor(p * 2^32) / 2^32; below that the
+ *      gaps between errors are drawn by inverse CDF from a table quantised to 2^-32.  Streams are keyed by (seed, global shot word,
  *      qubit) so results do not depend on how shots are split over calls or GPUs;
  *      first_shot must be a multiple of 128. ------------------------------------------------ */
 QCSS_API int qcss_mc_run(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,

@@ -15,6 +15,15 @@ Specification (what quantum_css_codes_b200/csrc/core.cuh::sample_site_word imple
   * stage 2, while some error lane is untyped: next block gives attempts (w0, w1) then (w2, w3)
     as (x bits, z bits); a lane accepts the first attempt where x|z = 1.
   * outputs: x plane word (X or Y), z plane word (Z or Y).
+
+Gap sampler (core.cuh::sample_site_word_gap), used instead when thr < 2^25 (p < 1/128):
+  * table cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32), k = 0..31, (1-p)^(k+1) by repeated multiplication
+    in IEEE double (gap_table); a uniform word u gives d = #{k : cdf[k] <= u} clean lanes before the
+    next error (d = 32: none left in this word).
+  * blocks q = 0, 1, ...; each block gives two draws (u, tw) = (w0, w1), (w2, w3).  With pos = next
+    lane to decide: pos + d >= 32 ends the word; otherwise the error sits at lane pos + d, its type is
+    the first two-bit field of tw (from the low end) that is not 00, read as (x, z); if all 16 fields
+    are 00 the draw is discarded (pos unchanged).
 """
 
 import numpy as np
@@ -46,6 +55,23 @@ def threshold(p):
     return int(min(max(int(np.floor(p * 4294967296.0)), 0), 0xFFFFFFFF))
 
 
+def gap_table(p):
+    """(cdf[32] uint32, inv) exactly as api.cu::gap_table_from_p computes them."""
+    q = 1.0 - float(p)
+    acc = 1.0
+    cdf = []
+    for _ in range(32):
+        acc = acc * q
+        v = np.floor((1.0 - acc) * 4294967296.0)
+        cdf.append(int(min(max(v, 0.0), 4294967295.0)))
+    inv = (4294967295 // cdf[0]) if cdf[0] else 0xFFFFFFFF
+    return np.array(cdf, dtype=np.uint64), inv
+
+
+def uses_gap_sampler(p):
+    return threshold(p) < (1 << 25)
+
+
 def _blocks(seed, g, j, q):
     g = np.asarray(g, dtype=np.uint64)
     ctr = np.stack([g & MASK32, g >> np.uint64(32),
@@ -56,8 +82,47 @@ def _blocks(seed, g, j, q):
     return philox4x32_10(ctr.astype(np.uint32), key)
 
 
-def sample_words(seed, first_word, n_words, n, p):
+def _sample_words_gap(seed, first_word, n_words, n, p):
+    cdf, _ = gap_table(p)
+    g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
+    ex = np.zeros((n, n_words), dtype=np.uint32)
+    ez = np.zeros((n, n_words), dtype=np.uint32)
+    for j in range(n):
+        w = _blocks(seed, g, j, np.zeros(n_words, dtype=np.uint64))
+        hit = np.flatnonzero(w[:, 0].astype(np.uint64) < cdf[31])          # words with at least one error
+        for idx in hit:
+            buf = w[idx]
+            pos, blk, x, z = 0, 1, 0, 0
+            done = False
+            while not done:
+                for h in (0, 1):
+                    u, tw = int(buf[2 * h]), int(buf[2 * h + 1])
+                    d = int(np.count_nonzero(cdf <= u))
+                    if pos + d >= 32:
+                        done = True
+                        break
+                    valid = (tw | (tw >> 1)) & 0x55555555
+                    if valid == 0:
+                        continue
+                    b = (valid & -valid).bit_length() - 1
+                    lane = pos + d
+                    x |= ((tw >> b) & 1) << lane
+                    z |= ((tw >> (b + 1)) & 1) << lane
+                    pos = lane + 1
+                    if pos >= 32:
+                        done = True
+                        break
+                if not done:
+                    buf = _blocks(seed, g[idx:idx + 1], j, np.array([blk], dtype=np.uint64))[0]
+                    blk += 1
+            ex[j, idx], ez[j, idx] = x, z
+    return ex, ez
+
+
+def sample_words(seed, first_word, n_words, n, p, force_bit_serial=False):
     """Sampled planes as uint32 words: (ex, ez), each (n, n_words)."""
+    if uses_gap_sampler(p) and not force_bit_serial:
+        return _sample_words_gap(seed, first_word, n_words, n, p)
     thr = threshold(p)
     g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
     ex = np.zeros((n, n_words), dtype=np.uint32)

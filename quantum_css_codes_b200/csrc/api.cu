@@ -251,6 +251,21 @@ int threshold_from_p(double p, uint32_t* thr) {
     return QCSS_OK;
 }
 
+// Gap-sampler table (core.cuh GapTable): cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32), (1-p)^(k+1) by repeated
+// multiplication in double precision -- oracle/philox.py::gap_table performs the same IEEE operations.
+void gap_table_from_p(double p, GapTable* t) {
+    const double q = 1.0 - p;
+    double acc = 1.0;
+    for (int k = 0; k < 32; ++k) {
+        acc = acc * q;
+        double v = std::floor((1.0 - acc) * 4294967296.0);
+        if (v > 4294967295.0) v = 4294967295.0;
+        if (v < 0.0) v = 0.0;
+        t->cdf[k] = (uint32_t)v;
+    }
+    t->inv = t->cdf[0] ? (uint32_t)(4294967295u / t->cdf[0]) : 0xFFFFFFFFu;
+}
+
 int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStream_t stream) {
     if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
     if (io->ex == nullptr && io->ez == nullptr) return fail(QCSS_ERR_INVALID, "no error planes given");
@@ -313,6 +328,9 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
     l.io.seed = seed;
     l.io.first_word = (uint64_t)(first_shot / 32);
     l.io.thr = thr;
+    // error rates below 1/128 take the gap sampler (measured crossover on Steane: p ~ 0.008) (QCSS_SAMPLER=bits forces the bit-serial one: A/B runs)
+    l.io.use_gap = (thr < (1u << 25) && getenv("QCSS_SAMPLER_BITS") == nullptr) ? 1u : 0u;
+    gap_table_from_p(p, &l.io.gap);
     l.named_id = c->named_id;
     l.sample = true;
     QCSS_CUDA(launch_small_any(c, l, stream));

@@ -162,6 +162,92 @@ QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t th
     }
 }
 
+// Gap sampler (p < 1/128): instead of deciding 32 lanes bit by bit, draw the number of error-free lanes
+// before the next error by inverse CDF.  cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32) (host table, computed
+// by repeated multiplication in double precision so that C and numpy agree bit for bit); a 32-bit
+// uniform u gives d = #{k : cdf[k] <= u} clean lanes, d = 32 meaning "no further error in this word".
+// One Philox block supplies two draws (u, tw) = (w0, w1), (w2, w3): tw provides 16 two-bit attempts at
+// the Pauli type ((x, z) != (0, 0), scanned from the low end); if all 16 are (0, 0) the whole draw is
+// discarded and redrawn, which keeps gap and type exactly independent.  Expected blocks per word:
+// 1 + 32 p / 2 instead of 2.2, and the common path is one compare after the block.
+//   counter = (g_lo, g_hi, j, block index), key = seed -- as in the bit-serial sampler above.
+struct GapTable {
+    uint32_t cdf[32];
+    uint32_t inv;            // floor((2^32 - 1) / max(cdf[0], 1)): first guess d ~ u / cdf[0]
+};
+
+QCSS_HD uint32_t gap_count(const GapTable& t, uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d = __umulhi(u, t.inv);
+#else
+    uint32_t d = (uint32_t)(((uint64_t)u * t.inv) >> 32);
+#endif
+    if (d > 32u) d = 32u;
+    while (d < 32u && u >= t.cdf[d]) ++d;
+    while (d > 0u && u < t.cdf[d - 1u]) --d;
+    return d;
+}
+
+QCSS_HD uint32_t ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
+// one draw (u, tw) at lane position pos; returns false when the word is finished
+QCSS_HD bool gap_draw(const GapTable& t, uint32_t u, uint32_t tw, uint32_t& pos, uint32_t& x, uint32_t& z) {
+    const uint32_t d = gap_count(t, u);
+    if (pos + d >= 32u) return false;
+    const uint32_t valid = (tw | (tw >> 1)) & 0x55555555u;
+    if (valid != 0u) {
+        const uint32_t b = ctz32(valid), lane = pos + d;
+        x |= ((tw >> b) & 1u) << lane;
+        z |= ((tw >> (b + 1u)) & 1u) << lane;
+        pos = lane + 1u;
+    }
+    return pos < 32u;
+}
+
+// Rare continuation (a second error in the same word, 5e-4 per word at p = 1e-3): out of line, so the
+// 4 x n unrolled call sites stay small.  Resumes with the block's second draw (w2, w3) at lane `pos`.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void sample_gap_rest(uint32_t k0, uint32_t k1, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t,
+                     uint32_t pos, uint32_t w2, uint32_t w3, uint32_t& x, uint32_t& z) {
+    Philox px;
+    px.k0 = k0;
+    px.k1 = k1;
+    if (!gap_draw(t, w2, w3, pos, x, z)) return;
+    uint32_t buf[4];
+    for (uint32_t blk = 1u;; ++blk) {
+        px.block(g_lo, g_hi, j, blk, buf);
+        if (!gap_draw(t, buf[0], buf[1], pos, x, z)) return;
+        if (!gap_draw(t, buf[2], buf[3], pos, x, z)) return;
+    }
+}
+
+QCSS_HD void sample_site_word_gap(uint64_t seed, uint64_t g, uint32_t j, const GapTable& t, uint32_t cdf31,
+                                  uint32_t& x, uint32_t& z) {
+    Philox px;
+    px.k0 = (uint32_t)seed;
+    px.k1 = (uint32_t)(seed >> 32);
+    const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+    uint32_t buf[4];
+    px.block(g_lo, g_hi, j, 0u, buf);
+    x = 0u;
+    z = 0u;
+    if (buf[0] >= cdf31) return;                       // no error among the 32 lanes (cdf31 = t.cdf[31])
+    uint32_t pos = 0u;
+    gap_draw(t, buf[0], buf[1], pos, x, z);            // first error: inline (3 % of the words)
+    if (pos >= 32u || buf[2] >= t.cdf[31u - pos]) return;              // usually the only one
+    sample_gap_rest(px.k0, px.k1, g_lo, g_hi, j, t, pos, buf[2], buf[3], x, z);
+}
+
 QCSS_HD uint32_t popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popc(v);

@@ -1,6 +1,7 @@
 // Small-code (n <= 32) syndrome + lookup-decode + logical-check pipeline for one "unit" of
 // VEC 32-shot words.  Shared by the sm_100a kernels and the test-only host emulation.
 #pragma once
+#include <type_traits>
 #include "core.cuh"
 
 namespace qcss {
@@ -34,6 +35,8 @@ struct DecodeIO {
     uint64_t seed;
     uint64_t first_word;         // global index of word 0 (first_shot / 32)
     uint32_t thr;                // floor(p * 2^32)
+    uint32_t use_gap;            // p < 1/128: gap sampler (core.cuh) with the table below, else bit-serial
+    GapTable gap;
 };
 
 // ---- loads ------------------------------------------------------------------------------------
@@ -238,7 +241,8 @@ QCSS_HD void load_side(const P& pol, const uint32_t* base, int64_t stride, uint3
 
 template <class PX, class PZ, int VEC, bool SAMPLE, bool FAST>
 QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_t unit,
-                          const SideLut& lut_x, const SideLut& lut_z, Counters& c) {
+                          const SideLut& lut_x, const SideLut& lut_z, Counters& c,
+                          const GapTable* gap_tab = nullptr) {
     static_assert(PX::NB == PZ::NB, "sides share the qubit count");
     constexpr int NB = PX::NB;
     const int64_t w0 = unit * VEC;
@@ -261,29 +265,42 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
         zero_side<PX, VEC>(sx, lex);
         zero_side<PZ, VEC>(sz, lez);
         const int n = px.n();
+        const GapTable& gtab = (gap_tab != nullptr) ? *gap_tab : io.gap;
+        // the sampler choice is hoisted out of the (fully unrolled) site loop: one run executes one copy
+        auto sample_all = [&](auto gap_tag) {
+            constexpr bool GAP = decltype(gap_tag)::value;
+            const uint32_t cdf31 = io.gap.cdf[31];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            if (j < n) {
-                uint32_t xe[VEC], ze[VEC];
+            for (int j = 0; j < NB; ++j) {
+                if (j < n) {
+                    uint32_t xe[VEC], ze[VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
-                                     xe[v], ze[v]);
-                if constexpr (!FAST) {
-                    // padding bits (past the last shot) are written as zero, whatever the unit width
-                    uint32_t xo[VEC], zo[VEC];
+                    for (int v = 0; v < VEC; ++v) {
+                        if constexpr (GAP)
+                            sample_site_word_gap(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, gtab, cdf31,
+                                                 xe[v], ze[v]);
+                        else
+                            sample_site_word(io.seed, io.first_word + (uint64_t)(w0 + v), (uint32_t)j, io.thr,
+                                             xe[v], ze[v]);
+                    }
+                    if constexpr (!FAST) {
+                        // padding bits (past the last shot) are written as zero, whatever the unit width
+                        uint32_t xo[VEC], zo[VEC];
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) { xo[v] = xe[v] & valid[v]; zo[v] = ze[v] & valid[v]; }
-                    if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xo);
-                    if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, zo);
-                }
+                        for (int v = 0; v < VEC; ++v) { xo[v] = xe[v] & valid[v]; zo[v] = ze[v] & valid[v]; }
+                        if (io.ex_out != nullptr) store_words<VEC>(io.ex_out + (int64_t)j * io.e_stride + w0, xo);
+                        if (io.ez_out != nullptr) store_words<VEC>(io.ez_out + (int64_t)j * io.e_stride + w0, zo);
+                    }
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    px.add(j, xe[v], sx[v], lex[v]);
-                    pz.add(j, ze[v], sz[v], lez[v]);
+                    for (int v = 0; v < VEC; ++v) {
+                        px.add(j, xe[v], sx[v], lex[v]);
+                        pz.add(j, ze[v], sz[v], lez[v]);
+                    }
                 }
             }
-        }
+        };
+        if (io.use_gap) sample_all(std::true_type{});
+        else sample_all(std::false_type{});
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             ox[v] = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x, io.c_stride,

@@ -100,11 +100,20 @@ __device__ __forceinline__ void run_small(const PX& px, const PZ& pz, const Deco
     const SideLut lut_z = stage_side<PZ, FAST>(pz, tz, cursor);
     if constexpr (!PX::kSliced || !PZ::kSliced) __syncthreads();
 
+    // the gap sampler's table is read with per-lane indices on its rare path: shared memory, not the
+    // kernel parameter block (whose address cannot be taken without a local copy)
+    __shared__ GapTable s_gap;
+    if constexpr (SAMPLE) {
+        if (threadIdx.x < 32) s_gap.cdf[threadIdx.x] = io.gap.cdf[threadIdx.x];
+        if (threadIdx.x == 32) s_gap.inv = io.gap.inv;
+        __syncthreads();
+    }
+
     Counters c = {0u, 0u, 0u, 0u, 0u};
     const int64_t units = (io.words + VEC - 1) / VEC;
     const int64_t step = (int64_t)gridDim.x * kThreads;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < units; u += step)
-        process_unit<PX, PZ, VEC, SAMPLE, FAST>(px, pz, io, u, lut_x, lut_z, c);
+        process_unit<PX, PZ, VEC, SAMPLE, FAST>(px, pz, io, u, lut_x, lut_z, c, SAMPLE ? &s_gap : nullptr);
     block_tally(c, io.tally);
 }
 
@@ -117,7 +126,7 @@ k_small_generic(const __grid_constant__ GenericArgs a) {
 }
 
 template <class DX, class DZ, int VEC, bool SAMPLE, bool FAST>
-__global__ void __launch_bounds__(kThreads, FAST ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, FAST ? (SAMPLE ? 3 : 2) : 1)
 k_small_named(const __grid_constant__ NamedArgs a) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;
@@ -248,9 +257,13 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
     a.io = l.io;
     const size_t smem = lut_smem(*l.x, *l.z, !DX::kSliced, !DZ::kSliced, false);
     const size_t smem_fast = lut_smem(*l.x, *l.z, !DX::kSliced, !DZ::kSliced, true);
+    // The sampling kernels load nothing, so the 16-byte-per-plane unit buys nothing there: one word per
+    // thread keeps 4x fewer syndrome accumulators live and 4x fewer unrolled sampler sites (measured on
+    // Golay-23 with VEC = 4: the first-error path inlined at 92 sites ran at 4.2e10 shots/s).
+    constexpr int SVEC = 1;
     if (l.sample)
-        return launch_split<VEC>(k_small_named<DX, DZ, VEC, true, true>, k_small_named<DX, DZ, VEC, true, false>,
-                                 a, l, smem_fast, smem, stream);
+        return launch_split<SVEC>(k_small_named<DX, DZ, SVEC, true, true>, k_small_named<DX, DZ, SVEC, true, false>,
+                                  a, l, smem_fast, smem, stream);
     return launch_split<VEC>(k_small_named<DX, DZ, VEC, false, true>, k_small_named<DX, DZ, VEC, false, false>,
                              a, l, smem_fast, smem, stream);
 }

@@ -32,7 +32,8 @@ class DecodeIO(ctypes.Structure):
                 ("miss_x", ctypes.c_void_p), ("miss_z", ctypes.c_void_p), ("tally", ctypes.c_void_p),
                 ("words", ctypes.c_int64), ("tail_mask", ctypes.c_uint32), ("sides", ctypes.c_int32),
                 ("ex_out", ctypes.c_void_p), ("ez_out", ctypes.c_void_p),
-                ("seed", ctypes.c_uint64), ("first_word", ctypes.c_uint64), ("thr", ctypes.c_uint32)]
+                ("seed", ctypes.c_uint64), ("first_word", ctypes.c_uint64), ("thr", ctypes.c_uint32),
+                ("use_gap", ctypes.c_uint32), ("gap_cdf", ctypes.c_uint32 * 32), ("gap_inv", ctypes.c_uint32)]
 
 
 def _needs_build():
@@ -131,6 +132,13 @@ def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1,
     else:
         io.sides = 3
         io.seed, io.first_word, io.thr = sample["seed"], sample["first_shot"] // 32, sample["thr"]
+        if "p" in sample:                                   # gap sampler for p < 1/64, as api.cu chooses
+            from oracle import philox as _ophilox
+            cdf, inv = _ophilox.gap_table(sample["p"])
+            io.use_gap = 1 if _ophilox.uses_gap_sampler(sample["p"]) else 0
+            for k in range(32):
+                io.gap_cdf[k] = int(cdf[k])
+            io.gap_inv = inv
         out["ex"] = np.zeros((n, stride), dtype=np.uint64)
         out["ez"] = np.zeros((n, stride), dtype=np.uint64)
         io.ex_out, io.ez_out = out["ex"].ctypes.data, out["ez"].ctypes.data

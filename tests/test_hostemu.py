@@ -154,13 +154,13 @@ def test_generic_random_codes_with_partial_tables(n, m1, m2):
 
 
 @pytest.mark.parametrize("name", ["steane", "golay23"])
-@pytest.mark.parametrize("p", [1e-3, 0.05, 0.5, 0.0, 1.0])
+@pytest.mark.parametrize("p", [1e-3, 0.012, 0.05, 0.5, 0.0, 1.0, 1e-9])
 def test_fused_sampler_bit_exact(name, p):
     """The fused sampler draws exactly the oracle sampler's bits and tallies them like the oracle."""
     code, sx, sz = build(name)
     shots, seed, first = 4000, 0x5EED1234ABCD, 128 * 7
     thr = ophilox.threshold(p)
-    got = emu.decode(sx, sz, shots=shots, named_id=NAMED[name], sample=dict(seed=seed, first_shot=first, thr=thr))
+    got = emu.decode(sx, sz, shots=shots, named_id=NAMED[name], sample=dict(seed=seed, first_shot=first, thr=thr, p=p))
     ex, ez = ophilox.sample_bits(seed, first, shots, code.n, p)
     assert np.array_equal(planes.unpack_planes(got["ex"], shots), ex)
     assert np.array_equal(planes.unpack_planes(got["ez"], shots), ez)
@@ -169,12 +169,17 @@ def test_fused_sampler_bit_exact(name, p):
         assert not ex.any() and not ez.any()
 
 
-def test_sampler_statistics():
-    """Per-qubit X/Y/Z frequencies of the oracle sampler (which the kernel matches bit-for-bit)."""
-    p, shots = 0.3, 400000
+@pytest.mark.parametrize("p", [0.3, 0.01])
+def test_sampler_statistics(p):
+    """Per-qubit X/Y/Z frequencies of the oracle sampler (which the kernel matches bit-for-bit): the
+    bit-serial sampler (p = 0.3) and the gap sampler (p = 0.01 < 1/64), plus lane uniformity of the latter."""
+    shots = 400000 if p > 0.1 else 3200000
     ex, ez = ophilox.sample_bits(99, 0, shots, 3, p)
     for freq in (np.mean(ex & ~ez & 1), np.mean(ez & ~ex & 1), np.mean(ex & ez)):
         assert abs(freq - p / 3) < 5 * np.sqrt(p / 3 * (1 - p / 3) / (3 * shots))
+    err = (ex | ez)[:, 0].reshape(-1, 32).sum(axis=0)                 # errors per lane position
+    expect = shots / 32 * p
+    assert np.all(np.abs(err - expect) < 5 * np.sqrt(expect))
 
 
 @pytest.mark.parametrize("name", list(NAMED))
@@ -192,7 +197,7 @@ def test_fast_instantiation_tallies(name, static, p):
     got = emu.decode(sx, sz, planes.pack_planes(ex), planes.pack_planes(ez), shots, nid, fast=True)
     assert got["tally"] == omc.tally_xz(code, ex, ez)
     got = emu.decode(sx, sz, shots=shots, named_id=nid, fast=True,
-                     sample=dict(seed=77, first_shot=256, thr=ophilox.threshold(p)))
+                     sample=dict(seed=77, first_shot=256, thr=ophilox.threshold(p), p=p))
     ox, oz = ophilox.sample_bits(77, 256, shots, code.n, p)
     assert got["tally"] == omc.tally_xz(code, ox, oz)
 

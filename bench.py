@@ -171,6 +171,10 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_node = None
+    if world > 1:
+        from quantum_css_codes_b200 import distributed as qdist
+        numa_node = qdist.bind_to_gpu_numa_node(local_rank)      # pinned e2e buffers local to the GPU's root
     lib = _native.load()
     _native.check(lib.qcss_set_device(local_rank))
     if world > 1:
@@ -274,7 +278,8 @@ def run_b200(args):
                        "shots_per_gpu_per_step": shots, "layout": "bit-plane, 2 x %d planes resident in HBM" % n,
                        "resident_bytes_per_gpu": int(2 * n * stride * 8),
                        "l2_policy": "inputs (%.1f GB) larger than L2, no flush" % (2 * n * stride * 8 / 1e9),
-                       "kernel": dev.kernel_name(), "parallelism": f"shots sharded over {world} GPU(s), weak"},
+                       "kernel": dev.kernel_name(), "parallelism": f"shots sharded over {world} GPU(s), weak",
+                       "rank0_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES_PER_SHOT[args.code] * shots

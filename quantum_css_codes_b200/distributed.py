@@ -54,3 +54,31 @@ def monte_carlo_sharded(code, p, total_shots, seed=0, rank=None, world_size=None
     run = local_run if local_run is not None else code.monte_carlo
     local = run(p, shots, seed, first) if shots > 0 else {k: 0 for k in TALLY_FIELDS}
     return allreduce_tally(local)
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers
+    allocated afterwards are local to the GPU's PCIe root (host-to-device copies of the end-to-end
+    path otherwise cross the socket interconnect for half of the ranks).  Returns the node or None."""
+    import os
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device_index)
+        bus_id = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus_id}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None

@@ -237,9 +237,10 @@ cudaError_t launch_generic(const SmallLaunch& l, cudaStream_t stream) {
     a.io = l.io;
     const bool lut = (MB != kSlicedM);
     const size_t smem = lut_smem(*l.x, *l.z, lut, lut, false), smem_fast = lut_smem(*l.x, *l.z, lut, lut, true);
+    constexpr int SVEC = 1;                          // sampling kernels: one word per thread (see launch_named)
     if (l.sample)
-        return launch_split<VEC>(k_small_generic<NB, MB, VEC, true, true>, k_small_generic<NB, MB, VEC, true, false>,
-                                 a, l, smem_fast, smem, stream);
+        return launch_split<SVEC>(k_small_generic<NB, MB, SVEC, true, true>, k_small_generic<NB, MB, SVEC, true, false>,
+                                  a, l, smem_fast, smem, stream);
     return launch_split<VEC>(k_small_generic<NB, MB, VEC, false, true>, k_small_generic<NB, MB, VEC, false, false>,
                              a, l, smem_fast, smem, stream);
 }

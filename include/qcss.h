@@ -117,6 +117,15 @@ QCSS_API int qcss_syndrome(qcss_code* code, int which, const uint64_t* e_planes,
 QCSS_API int qcss_syndrome_dev(qcss_code* code, int which, const uint64_t* d_e_planes, int64_t e_stride,
                       int64_t shots, uint64_t* d_s_planes, int64_t s_stride, void* stream);
 
+/* Per-syndrome histogram (the tallies a multi-GPU run all-reduces): hist[key] += number of
+ * shots whose syndrome has big-endian key `key` (bin_matrix.vec_to_int, bin_matrix.py:36-43);
+ * hist has 2^m uint64 entries, m <= 24.  The device form accumulates into d_hist, the host form
+ * overwrites hist. */
+QCSS_API int qcss_syndrome_hist(qcss_code* code, int which, const uint64_t* e_planes, int64_t e_stride, int64_t shots,
+                       uint64_t* hist);
+QCSS_API int qcss_syndrome_hist_dev(qcss_code* code, int which, const uint64_t* d_e_planes, int64_t e_stride,
+                           int64_t shots, uint64_t* d_hist, void* stream);
+
 /* ---- K1+K2 lookup decode + logical check: replaces the table scan of
  *      quil_classical_correct (css_code.py:649-685) and the Lz/Lx readout (css_code.py:641-646).
  *      corr/flip/miss planes may be NULL; tally may be NULL. ------------------------------ */

@@ -71,6 +71,10 @@ PROTOTYPES = {
                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
     "qcss_syndrome_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "qcss_syndrome_hist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_void_p]),
+    "qcss_syndrome_hist_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "qcss_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.POINTER(Tally)]),
@@ -219,6 +223,17 @@ class DeviceCode:
         out = np.zeros((self.m(which), stride), dtype=np.uint64)
         check(self._lib.qcss_syndrome(self.handle, which, _ptr(e_planes), stride, shots, _ptr(out), stride))
         return out
+
+    def syndrome_hist_planes(self, e_planes, shots, which):
+        """uint64[2^m] counts of the big-endian syndrome keys of a batch of error planes."""
+        e_planes = self._check_planes(e_planes, shots)
+        hist = np.zeros(1 << self.m(which), dtype=np.uint64)
+        check(self._lib.qcss_syndrome_hist(self.handle, which, _ptr(e_planes), e_planes.shape[1], shots, _ptr(hist)))
+        return hist
+
+    def syndrome_hist_dev(self, which, e_ptr, e_stride, shots, hist_ptr, stream=0):
+        check(self._lib.qcss_syndrome_hist_dev(self.handle, which, ctypes.c_void_p(e_ptr), e_stride, shots,
+                                               ctypes.c_void_p(hist_ptr), ctypes.c_void_p(stream)))
 
     def decode_planes(self, e_planes, shots, which):
         e_planes = self._check_planes(e_planes, shots)

@@ -882,3 +882,53 @@ QCSS_API int qcss_code_load_specialized(qcss_code* c, const char* so_path, const
 }
 
 }  // extern "C"
+
+// ---- per-syndrome histograms ------------------------------------------------
+
+extern "C" {
+
+QCSS_API int qcss_syndrome_hist_dev(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stride, int64_t shots,
+                           uint64_t* d_hist, void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!d_hist) return fail(QCSS_ERR_INVALID, "NULL histogram");
+    const int m = (which == 1) ? c->m1 : c->m2;
+    if (m < 1 || m > 24) return fail(QCSS_ERR_UNSUPPORTED, "syndrome histograms cover 1 <= m <= 24 (got %d)", m);
+    if (shots <= 0) return shots == 0 ? QCSS_OK : fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t s_stride = ((shots + 127) / 128) * 2;                  // uint64 words per syndrome plane
+    void* d_s = nullptr;
+    QCSS_CUDA(cudaMallocAsync(&d_s, (size_t)m * s_stride * 8, st));
+    int rc = launch_syndrome(c, which, d_e, e_stride, shots, (uint64_t*)d_s, s_stride, st);
+    cudaError_t e = cudaSuccess;
+    if (!rc)
+        e = launch_syndrome_hist((const uint32_t*)d_s, s_stride * 2, m, (shots + 31) / 32, tail_mask_for(shots),
+                                 (unsigned long long*)d_hist, st);
+    cudaFreeAsync(d_s, st);
+    if (rc) return rc;
+    QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_syndrome_hist(qcss_code* c, int which, const uint64_t* e_planes, int64_t e_stride, int64_t shots,
+                       uint64_t* hist) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!e_planes || !hist) return fail(QCSS_ERR_INVALID, "NULL argument");
+    const int m = (which == 1) ? c->m1 : c->m2;
+    if (m < 1 || m > 24) return fail(QCSS_ERR_UNSUPPORTED, "syndrome histograms cover 1 <= m <= 24 (got %d)", m);
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const size_t eb = (size_t)c->n * e_stride * 8, hb = ((size_t)1 << m) * 8;
+    QCSS_CUDA(c->buf_a.reserve(eb));
+    QCSS_CUDA(c->buf_c.reserve(hb));
+    QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_planes, eb, cudaMemcpyHostToDevice, c->stream));
+    QCSS_CUDA(cudaMemsetAsync(c->buf_c.p, 0, hb, c->stream));
+    rc = qcss_syndrome_hist_dev(c, which, (const uint64_t*)c->buf_a.p, e_stride, shots, (uint64_t*)c->buf_c.p, c->stream);
+    if (rc) return rc;
+    QCSS_CUDA(cudaMemcpyAsync(hist, c->buf_c.p, hb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
+}  // extern "C"

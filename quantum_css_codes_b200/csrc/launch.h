@@ -70,4 +70,8 @@ int64_t table_count(const TableBuild* tb);
 cudaError_t table_read(const TableBuild* tb, int64_t* keys, uint64_t* supports);
 void table_free(TableBuild* tb);
 
+// per-syndrome histogram over syndrome planes (hist_kernels.cu)
+cudaError_t launch_syndrome_hist(const uint32_t* s, int64_t s_stride, int m, int64_t words, uint32_t tail_mask,
+                                 unsigned long long* hist, cudaStream_t stream);
+
 }  // namespace qcss

@@ -285,6 +285,12 @@ class CSSCode:
                 self._c1_syndromes, self._c2_syndromes)
         return self._device_code
 
+    def syndrome_histogram(self, errors, which):
+        """Counts of every syndrome key over a batch: ``hist[vec_to_int(H.e mod 2)]`` (uint64[2^m]),
+        computed on the device (``qcss_syndrome_hist``).  The keys are those of ``_c1/_c2_syndromes``."""
+        errors = np.asarray(errors)
+        return self.device.syndrome_hist_planes(_planes.pack_planes(errors), errors.shape[0], which)
+
     def specialize(self):
         """Compile and attach decode kernels specialised for this code (``specialize.py``): the static
         family that runs Steane / QRM-15 / Golay-23 at the HBM roofline, for any code with n <= 32 and

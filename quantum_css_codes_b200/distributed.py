@@ -40,6 +40,20 @@ def allreduce_tally(tally, device=None):
     return {k: int(v) for k, v in zip(TALLY_FIELDS, t.cpu().tolist())}
 
 
+def allreduce_histogram(hist, device=None):
+    """Sum a syndrome histogram (uint64[2^m] numpy array or int64 CUDA tensor) over all ranks."""
+    import torch
+    import torch.distributed as dist
+    is_tensor = isinstance(hist, torch.Tensor)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return hist
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = hist if is_tensor else torch.from_numpy(np.ascontiguousarray(hist).view(np.int64)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t if is_tensor else t.cpu().numpy().view(np.uint64)
+
+
 def monte_carlo_sharded(code, p, total_shots, seed=0, rank=None, world_size=None, local_run=None):
     """Run this rank's shard of a `total_shots` Monte-Carlo job and all-reduce the tallies.
 

@@ -366,3 +366,42 @@ def test_syndrome_table_gpu_larger_codes():
     assert css_code.syndrome_table_gpu(np.eye(6, dtype=np.int64))[0] == 6        # no collision at all: t = n
     with pytest.raises(MemoryError):
         css_code.syndrome_table_gpu(np.eye(20, dtype=np.int64), max_entries=1000)
+
+
+# ---- per-syndrome histograms ------------------------------------------------
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("shots", [1, 95, 4096, 100003])
+def test_syndrome_histograms(name, shots):
+    """hist[key] = number of shots with that big-endian syndrome key, both Pauli types; sums to shots."""
+    code, ref = pair(name)
+    rng = np.random.default_rng(shots)
+    errs = (rng.random((shots, code.n)) < 0.2).astype(np.uint8)
+    for which in (1, 2):
+        h, table, lop = ocss.pauli_side(ref, which)
+        keys = omc.keys_batch(omc.syndromes_batch(h, errs))
+        want = np.bincount(keys, minlength=1 << h.shape[0]).astype(np.uint64)
+        got = code.syndrome_histogram(errs, which)
+        assert got.dtype == np.uint64 and np.array_equal(got, want)
+        assert int(got.sum()) == shots
+
+
+def test_syndrome_histogram_device_accumulates():
+    import torch
+    code, _ = pair("golay23")
+    dev = code.device
+    shots = 1 << 22
+    stride = ((shots + 127) // 128) * 2
+    ex = torch.empty((code.n, stride), dtype=torch.int64, device="cuda")
+    ez = torch.empty((code.n, stride), dtype=torch.int64, device="cuda")
+    dev.mc_sample_dev(0.02, shots, 4, 0, ex.data_ptr(), ez.data_ptr(), stride, 0)
+    hist = torch.zeros(1 << 11, dtype=torch.int64, device="cuda")
+    dev.syndrome_hist_dev(2, ex.data_ptr(), stride, shots, hist.data_ptr(), 0)
+    dev.syndrome_hist_dev(2, ex.data_ptr(), stride, shots, hist.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert int(hist.sum()) == 2 * shots
+    once = code.syndrome_histogram(planes.unpack_planes(ex.cpu().numpy().view(np.uint64), 4096), 2)
+    sub = torch.zeros(1 << 11, dtype=torch.int64, device="cuda")
+    dev.syndrome_hist_dev(2, ex.data_ptr(), stride, 4096, sub.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(sub.cpu().numpy().astype(np.uint64), once)

@@ -48,8 +48,15 @@ def _worker(rank, world, port, total, seed, p, out_path):
         return omc.tally_xz(ref, ex, ez)
 
     got = qd.monte_carlo_sharded(None, p, total, seed, local_run=local_run)
+    # syndrome histogram of this rank's shard (oracle keys), summed over ranks
+    first, shots = qd.shard_range(total, rank, world)
+    ex, _ = ophilox.sample_bits(seed, first, shots, ref.n, p)
+    h, _, _ = ocss.pauli_side(ref, 2)
+    hist = np.bincount(omc.keys_batch(omc.syndromes_batch(h, ex)), minlength=1 << h.shape[0]).astype(np.uint64)
+    hist = qd.allreduce_histogram(hist)
     if rank == 0:
         np.save(out_path, np.array([got[k] for k in qd.TALLY_FIELDS], dtype=np.int64))
+        np.save(out_path + ".hist.npy", hist)
     dist.destroy_process_group()
 
 
@@ -64,3 +71,6 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     ex, ez = ophilox.sample_bits(seed, 0, total, ref.n, p)
     want = omc.tally_xz(ref, ex, ez)
     assert got == [want[k] for k in qdist.TALLY_FIELDS]
+    h, _, _ = ocss.pauli_side(ref, 2)
+    want_hist = np.bincount(omc.keys_batch(omc.syndromes_batch(h, ex)), minlength=1 << h.shape[0])
+    assert np.array_equal(np.load(out + ".hist.npy"), want_hist.astype(np.uint64))

@@ -18,6 +18,8 @@
 //   epilogue  : tcgen05.ld 32 columns at a time, bit 0 of 32 accumulators -> one syndrome word.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "launch.h"
 
 namespace qcss {
@@ -65,7 +67,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, unsigned parity)
 __global__ void __launch_bounds__(kMmaThreads, 1)
 k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, const uint32_t* __restrict__ e,
                int n, int64_t e_stride, uint32_t* __restrict__ s, int64_t s_stride, int64_t words,
-               uint32_t tail_mask) {
+               uint32_t tail_mask, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t free_bar[kStages];
     __shared__ __align__(8) uint64_t done_bar;
@@ -92,7 +94,11 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     // instruction descriptor: D = S32, A = B = unsigned 8-bit, A K-major, B MN-major, N = 256, M = 128
-    const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // dbg (timing experiments only, results are garbage): bit 0 skips the B expansion, bit 1 describes B as
+    // K-major, bit 2 skips the A copies.  Measured (1024 x 2048, 2^21 shots): 6.59 ms as is; 6.56 without the
+    // expansion; 6.59 with a K-major B descriptor; 5.77 without the A copies; 5.75 with neither -- the MMAs with
+    // no-swizzle operands are what the time goes to, not the bit expansion.
+    const uint32_t idesc = (2u << 4) | ((dbg & 2) ? 0u : (1u << 16)) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
     // expansion role of this thread: qubit kq of the chunk, shot words 2*wp, 2*wp+1 of the tile
     const int kq = tid % kKC, wp = tid / kKC;                 // 64 x 4
@@ -103,7 +109,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
         if (use > 0) mbar_wait_parity(&free_bar[st], (unsigned)((use - 1) & 1));
         uint8_t* sA = smem + (size_t)st * kStageBytes;
         const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
-        for (int i = tid; i < kABytes / 16; i += kMmaThreads) {
+        for (int i = tid; i < kABytes / 16 && !(dbg & 4); i += kMmaThreads) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
         }
@@ -130,7 +136,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
         const uint2 bits = bits_next;
         bits_next = load_bits(kc + 1);
         // ---- B: expand 64 shots of qubit kc*64+kq to bytes (stage st was freed when its A was issued) ----
-        {
+        if (!(dbg & 1)) {
             const uint32_t wv[2] = {bits.x, bits.y};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {                     // 4 groups of 16 shots
@@ -153,7 +159,8 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
 #pragma unroll
                 for (int ks = 0; ks < kKC / 32; ++ks) {
                     const uint64_t da = umma_desc(a0 + mt * kABlock + ks * 2 * 16 * 128, 16 * 128, 128);
-                    const uint64_t db = umma_desc(b0 + ks * 4 * (kNT / 16) * 128, (kNT / 16) * 128, 128);
+                    const uint64_t db = (dbg & 2) ? umma_desc(b0 + ks * 2 * (kNT / 8) * 128, (kNT / 8) * 128, 128)
+                                                  : umma_desc(b0 + ks * 4 * (kNT / 16) * 128, (kNT / 16) * 128, 128);
                     const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
                     asm volatile(
                         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -245,8 +252,9 @@ cudaError_t launch_syndrome_mma(const uint8_t* hq, int m, int n, const uint32_t*
     if (err != cudaSuccess) return err;
     const int64_t grid = tiles * mgroups;
     if (grid <= 0 || grid > 0x7FFFFFFF) return cudaErrorInvalidValue;
+    const int dbg = getenv("QCSS_DENSE_DBG") ? atoi(getenv("QCSS_DENSE_DBG")) : 0;
     k_syndrome_mma<<<(unsigned)grid, kMmaThreads, smem, stream>>>(hq, m, kchunks, mgroups, e, n, e_stride, s, s_stride,
-                                                                  words, tail_mask);
+                                                                  words, tail_mask, dbg);
     return cudaGetLastError();
 }
 

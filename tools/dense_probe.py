@@ -1,0 +1,28 @@
+"""Time the dense tcgen05 syndrome kernel (optionally with QCSS_DENSE_DBG timing knobs).
+    python tools/dense_probe.py [shots]"""
+import os, sys
+import numpy as np
+import torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from quantum_css_codes_b200 import SyndromeCode
+shots = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 21
+rng = np.random.default_rng(5)
+h = rng.integers(0, 2, size=(1024, 2048), dtype=np.uint8)
+os.environ["QCSS_DENSE"] = "1"
+dev = SyndromeCode(h, h).device
+stride = ((shots + 127) // 128) * 2
+e = torch.randint(-2**62, 2**62, (2048, stride), dtype=torch.int64, device="cuda")
+s = torch.empty((1024, stride), dtype=torch.int64, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+for _ in range(2):
+    dev.syndrome_dev(2, e.data_ptr(), stride, shots, s.data_ptr(), stride, st)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(3):
+    dev.syndrome_dev(2, e.data_ptr(), stride, shots, s.data_ptr(), stride, st)
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 3
+print(dev.kernel_name(), "dbg", os.environ.get("QCSS_DENSE_DBG", "0"), "ms", round(ms, 3), "POPS", round(2 * 1024 * 2048 * shots / ms / 1e12, 3),
+      "checksum", int(s.sum()))

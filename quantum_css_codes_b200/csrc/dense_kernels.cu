@@ -97,7 +97,8 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     // dbg (timing experiments only, results are garbage): bit 0 skips the B expansion, bit 1 describes B as
     // K-major, bit 2 skips the A copies.  Measured (1024 x 2048, 2^21 shots): 6.59 ms as is; 6.56 without the
     // expansion; 6.59 with a K-major B descriptor; 5.77 without the A copies; 5.75 with neither -- the MMAs with
-    // no-swizzle operands are what the time goes to, not the bit expansion.
+    // MMAs themselves are what the time goes to, not the bit expansion (K-major SWIZZLE_128B descriptors on
+    // both operands, timing only: 5.78 ms, so the operand layout is not it either).
     const uint32_t idesc = (2u << 4) | ((dbg & 2) ? 0u : (1u << 16)) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
     // expansion role of this thread: qubit kq of the chunk, shot words 2*wp, 2*wp+1 of the tile

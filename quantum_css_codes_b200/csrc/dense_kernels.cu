@@ -12,9 +12,15 @@
 //               16 consecutive shots of one qubit are one 16-byte row of a core matrix.
 //   D         : two 128 x 256 accumulators (two 128-row tiles of H share the expanded E tile) fill the
 //               512 TMEM columns; tcgen05.mma.cta_group::1.kind::i8, M = 128, N = 256, K = 32.
-//   pipeline  : 4 shared-memory stages of 64 qubits; a stage is refilled as soon as the
-//               tcgen05.commit of the MMAs that read it arrives on its mbarrier, so staging and
-//               bit expansion of chunk c+1..c+3 overlap the MMAs of chunk c.
+//   pipeline  : warp-specialised.  Warps 0-7 (producers) stage chunks of 64 qubits into a ring of 6
+//               shared-memory stages (H block and raw error bits by cp.async three chunks ahead,
+//               then the bit expansion) and arrive on the stage's `full` mbarrier; one lane of warp 8
+//               waits for `full`, issues the chunk's four MMAs and commits them to the stage's `free`
+//               mbarrier, which the producers wait on before refilling it.  The MMA lane never joins
+//               a block barrier: with the first version (every thread staged, one __syncthreads per
+//               chunk, thread 0 issuing) the tensor pipe idled 70 % of the time although neither the
+//               expansion nor the copies were the limit (timing knobs: 6.59 ms as is, 5.75 ms with
+//               all data movement removed, 2.68 ms with the MMAs issued back to back).
 //   epilogue  : tcgen05.ld 32 columns at a time, bit 0 of 32 accumulators -> one syndrome word.
 #include <cuda_runtime.h>
 
@@ -26,15 +32,17 @@ namespace qcss {
 
 namespace {
 
-constexpr int kMmaThreads = 256;
+constexpr int kProducers = 256;              // warps 0-7: stage H, expand E; also the epilogue warps
+constexpr int kMmaThreads = kProducers + 32; // warp 8: one lane issues every tcgen05.mma
 constexpr int kMT = 2;                       // 128-row tiles of H per CTA
 constexpr int kNT = 256;                     // shots per CTA
 constexpr int kKC = 64;                      // qubits per stage
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kABlock = 128 * kKC;           // bytes of one 128-row x 64-qubit block of H
 constexpr int kABytes = kMT * kABlock;       // 16 KB
 constexpr int kBBytes = kKC * kNT;           // 16 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kRBytes = kKC * (kNT / 8);      // 2 KB: the chunk's raw error bits (64 qubits x 256 shots)
+constexpr int kStageBytes = kABytes + kBBytes + kRBytes;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -69,6 +77,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
                int n, int64_t e_stride, uint32_t* __restrict__ s, int64_t s_stride, int64_t words,
                uint32_t tail_mask, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t free_bar[kStages];
     __shared__ __align__(8) uint64_t done_bar;
     __shared__ uint32_t tmem_base_s;
@@ -78,8 +87,11 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     const int64_t w0 = tile * (kNT / 32);                     // first shot word of this tile
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i)
+        for (int i = 0; i < kStages; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[i])),
+                         "r"(kProducers));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&free_bar[i])));
+        }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&done_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -94,95 +106,99 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     // instruction descriptor: D = S32, A = B = unsigned 8-bit, A K-major, B MN-major, N = 256, M = 128
-    // dbg (timing experiments only, results are garbage): bit 0 skips the B expansion, bit 1 describes B as
-    // K-major, bit 2 skips the A copies.  Measured (1024 x 2048, 2^21 shots): 6.59 ms as is; 6.56 without the
-    // expansion; 6.59 with a K-major B descriptor; 5.77 without the A copies; 5.75 with neither -- the MMAs with
-    // MMAs themselves are what the time goes to, not the bit expansion (K-major SWIZZLE_128B descriptors on
-    // both operands, timing only: 5.78 ms, so the operand layout is not it either).
-    const uint32_t idesc = (2u << 4) | ((dbg & 2) ? 0u : (1u << 16)) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int kAhead = 3;                                 // H blocks and error bits are fetched three chunks ahead
 
-    // expansion role of this thread: qubit kq of the chunk, shot words 2*wp, 2*wp+1 of the tile
-    const int kq = tid % kKC, wp = tid / kKC;                 // 64 x 4
-    constexpr int kAhead = 2;                                 // H blocks are fetched two chunks ahead
-
-    auto issue_a = [&](int c) {                               // contiguous 16 KB block of the pre-laid-out H
-        const int st = c % kStages, use = c / kStages;
-        if (use > 0) mbar_wait_parity(&free_bar[st], (unsigned)((use - 1) & 1));
-        uint8_t* sA = smem + (size_t)st * kStageBytes;
-        const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
-        for (int i = tid; i < kABytes / 16 && !(dbg & 4); i += kMmaThreads) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
-        }
-    };
-    auto load_bits = [&](int c) {                             // 64 shots of qubit c*64+kq
-        const int j = c * kKC + kq;
-        const int64_t w = w0 + 2 * wp;
-        uint2 bits = make_uint2(0u, 0u);
-        if (c < kchunks && j < n && w < e_stride) bits = __ldg(reinterpret_cast<const uint2*>(e + (int64_t)j * e_stride + w));
-        return bits;
-    };
-
-    for (int c = 0; c < kAhead && c < kchunks; ++c) {
-        issue_a(c);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    uint2 bits_next = load_bits(0);
-    for (int kc = 0; kc < kchunks; ++kc) {
-        const int st = kc % kStages;
-        uint8_t* sA = smem + (size_t)st * kStageBytes;
-        uint8_t* sB = sA + kABytes;
-        if (kc + kAhead < kchunks) issue_a(kc + kAhead);
-        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per iteration (possibly empty)
-        const uint2 bits = bits_next;
-        bits_next = load_bits(kc + 1);
-        // ---- B: expand 64 shots of qubit kc*64+kq to bytes (stage st was freed when its A was issued) ----
-        if (!(dbg & 1)) {
-            const uint32_t wv[2] = {bits.x, bits.y};
+    if (warp == kProducers / 32) {
+        // ---- MMA warp: one lane, no block barriers ------------------------------------------------------
+        if (lane == 0) {
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int st = kc % kStages, use = kc / kStages;
+                mbar_wait_parity(&full_bar[st], (unsigned)(use & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint8_t* sA = smem + (size_t)st * kStageBytes;
+                const uint32_t a0 = (unsigned)__cvta_generic_to_shared(sA), b0 = a0 + kABytes;
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {                     // 4 groups of 16 shots
-                const uint32_t v = wv[h >> 1] >> (16 * (h & 1));
-                const uint4 bytes = make_uint4(spread4(v & 0xFu), spread4((v >> 4) & 0xFu),
-                                               spread4((v >> 8) & 0xFu), spread4((v >> 12) & 0xFu));
-                const int nb = (2 * wp) * 2 + h;              // 16-shot group index within the tile
-                *reinterpret_cast<uint4*>(sB + (size_t)(kq / 8) * (kNT / 16) * 128 + nb * 128 + (kq % 8) * 16) = bytes;
-            }
-        }
-        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");     // chunk kc's H block has landed
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        // ---- MMAs of this chunk: 2 row tiles x 2 K-steps of 32 ------------------------------------
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = (unsigned)__cvta_generic_to_shared(sA), b0 = (unsigned)__cvta_generic_to_shared(sB);
+                for (int mt = 0; mt < kMT; ++mt) {
 #pragma unroll
-            for (int mt = 0; mt < kMT; ++mt) {
-#pragma unroll
-                for (int ks = 0; ks < kKC / 32; ++ks) {
-                    const uint64_t da = umma_desc(a0 + mt * kABlock + ks * 2 * 16 * 128, 16 * 128, 128);
-                    const uint64_t db = (dbg & 2) ? umma_desc(b0 + ks * 2 * (kNT / 8) * 128, (kNT / 8) * 128, 128)
-                                                  : umma_desc(b0 + ks * 4 * (kNT / 16) * 128, (kNT / 16) * 128, 128);
-                    const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + mt * kNT),
-                        "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                        : "memory");
+                    for (int ks = 0; ks < kKC / 32; ++ks) {
+                        const uint64_t da = umma_desc(a0 + mt * kABlock + ks * 2 * 16 * 128, 16 * 128, 128);
+                        const uint64_t db = umma_desc(b0 + ks * 4 * (kNT / 16) * 128, (kNT / 16) * 128, 128);
+                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + mt * kNT),
+                            "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                            : "memory");
+                    }
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(&free_bar[st]))
+                             : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             (unsigned)__cvta_generic_to_shared(&free_bar[st]))
+                             (unsigned)__cvta_generic_to_shared(&done_bar))
                          : "memory");
-            if (kc == kchunks - 1)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 (unsigned)__cvta_generic_to_shared(&done_bar))
-                             : "memory");
+        }
+    } else {
+        // ---- producers: expansion role of this thread: qubit kq of the chunk, shot words 2*wp, 2*wp+1 ----
+        const int kq = tid % kKC, wp = tid / kKC;             // 64 x 4
+        auto issue_copies = [&](int c) {                      // 16 KB block of the pre-laid-out H + 2 KB of error bits
+            const int st = c % kStages, use = c / kStages;
+            if (use > 0) mbar_wait_parity(&free_bar[st], (unsigned)((use - 1) & 1));
+            uint8_t* sA = smem + (size_t)st * kStageBytes;
+            const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
+            for (int i = tid; i < kABytes / 16; i += kProducers) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
+            }
+            if (tid < 2 * kKC) {                              // qubit c*64 + q, shot words w0 + 4*half .. +3
+                const int q = tid >> 1, half = tid & 1;
+                const int j = c * kKC + q;
+                const int64_t w = w0 + 4 * half;
+                uint8_t* dstp = sA + kABytes + kBBytes + q * (kNT / 8) + half * 16;
+                if (j < n && w < e_stride) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(dstp);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(e + (int64_t)j * e_stride + w)
+                                 : "memory");
+                } else {
+                    *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        };
+        for (int c = 0; c < kAhead && c < kchunks; ++c) {
+            issue_copies(c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int st = kc % kStages;
+            uint8_t* sB = smem + (size_t)st * kStageBytes + kABytes;
+            if (kc + kAhead < kchunks) issue_copies(kc + kAhead);
+            asm volatile("cp.async.commit_group;" ::: "memory");                  // one group per iteration (possibly empty)
+            asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");      // my copies of chunk kc have landed
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");         // ... and every producer's
+            // B: expand 64 shots of qubit kc*64+kq to bytes
+            {
+                const uint2 bits = *reinterpret_cast<const uint2*>(sB + kBBytes + kq * (kNT / 8) + wp * 8);
+                const uint32_t wv[2] = {bits.x, bits.y};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {                 // 4 groups of 16 shots
+                    const uint32_t v = wv[h >> 1] >> (16 * (h & 1));
+                    const uint4 bytes = make_uint4(spread4(v & 0xFu), spread4((v >> 4) & 0xFu),
+                                                   spread4((v >> 8) & 0xFu), spread4((v >> 12) & 0xFu));
+                    const int nb = (2 * wp) * 2 + h;          // 16-shot group index within the tile
+                    *reinterpret_cast<uint4*>(sB + (size_t)(kq / 8) * (kNT / 16) * 128 + nb * 128 + (kq % 8) * 16) = bytes;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic writes -> tensor-core reads
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[st]))
+                         : "memory");
         }
     }
     // ---- epilogue: bit 0 of the accumulators -> syndrome words ------------------------------------
     mbar_wait_parity(&done_bar, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
+    if (warp < kProducers / 32) {
         const int mt = warp >> 2, lane_base = (warp & 3) * 32;
         const int row = (mg * kMT + mt) * 128 + lane_base + lane;
         uint32_t out[kNT / 32];

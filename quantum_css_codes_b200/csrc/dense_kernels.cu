@@ -152,17 +152,17 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
             }
-            if (tid < 2 * kKC) {                              // qubit c*64 + q, shot words w0 + 4*half .. +3
-                const int q = tid >> 1, half = tid & 1;
-                const int j = c * kKC + q;
-                const int64_t w = w0 + 4 * half;
-                uint8_t* dstp = sA + kABytes + kBBytes + q * (kNT / 8) + half * 16;
+            {   // the 8 bytes of error bits THIS thread expands (qubit c*64 + kq, shot words w0 + 2wp, +1): no other
+                // producer reads them, so no barrier is needed between the copy and the expansion
+                const int j = c * kKC + kq;
+                const int64_t w = w0 + 2 * wp;
+                uint8_t* dstp = sA + kABytes + kBBytes + wp * (kKC * 8) + kq * 8;      // [wp][kq]: lanes contiguous
                 if (j < n && w < e_stride) {
                     const unsigned dst = (unsigned)__cvta_generic_to_shared(dstp);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(e + (int64_t)j * e_stride + w)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(e + (int64_t)j * e_stride + w)
                                  : "memory");
                 } else {
-                    *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint2*>(dstp) = make_uint2(0u, 0u);
                 }
             }
         };
@@ -176,10 +176,9 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
             if (kc + kAhead < kchunks) issue_copies(kc + kAhead);
             asm volatile("cp.async.commit_group;" ::: "memory");                  // one group per iteration (possibly empty)
             asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");      // my copies of chunk kc have landed
-            asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");         // ... and every producer's
             // B: expand 64 shots of qubit kc*64+kq to bytes
             {
-                const uint2 bits = *reinterpret_cast<const uint2*>(sB + kBBytes + kq * (kNT / 8) + wp * 8);
+                const uint2 bits = *reinterpret_cast<const uint2*>(sB + kBBytes + wp * (kKC * 8) + kq * 8);
                 const uint32_t wv[2] = {bits.x, bits.y};
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {                 // 4 groups of 16 shots

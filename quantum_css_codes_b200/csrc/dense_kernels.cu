@@ -89,7 +89,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[i])),
-                         "r"(kProducers));
+                         "r"(kProducers / 32 + 1));            // one arrival per producer warp + the H bulk copy
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&free_bar[i])));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&done_bar)));
@@ -115,7 +115,6 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
             for (int kc = 0; kc < kchunks; ++kc) {
                 const int st = kc % kStages, use = kc / kStages;
                 mbar_wait_parity(&full_bar[st], (unsigned)(use & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint8_t* sA = smem + (size_t)st * kStageBytes;
                 const uint32_t a0 = (unsigned)__cvta_generic_to_shared(sA), b0 = a0 + kABytes;
 #pragma unroll
@@ -147,10 +146,15 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
             const int st = c % kStages, use = c / kStages;
             if (use > 0) mbar_wait_parity(&free_bar[st], (unsigned)((use - 1) & 1));
             uint8_t* sA = smem + (size_t)st * kStageBytes;
-            const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
-            for (int i = tid; i < kABytes / 16; i += kProducers) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(sA + i * 16);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(asrc + i * 16) : "memory");
+            if (tid == 0) {
+                // the pre-laid-out 16 KB block of H: ONE bulk copy (TMA), completing on the stage's full barrier
+                const uint8_t* asrc = hq + ((size_t)mg * kchunks + c) * kABytes;
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[st]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kABytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(sA)),
+                             "l"(asrc), "r"(kABytes), "r"(bar)
+                             : "memory");
             }
             {   // the 8 bytes of error bits THIS thread expands (qubit c*64 + kq, shot words w0 + 2wp, +1): no other
                 // producer reads them, so no barrier is needed between the copy and the expansion
@@ -190,8 +194,10 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic writes -> tensor-core reads
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[st]))
-                         : "memory");
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[st]))
+                             : "memory");
         }
     }
     // ---- epilogue: bit 0 of the accumulators -> syndrome words ------------------------------------

@@ -107,7 +107,7 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
     const uint32_t tmem_base = tmem_base_s;
     // instruction descriptor: D = S32, A = B = unsigned 8-bit, A K-major, B MN-major, N = 256, M = 128
     const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    constexpr int kAhead = 3;                                 // H blocks and error bits are fetched three chunks ahead
+    constexpr int kAhead = 4;                                 // H blocks and error bits are fetched four chunks ahead
 
     if (warp == kProducers / 32) {
         // ---- MMA warp: one lane, no block barriers ------------------------------------------------------
@@ -170,34 +170,46 @@ k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, 
                 }
             }
         };
-        for (int c = 0; c < kAhead && c < kchunks; ++c) {
-            issue_copies(c);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        for (int kc = 0; kc < kchunks; ++kc) {
+        // Two chunks per iteration: their expansions interleave (the iteration is a chain of dependent
+        // instructions, so one chunk at a time left the tensor pipe waiting ~1000 cycles per chunk), and the
+        // refill of the stages four and five chunks ahead comes AFTER the expansion, off the critical path.
+        auto expand = [&](int kc) {
             const int st = kc % kStages;
             uint8_t* sB = smem + (size_t)st * kStageBytes + kABytes;
-            if (kc + kAhead < kchunks) issue_copies(kc + kAhead);
-            asm volatile("cp.async.commit_group;" ::: "memory");                  // one group per iteration (possibly empty)
-            asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");      // my copies of chunk kc have landed
-            // B: expand 64 shots of qubit kc*64+kq to bytes
-            {
-                const uint2 bits = *reinterpret_cast<const uint2*>(sB + kBBytes + wp * (kKC * 8) + kq * 8);
-                const uint32_t wv[2] = {bits.x, bits.y};
+            const uint2 bits = *reinterpret_cast<const uint2*>(sB + kBBytes + wp * (kKC * 8) + kq * 8);
+            const uint32_t wv[2] = {bits.x, bits.y};
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {                 // 4 groups of 16 shots
-                    const uint32_t v = wv[h >> 1] >> (16 * (h & 1));
-                    const uint4 bytes = make_uint4(spread4(v & 0xFu), spread4((v >> 4) & 0xFu),
-                                                   spread4((v >> 8) & 0xFu), spread4((v >> 12) & 0xFu));
-                    const int nb = (2 * wp) * 2 + h;          // 16-shot group index within the tile
-                    *reinterpret_cast<uint4*>(sB + (size_t)(kq / 8) * (kNT / 16) * 128 + nb * 128 + (kq % 8) * 16) = bytes;
-                }
+            for (int h = 0; h < 4; ++h) {                     // 4 groups of 16 shots
+                const uint32_t v = wv[h >> 1] >> (16 * (h & 1));
+                const uint4 bytes = make_uint4(spread4(v & 0xFu), spread4((v >> 4) & 0xFu),
+                                               spread4((v >> 8) & 0xFu), spread4((v >> 12) & 0xFu));
+                const int nb = (2 * wp) * 2 + h;              // 16-shot group index within the tile
+                *reinterpret_cast<uint4*>(sB + (size_t)(kq / 8) * (kNT / 16) * 128 + nb * 128 + (kq % 8) * 16) = bytes;
             }
+        };
+        auto arrive = [&](int kc) {
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(&full_bar[kc % kStages]))
+                             : "memory");
+        };
+        for (int c = 0; c < kAhead && c < kchunks; c += 2) {          // chunks 0..3 as two groups
+            issue_copies(c);
+            if (c + 1 < kchunks) issue_copies(c + 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kc = 0; kc < kchunks; kc += 2) {
+            const bool two = kc + 1 < kchunks;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");      // my bits of chunks kc, kc+1 have landed
+            expand(kc);
+            if (two) expand(kc + 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic writes -> tensor-core reads
             __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[st]))
-                             : "memory");
+            arrive(kc);
+            if (two) arrive(kc + 1);
+            if (kc + kAhead < kchunks) issue_copies(kc + kAhead);
+            if (kc + kAhead + 1 < kchunks) issue_copies(kc + kAhead + 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");                  // one group per iteration (possibly empty)
         }
     }
     // ---- epilogue: bit 0 of the accumulators -> syndrome words ------------------------------------

@@ -76,9 +76,17 @@ def bind_to_gpu_numa_node(device_index):
     path otherwise cross the socket interconnect for half of the ranks).  Returns the node or None."""
     import os
     try:
-        import torch
-        prop = torch.cuda.get_device_properties(device_index)
-        bus_id = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        bus_id = None
+        try:
+            import torch
+            prop = torch.cuda.get_device_properties(device_index)
+            bus_id = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        except Exception:
+            import pynvml
+            pynvml.nvmlInit()
+            raw = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            raw = raw.decode() if isinstance(raw, bytes) else raw          # "00000000:1B:00.0"
+            bus_id = raw.lower()[-12:]
         with open(f"/sys/bus/pci/devices/{bus_id}/numa_node") as fh:
             node = int(fh.read().strip())
         if node < 0:

@@ -2,4 +2,4 @@
 (test/test_css_code.py:5-7).  Everything lives in quantum_css_codes_b200.css_code."""
 from quantum_css_codes_b200.css_code import (            # noqa: F401
     CSSCode, SyndromeCode, syndrome_table, syndrome_table_gpu, swap_columns, normalize_parity_check,
-    codes_equal, is_doubly_even, InvalidCodeError, UnsupportedGateError)
+    codes_equal, is_doubly_even, quil_classical_correct, quil_classical_detect, InvalidCodeError, UnsupportedGateError)

@@ -10,8 +10,12 @@ What is mirrored (same names, argument meaning, exceptions, evaluation order):
   codes_equal, is_doubly_even                         css_code.py:715-735, 783-785, 809-850
 What is new (the Monte-Carlo hot path the north star adds):
   CSSCode.syndromes / decode / decode_xz / monte_carlo / sample_errors  -> CUDA kernels K1-K3
+Host-side tie to the on-wire decoder:
+  quil_classical_correct / quil_classical_detect      css_code.py:649-713 -- same signature; the
+  instructions are appended to ``prog`` as Quil text lines (``quil_text.py``; a list, or anything with
+  ``+=`` such as a pyquil Program, which parses strings), and ``quil_text.run`` interprets them.
 Out of scope here (stays with the reference's host code): every method that
-emits Quil into a pyquil Program (encode_*, error_correct, measure, quil_classical_*).
+emits quantum gates into a pyquil Program (encode_*, error_correct, measure, ftqc rewriting).
 
 Naming follows the reference's (inverted) convention, css_code.py:28-30 and 461-470:
   X errors <-> parity_check_c2 / _c2_syndromes / z_operator_matrix      ("which" = 2)
@@ -149,6 +153,27 @@ def codes_equal(parity_check_1, parity_check_2) -> bool:
 def is_doubly_even(mat):
     """True when every row weight is a multiple of 4 (css_code.py:846-850)."""
     return not np.any(np.mod(np.sum(mat, axis=1), 4))
+
+
+def quil_classical_correct(prog, codeword, errors, scratch, parity_check, syndromes):
+    """css_code.quil_classical_correct (css_code.py:649-685): append the classical Quil that extracts
+    the syndrome of ``codeword ^ errors`` and folds the matching table correction into ``errors``.
+    ``codeword`` / ``errors`` / ``scratch`` are ``quil_text.Chunk`` register slices (or anything
+    indexable to ``name[i]`` cells with slicing); instructions are appended to ``prog`` one text
+    line at a time, in the reference's order."""
+    from . import quil_text
+    for line in quil_text.quil_classical_correct(codeword, errors, scratch, parity_check, syndromes):
+        prog += [line] if isinstance(prog, list) else line
+    return prog
+
+
+def quil_classical_detect(prog, codeword, errors, outcome, scratch, parity_check):
+    """css_code.quil_classical_detect (css_code.py:687-713): ``outcome`` = 1 iff the syndrome of
+    ``codeword ^ errors`` is non-zero."""
+    from . import quil_text
+    for line in quil_text.quil_classical_detect(codeword, errors, outcome, scratch, parity_check):
+        prog += [line] if isinstance(prog, list) else line
+    return prog
 
 
 class CSSCode:

@@ -184,6 +184,36 @@ QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch
 QCSS_API int qcss_gf2_solve_dev(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
                        int32_t* d_consistent, void* stream);
 
+/* ---- CSS construction numerics on the device.
+ *      qcss_gf2_normalize replaces css_code.normalize_parity_check (css_code.py:809-836): every matrix
+ *      (layout as for qcss_gf2_rref) is brought to [.. I ..] with the identity block at columns
+ *      offset .. offset+m-1 using the reference's pivot rule -- first row at or below the diagonal with a
+ *      1 in the pivot column, else a QUBIT swap of the pivot column with the first later column where
+ *      row i has a 1.  out = np.mod(h, 2) of the reference; swaps[b][k] = (i + offset, col) pairs in
+ *      order, n_swaps[b] of them, capacity n pairs per matrix (unused entries -1); status[b] = 0 or
+ *      QCSS_FORM_DEPENDENT_ROWS ("rows are not independent", css_code.py:825-826; out is then
+ *      unspecified).  n < offset + m fails with QCSS_ERR_INVALID "not enough columns" (:811-812).
+ *      The _dev form works in place on device matrices.
+ *      qcss_css_standard_form replaces the numeric core of CSSCode.__init__ (css_code.py:47-61): the CSS
+ *      condition H1.H2^T = 0 mod 2, H1 normalised at offset 0 with its swaps replayed on H2, then H2
+ *      normalised at offset r1 with its swaps replayed on H1.  *status = 0, QCSS_FORM_NOT_CSS
+ *      ("C_2 dual code must be a subspace of C_1", :48-49), QCSS_FORM_DEPENDENT_ROWS_C1 / _C2 or
+ *      QCSS_FORM_FEW_COLUMNS_C1 / _C2 -- whichever the reference would raise first.
+ *      swaps (capacity n pairs, may be NULL) logs both stages in order; *n_swaps their count. ------- */
+#define QCSS_FORM_OK                0
+#define QCSS_FORM_NOT_CSS           1
+#define QCSS_FORM_DEPENDENT_ROWS    2
+#define QCSS_FORM_DEPENDENT_ROWS_C1 2
+#define QCSS_FORM_DEPENDENT_ROWS_C2 3
+#define QCSS_FORM_FEW_COLUMNS_C1    4   /* "not enough columns": n < r1, or n < r1 + r2 (css_code.py:811-812), */
+#define QCSS_FORM_FEW_COLUMNS_C2    5   /* reported in the reference's order of checks                          */
+QCSS_API int qcss_gf2_normalize(const uint64_t* mats, int batch, int m, int n, int offset, uint64_t* out, int32_t* swaps,
+                       int32_t* n_swaps, int32_t* status);
+QCSS_API int qcss_gf2_normalize_dev(uint64_t* d_mats, int batch, int m, int n, int offset, int32_t* d_swaps,
+                           int32_t* d_n_swaps, int32_t* d_status, void* stream);
+QCSS_API int qcss_css_standard_form(const uint64_t* H1, int r1, const uint64_t* H2, int r2, int n, uint64_t* out1,
+                           uint64_t* out2, int32_t* swaps, int32_t* n_swaps, int32_t* status);
+
 /* ---- GPU-assisted syndrome table: replaces the weight-layer search of css_code.syndrome_table
  *      (css_code.py:715-735; bin_matrix.weight_w_vectors order, bin_matrix.py:57-72).
  *      H: row-major 0/1 bytes of an m x n parity check, n <= 64, m <= 62.  Layers w = 0, 1, ... are

@@ -95,6 +95,12 @@ PROTOTYPES = {
                                      ctypes.c_void_p, _c_i32p, _c_i32p]),
     "qcss_gf2_rref_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_gf2_normalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, _c_i32p, _c_i32p, _c_i32p]),
+    "qcss_gf2_normalize_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_css_standard_form": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, _c_i32p]),
     "qcss_table_build": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_u8p, ctypes.c_int64,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
                                         ctypes.POINTER(ctypes.c_int64)]),
@@ -376,6 +382,46 @@ def gf2_solve_packed(packed, rhs_packed, n):
     ok = np.zeros(batch, dtype=np.int32)
     check(lib.qcss_gf2_solve(_ptr(packed), _ptr(rhs_packed), batch, m, n, _ptr(x), ok.ctypes.data_as(_c_i32p)))
     return x, ok
+
+
+FORM_NOT_CSS, FORM_DEPENDENT_ROWS_C1, FORM_DEPENDENT_ROWS_C2, FORM_FEW_COLUMNS_C1, FORM_FEW_COLUMNS_C2 = 1, 2, 3, 4, 5
+
+
+def gf2_normalize_packed(packed, n, offset):
+    """(batch, m, words) packed matrices -> (normalised, swaps list per matrix, status (batch,)) through
+    qcss_gf2_normalize: the standard form of css_code.normalize_parity_check with its column-swap rule."""
+    lib = load()
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    if packed.ndim != 3:
+        raise ValueError("expected (batch, m, words) packed matrices")
+    batch, m, words = packed.shape
+    if words != (n + 63) // 64:
+        raise ValueError("words must be ceil(n / 64)")
+    out = np.empty_like(packed)
+    swaps = np.full((batch, max(n, 1), 2), -1, dtype=np.int32)
+    counts = np.zeros(batch, dtype=np.int32)
+    status = np.zeros(batch, dtype=np.int32)
+    check(lib.qcss_gf2_normalize(_ptr(packed), batch, m, n, int(offset), _ptr(out), swaps.ctypes.data_as(_c_i32p),
+                                 counts.ctypes.data_as(_c_i32p), status.ctypes.data_as(_c_i32p)))
+    lists = [[(int(a), int(b)) for a, b in swaps[i, :counts[i]]] for i in range(batch)]
+    return out, lists, status
+
+
+def css_standard_form_bits(h1_u8, h2_u8):
+    """qcss_css_standard_form on 0/1 byte matrices -> (status, H1', H2', swaps)."""
+    lib = load()
+    h1 = np.ascontiguousarray(h1_u8, dtype=np.uint8)
+    h2 = np.ascontiguousarray(h2_u8, dtype=np.uint8)
+    (r1, n), (r2, _) = h1.shape, h2.shape
+    p1, p2 = pack_bits(h1), pack_bits(h2)
+    o1, o2 = np.empty_like(p1), np.empty_like(p2)
+    swaps = np.full((max(n, 1), 2), -1, dtype=np.int32)
+    count = ctypes.c_int32()
+    status = ctypes.c_int32()
+    check(lib.qcss_css_standard_form(_ptr(p1), r1, _ptr(p2), r2, n, _ptr(o1), _ptr(o2),
+                                     swaps.ctypes.data_as(_c_i32p), ctypes.byref(count), ctypes.byref(status)))
+    pairs = [(int(a), int(b)) for a, b in swaps[:count.value]]
+    return status.value, unpack_bits(o1, n), unpack_bits(o2, n), pairs
 
 
 def syndrome_table_arrays(parity_check_u8, max_entries=1 << 28):

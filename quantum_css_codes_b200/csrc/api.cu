@@ -780,6 +780,102 @@ QCSS_API int qcss_gf2_solve(const uint64_t* mats, const uint64_t* rhs, int batch
     return rc;
 }
 
+// ---- CSS construction numerics ----------------------------------------------------
+
+QCSS_API int qcss_gf2_normalize_dev(uint64_t* d_mats, int batch, int m, int n, int offset, int32_t* d_swaps,
+                           int32_t* d_n_swaps, int32_t* d_status, void* stream) {
+    if (batch < 0 || m < 0 || n < 0 || offset < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (n < offset + m) return fail(QCSS_ERR_INVALID, "not enough columns");
+    if (batch == 0 || m == 0) return QCSS_OK;
+    if (!d_mats || !d_status) return fail(QCSS_ERR_INVALID, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    QCSS_CUDA(cudaMemsetAsync(d_status, 0, (size_t)batch * sizeof(int32_t), st));
+    if (d_n_swaps) QCSS_CUDA(cudaMemsetAsync(d_n_swaps, 0, (size_t)batch * sizeof(int32_t), st));
+    QCSS_CUDA(launch_gf2_normalize(d_mats, batch, m, n, offset, nullptr, 0, d_swaps, d_n_swaps, d_status,
+                                   QCSS_FORM_DEPENDENT_ROWS, st));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_gf2_normalize(const uint64_t* mats, int batch, int m, int n, int offset, uint64_t* out, int32_t* swaps,
+                       int32_t* n_swaps, int32_t* status) {
+    if (batch < 0 || m < 0 || n < 0 || offset < 0) return fail(QCSS_ERR_INVALID, "negative dimensions");
+    if (n < offset + m) return fail(QCSS_ERR_INVALID, "not enough columns");
+    if (batch == 0 || m == 0) return QCSS_OK;
+    if (!mats || !out || !status) return fail(QCSS_ERR_INVALID, "NULL argument");
+    const size_t W = (size_t)(n + 63) / 64, bytes = (size_t)batch * m * W * 8;
+    const size_t swap_bytes = (size_t)batch * n * 2 * sizeof(int32_t), cnt_bytes = (size_t)batch * sizeof(int32_t);
+    void* d_mat = nullptr;
+    int32_t *d_swaps = nullptr, *d_cnt = nullptr, *d_status = nullptr;
+    int rc = QCSS_OK;
+    cudaError_t e = cudaMalloc(&d_mat, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_swaps, swap_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_cnt, cnt_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_status, cnt_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mat, mats, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_swaps, 0xFF, swap_bytes);
+    if (e == cudaSuccess) {
+        rc = qcss_gf2_normalize_dev((uint64_t*)d_mat, batch, m, n, offset, d_swaps, d_cnt, d_status, nullptr);
+        if (rc == QCSS_OK) e = cudaDeviceSynchronize();
+    }
+    if (rc == QCSS_OK) {
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_mat, bytes, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && swaps) e = cudaMemcpy(swaps, d_swaps, swap_bytes, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && n_swaps) e = cudaMemcpy(n_swaps, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(status, d_status, cnt_bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+            rc = fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "gf2_normalize: %s",
+                      cudaGetErrorString(e));
+    }
+    cudaFree(d_mat); cudaFree(d_swaps); cudaFree(d_cnt); cudaFree(d_status);
+    return rc;
+}
+
+QCSS_API int qcss_css_standard_form(const uint64_t* H1, int r1, const uint64_t* H2, int r2, int n, uint64_t* out1,
+                           uint64_t* out2, int32_t* swaps, int32_t* n_swaps, int32_t* status) {
+    if (r1 < 1 || r2 < 1 || n < 1) return fail(QCSS_ERR_INVALID, "empty parity check");
+    if (!H1 || !H2 || !out1 || !out2 || !status) return fail(QCSS_ERR_INVALID, "NULL argument");
+    const size_t W = (size_t)(n + 63) / 64, b1 = (size_t)r1 * W * 8, b2 = (size_t)r2 * W * 8;
+    const size_t swap_bytes = (size_t)n * 2 * sizeof(int32_t);
+    void *d1 = nullptr, *d2 = nullptr;
+    int32_t *d_swaps = nullptr, *d_meta = nullptr;          // meta[0] = status, meta[1] = swap count
+    int rc = QCSS_OK;
+    cudaError_t e = cudaMalloc(&d1, b1);
+    if (e == cudaSuccess) e = cudaMalloc(&d2, b2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_swaps, swap_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_meta, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d1, H1, b1, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d2, H2, b2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_swaps, 0xFF, swap_bytes);
+    if (e == cudaSuccess) e = cudaMemset(d_meta, 0, 2 * sizeof(int32_t));
+    // css_code.py:47-49, then :55-61: H1 at offset 0 with its swaps replayed on H2, H2 at offset r1 with its
+    // swaps replayed on H1.  Each stage is skipped once the status word is non-zero; the reference's
+    // "not enough columns" checks (:811-812) sit between the stages, in its order.
+    int few_columns = 0;
+    if (e == cudaSuccess)
+        e = launch_css_condition((const uint64_t*)d1, r1, (const uint64_t*)d2, r2, n, d_meta, QCSS_FORM_NOT_CSS, 0);
+    if (n < r1) few_columns = QCSS_FORM_FEW_COLUMNS_C1;
+    if (e == cudaSuccess && !few_columns)
+        e = launch_gf2_normalize((uint64_t*)d1, 1, r1, n, 0, (uint64_t*)d2, r2, d_swaps, d_meta + 1, d_meta,
+                                 QCSS_FORM_DEPENDENT_ROWS_C1, 0);
+    if (!few_columns && n < r1 + r2) few_columns = QCSS_FORM_FEW_COLUMNS_C2;
+    if (e == cudaSuccess && !few_columns)
+        e = launch_gf2_normalize((uint64_t*)d2, 1, r2, n, r1, (uint64_t*)d1, r1, d_swaps, d_meta + 1, d_meta,
+                                 QCSS_FORM_DEPENDENT_ROWS_C2, 0);
+    int32_t meta[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(meta, d_meta, sizeof(meta), cudaMemcpyDeviceToHost);
+    if (meta[0] == 0) meta[0] = few_columns;
+    if (e == cudaSuccess) e = cudaMemcpy(out1, d1, b1, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out2, d2, b2, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && swaps) e = cudaMemcpy(swaps, d_swaps, swap_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+        rc = fail(e == cudaErrorMemoryAllocation ? QCSS_ERR_NOMEM : QCSS_ERR_CUDA, "css_standard_form: %s",
+                  cudaGetErrorString(e));
+    *status = meta[0];
+    if (n_swaps) *n_swaps = meta[1];
+    cudaFree(d1); cudaFree(d2); cudaFree(d_swaps); cudaFree(d_meta);
+    return rc;
+}
+
 // ---- GPU-assisted syndrome table -----------------------------------------------
 
 QCSS_API int qcss_table_build(int n, int m, const uint8_t* H, int64_t max_entries, qcss_table** out, int* t,

@@ -62,6 +62,13 @@ cudaError_t launch_gf2_nullspace(const uint64_t* d_mats, int batch, int m, int n
 cudaError_t launch_gf2_solve(const uint64_t* d_mats, const uint64_t* d_rhs, int batch, int m, int n, uint64_t* d_x,
                              int32_t* d_consistent, cudaStream_t stream);
 
+// standard form with the reference's column-swap pivot rule, CSS condition (gf2_normalize.cu)
+cudaError_t launch_gf2_normalize(uint64_t* d_mats, int batch, int m, int n, int offset, uint64_t* d_partner, int mp,
+                                 int32_t* d_swaps, int32_t* d_nswaps, int32_t* d_status, int fail_code,
+                                 cudaStream_t stream);
+cudaError_t launch_css_condition(const uint64_t* d_h1, int r1, const uint64_t* d_h2, int r2, int n, int32_t* d_status,
+                                 int fail_code, cudaStream_t stream);
+
 // GPU-assisted syndrome table (table_kernels.cu)
 struct TableBuild;
 cudaError_t table_build(int n, int m, const uint8_t* H, int64_t max_entries, TableBuild** out, const char** why);

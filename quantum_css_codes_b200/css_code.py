@@ -70,6 +70,36 @@ def normalize_parity_check(h, offset):
     return np.mod(h, 2), qubit_swaps
 
 
+def normalize_parity_check_gpu(h, offset):
+    """``normalize_parity_check`` on the device (``qcss_gf2_normalize``): the same
+    ``(np.mod(h, 2), qubit_swaps)`` -- same pivot rule, same swap pairs in the same order, same
+    exceptions -- computed by one CTA over bit-packed rows.  ``h`` is updated in place like the
+    reference's, except that it receives the REDUCED matrix (entries 0/1) where the reference leaves
+    un-reduced integer row sums of the same parity."""
+    r, n = h.shape
+    if n < offset + r:
+        raise ValueError("not enough columns")
+    bits = np.mod(np.asarray(h), 2).astype(np.uint8)
+    out, swaps, status = _native.gf2_normalize_packed(_native.pack_bits(bits)[None], n, offset)
+    if status[0] != 0:
+        raise InvalidCodeError("rows are not independent")
+    result = _native.unpack_bits(out[0], n).astype(h.dtype)
+    h[...] = result
+    return np.mod(h, 2), swaps[0]
+
+
+def _standard_form_gpu(h_1, h_2):
+    """CSS condition and both normalisations (css_code.py:47-61) in one ``qcss_css_standard_form`` call."""
+    status, n_1, n_2, _ = _native.css_standard_form_bits(h_1.astype(np.uint8), h_2.astype(np.uint8))
+    if status == _native.FORM_NOT_CSS:
+        raise ValueError("C_2 dual code must be a subspace of C_1")
+    if status in (_native.FORM_FEW_COLUMNS_C1, _native.FORM_FEW_COLUMNS_C2):
+        raise ValueError("not enough columns")
+    if status != 0:
+        raise InvalidCodeError("rows are not independent")
+    return n_1.astype('int'), n_2.astype('int')
+
+
 def _layer_keys(parity_check, supports):
     """Big-endian keys (bin_matrix.vec_to_int of H.e mod 2) for a block of supports."""
     m = parity_check.shape[0]
@@ -184,16 +214,21 @@ class CSSCode:
     sampling -- runs in CUDA kernels on bit-plane batches through ``libqcss.so``.
     """
 
-    def __init__(self, parity_check_c1, parity_check_c2, table_builder=None):
+    def __init__(self, parity_check_c1, parity_check_c2, table_builder=None, standard_form=None):
         """``table_builder`` (extension, not in the reference): ``"gpu"`` builds both syndrome tables
         with the device weight-layer search (``syndrome_table_gpu``); the default is the host search
-        (``syndrome_table``), which needs no GPU.  Both give identical tables."""
+        (``syndrome_table``), which needs no GPU.  Both give identical tables.
+        ``standard_form`` (extension): ``"gpu"`` runs the CSS condition and both normalisations with
+        their qubit swaps on the device (``qcss_css_standard_form``); default host numpy.  Identical
+        matrices and exceptions either way."""
         r_1, n_1 = parity_check_c1.shape
         r_2, n_2 = parity_check_c2.shape
         if n_1 != n_2:
             raise ValueError("C_1 and C_2 must have the same code word length")
         if table_builder not in (None, "host", "gpu"):
             raise ValueError("table_builder must be None, 'host' or 'gpu'")
+        if standard_form not in (None, "host", "gpu"):
+            raise ValueError("standard_form must be None, 'host' or 'gpu'")
         build_table = syndrome_table_gpu if table_builder == "gpu" else syndrome_table
 
         h_1 = np.mod(np.array(parity_check_c1, dtype='int'), 2)
@@ -203,18 +238,21 @@ class CSSCode:
         if not np.array_equal(h_2, parity_check_c2):
             raise ValueError("C_2 parity check matrix must be binary")
 
-        # CSS condition: every C_2 check is orthogonal to every C_1 check (css_code.py:47-49).
-        if np.any(np.mod(h_1 @ h_2.T, 2)):
-            raise ValueError("C_2 dual code must be a subspace of C_1")
+        if standard_form == "gpu":
+            h_1, h_2 = _standard_form_gpu(h_1, h_2)
+        else:
+            # CSS condition: every C_2 check is orthogonal to every C_1 check (css_code.py:47-49).
+            if np.any(np.mod(h_1 @ h_2.T, 2)):
+                raise ValueError("C_2 dual code must be a subspace of C_1")
 
-        # Standard form H_1 = [I A_1 A_2], H_2 = [D I E]; qubit swaps found while normalising one
-        # matrix are replayed on the other (css_code.py:55-61).
-        h_1, swaps = normalize_parity_check(h_1, offset=0)
-        for pair in swaps:
-            swap_columns(h_2, pair)
-        h_2, swaps = normalize_parity_check(h_2, offset=r_1)
-        for pair in swaps:
-            swap_columns(h_1, pair)
+            # Standard form H_1 = [I A_1 A_2], H_2 = [D I E]; qubit swaps found while normalising one
+            # matrix are replayed on the other (css_code.py:55-61).
+            h_1, swaps = normalize_parity_check(h_1, offset=0)
+            for pair in swaps:
+                swap_columns(h_2, pair)
+            h_2, swaps = normalize_parity_check(h_2, offset=r_1)
+            for pair in swaps:
+                swap_columns(h_1, pair)
 
         self._n = n_1
         self._k = n_1 - r_1 - r_2

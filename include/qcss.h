@@ -155,6 +155,21 @@ QCSS_API int qcss_mc_sample(qcss_code* code, double p, int64_t shots, uint64_t s
 QCSS_API int qcss_mc_sample_dev(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
                        uint64_t* d_ex_planes, uint64_t* d_ez_planes, int64_t e_stride, void* stream);
 
+/* ---- Pauli-frame Monte Carlo of repeated Steane error correction: the gadget emitted by
+ *      CSSCode.error_correct (css_code.py:436-470; the reference only runs it on a QVM,
+ *      test/test_fidelity.py), tracked as Pauli errors.  Per round: depolarising(p_data) on the data;
+ *      a |+>_L ancilla with depolarising(p_ancilla) takes the data's X errors through a transversal
+ *      CNOT (its Z errors flow back), is measured, and the X frame is updated exactly as
+ *      quil_classical_correct does with parity_check_c2 / _c2_syndromes (css_code.py:649-685); the same
+ *      with a |0>_L ancilla, CNOT ancilla -> data and parity_check_c1 / _c1_syndromes for Z.  After
+ *      `rounds` rounds the residual is decoded ideally and tallied like qcss_mc_run.  rounds = 1 and
+ *      p_ancilla = 0 reproduce qcss_mc_run(p_data) bit for bit; shot-sharding and first_shot as there.
+ *      The model is spelled out in csrc/ec_rounds.cuh and restated in oracle/ec_rounds.py. -------------- */
+QCSS_API int qcss_ec_run(qcss_code* code, double p_data, double p_ancilla, int rounds, int64_t shots, uint64_t seed,
+                int64_t first_shot, qcss_tally* tally);
+QCSS_API int qcss_ec_run_dev(qcss_code* code, double p_data, double p_ancilla, int rounds, int64_t shots, uint64_t seed,
+                    int64_t first_shot, uint64_t* d_tally /* [6], accumulated */, void* stream);
+
 /* ---- K4 batched GF(2) Gauss-Jordan: replaces bin_matrix.reduced_row_echelon_form
  *      (bin_matrix.py:8-34; the reference has no batch API and no rank/pivot outputs).
  *      mats: batch matrices of m rows, each row ceil(n/64) uint64 words, column 64w+j is bit j

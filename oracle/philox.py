@@ -82,12 +82,13 @@ def _blocks(seed, g, j, q):
     return philox4x32_10(ctr.astype(np.uint32), key)
 
 
-def _sample_words_gap(seed, first_word, n_words, n, p):
+def _sample_words_gap(seed, first_word, n_words, n, p, site0=0):
     cdf, _ = gap_table(p)
     g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
     ex = np.zeros((n, n_words), dtype=np.uint32)
     ez = np.zeros((n, n_words), dtype=np.uint32)
-    for j in range(n):
+    for row in range(n):
+        j = site0 + row
         w = _blocks(seed, g, j, np.zeros(n_words, dtype=np.uint64))
         hit = np.flatnonzero(w[:, 0].astype(np.uint64) < cdf[31])          # words with at least one error
         for idx in hit:
@@ -115,20 +116,23 @@ def _sample_words_gap(seed, first_word, n_words, n, p):
                 if not done:
                     buf = _blocks(seed, g[idx:idx + 1], j, np.array([blk], dtype=np.uint64))[0]
                     blk += 1
-            ex[j, idx], ez[j, idx] = x, z
+            ex[row, idx], ez[row, idx] = x, z
     return ex, ez
 
 
-def sample_words(seed, first_word, n_words, n, p, force_bit_serial=False):
-    """Sampled planes as uint32 words: (ex, ez), each (n, n_words)."""
+def sample_words(seed, first_word, n_words, n, p, force_bit_serial=False, site0=0):
+    """Sampled planes as uint32 words: (ex, ez), each (n, n_words).  Row r is Philox site ``site0 + r``
+    (the third counter word); the single-shot sampler uses sites 0..n-1, the error-correction rounds
+    (oracle/ec_rounds.py) site 32 * stream + qubit."""
     if uses_gap_sampler(p) and not force_bit_serial:
-        return _sample_words_gap(seed, first_word, n_words, n, p)
+        return _sample_words_gap(seed, first_word, n_words, n, p, site0)
     thr = threshold(p)
     g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
     ex = np.zeros((n, n_words), dtype=np.uint32)
     ez = np.zeros((n, n_words), dtype=np.uint32)
     full = np.uint32(0xFFFFFFFF)
-    for j in range(n):
+    for row in range(n):
+        j = site0 + row
         und = np.full(n_words, full, dtype=np.uint32)
         err = np.zeros(n_words, dtype=np.uint32)
         blk = np.zeros(n_words, dtype=np.uint64)
@@ -164,7 +168,7 @@ def sample_words(seed, first_word, n_words, n, p, force_bit_serial=False):
                 nd &= ~ok
             need[active], x[active], z[active] = nd, xa, za
             blk[active] += np.uint64(1)
-        ex[j], ez[j] = x, z
+        ex[row], ez[row] = x, z
     return ex, ez
 
 

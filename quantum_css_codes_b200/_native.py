@@ -86,6 +86,10 @@ PROTOTYPES = {
                                    ctypes.c_int64, ctypes.POINTER(Tally)]),
     "qcss_mc_run_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_ec_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int64,
+                                   ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(Tally)]),
+    "qcss_ec_run_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int64,
+                                       ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "qcss_mc_sample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "qcss_mc_sample_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
@@ -275,6 +279,17 @@ class DeviceCode:
         check(self._lib.qcss_mc_run(self.handle, float(p), int(shots), int(seed), int(first_shot),
                                     ctypes.byref(tally)))
         return tally.as_dict()
+
+    def ec_run(self, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0):
+        tally = Tally()
+        check(self._lib.qcss_ec_run(self.handle, float(p_data), float(p_ancilla), int(rounds), int(shots),
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_shot), ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def ec_run_dev(self, p_data, p_ancilla, rounds, shots, seed, first_shot, tally_ptr, stream=0):
+        check(self._lib.qcss_ec_run_dev(self.handle, float(p_data), float(p_ancilla), int(rounds), int(shots),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_shot),
+                                       ctypes.c_void_p(tally_ptr), ctypes.c_void_p(stream)))
 
     def mc_sample(self, p, shots, seed=0, first_shot=0):
         stride = _planes.stride_words(shots)

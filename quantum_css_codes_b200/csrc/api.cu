@@ -337,6 +337,39 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
     return QCSS_OK;
 }
 
+int launch_ec(qcss_code* c, double p_data, double p_anc, int rounds, int64_t shots, uint64_t seed, int64_t first_shot,
+              uint64_t* d_tally, cudaStream_t stream) {
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (rounds < 0 || rounds > (1 << 20)) return fail(QCSS_ERR_INVALID, "rounds must be in [0, 2^20]");
+    if (first_shot < 0 || (first_shot & 127)) return fail(QCSS_ERR_INVALID, "first_shot must be a multiple of 128");
+    if (!c->small) return fail(QCSS_ERR_UNSUPPORTED, "error-correction Monte Carlo covers n <= %d and m <= %d", kMaxN, kMaxM);
+    if (!d_tally) return fail(QCSS_ERR_INVALID, "tally is NULL");
+    if (c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
+        return fail(QCSS_ERR_INVALID, "error-correction Monte Carlo needs both syndrome tables");
+    EcLaunch l;
+    memset(&l.ec, 0, sizeof(l.ec));
+    int rc = threshold_from_p(p_data, &l.ec.thr_p);
+    if (rc) return rc;
+    if ((rc = threshold_from_p(p_anc, &l.ec.thr_q))) return rc;
+    if (shots == 0) return QCSS_OK;
+    l.x = &c->side_x;
+    l.z = &c->side_z;
+    l.named_id = c->named_id;
+    l.ec.tally = (unsigned long long*)d_tally;
+    l.ec.words = (shots + 31) / 32;
+    l.ec.tail_mask = tail_mask_for(shots);
+    l.ec.rounds = rounds;
+    l.ec.seed = seed;
+    l.ec.first_word = (uint64_t)(first_shot / 32);
+    const bool bits_only = getenv("QCSS_SAMPLER_BITS") != nullptr;      // same sampler rule as qcss_mc_run
+    l.ec.gap_p = (l.ec.thr_p < (1u << 25) && !bits_only) ? 1u : 0u;
+    l.ec.gap_q = (l.ec.thr_q < (1u << 25) && !bits_only) ? 1u : 0u;
+    gap_table_from_p(p_data, &l.ec.tab_p);
+    gap_table_from_p(p_anc, &l.ec.tab_q);
+    QCSS_CUDA(launch_ec_rounds(l, stream));
+    return QCSS_OK;
+}
+
 int launch_syndrome(qcss_code* c, int which, const uint64_t* d_e, int64_t e_stride, int64_t shots,
                     uint64_t* d_s, int64_t s_stride, cudaStream_t stream) {
     if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
@@ -641,6 +674,28 @@ QCSS_API int qcss_mc_run(qcss_code* c, double p, int64_t shots, uint64_t seed, i
     QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
     rc = launch_mc(c, p, shots, seed, first_shot, (uint64_t*)c->tally.p, nullptr, nullptr, 0, c->stream);
+    if (rc) return rc;
+    uint64_t h[6];
+    QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_ec_run_dev(qcss_code* c, double p_data, double p_ancilla, int rounds, int64_t shots, uint64_t seed,
+                    int64_t first_shot, uint64_t* d_tally, void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    return launch_ec(c, p_data, p_ancilla, rounds, shots, seed, first_shot, d_tally, (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_ec_run(qcss_code* c, double p_data, double p_ancilla, int rounds, int64_t shots, uint64_t seed,
+                int64_t first_shot, qcss_tally* tally) {
+    if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
+    rc = launch_ec(c, p_data, p_ancilla, rounds, shots, seed, first_shot, (uint64_t*)c->tally.p, c->stream);
     if (rc) return rc;
     uint64_t h[6];
     QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

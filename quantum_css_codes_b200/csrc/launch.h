@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "decode.cuh"
+#include "ec_rounds.cuh"
 
 namespace qcss {
 
@@ -20,6 +21,15 @@ int match_named(const GenericSide& x, const uint32_t* rows_x, uint32_t lx, const
                 const uint32_t* rows_z, uint32_t lz);
 const char* named_name(int id);
 int small_bucket_m(int mx, int mz);
+
+// ---- repeated Steane EC, Pauli-frame Monte Carlo (ec_kernels.cu) -------------------------------
+struct EcLaunch {
+    const GenericSide* x;
+    const GenericSide* z;
+    EcParams ec;
+    int named_id;
+};
+cudaError_t launch_ec_rounds(const EcLaunch& l, cudaStream_t stream);
 
 // ---- any-size sparse syndrome (tiled_kernels.cu) --------------------------------------------
 struct SparseRows {            // CSR of one parity-check matrix, device pointers

@@ -393,6 +393,18 @@ class CSSCode:
         kernel); returns the tally dict."""
         return self.device.mc_run(p, shots, seed, first_shot)
 
+    def error_correct_monte_carlo(self, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0):
+        """Pauli-frame Monte Carlo of ``rounds`` repetitions of the Steane error-correction gadget that
+        ``error_correct`` emits in the reference (css_code.py:436-470): each round the data block
+        suffers depolarising(p_data), a |+>_L and a |0>_L ancilla with depolarising(p_ancilla) extract
+        the X and Z syndromes through transversal CNOTs (with their back-action on the data), and the
+        Pauli frames are updated as ``quil_classical_correct`` does with ``_c2_syndromes`` /
+        ``_c1_syndromes``; the residual after the last round is decoded ideally.  Entirely on the
+        device (``qcss_ec_run``: sampler, syndromes, lookups and frames in registers); returns the tally
+        dict of ``monte_carlo``.  ``rounds=1, p_ancilla=0`` is ``monte_carlo(p_data)`` bit for bit.
+        Model and Philox stream layout: ``csrc/ec_rounds.cuh``."""
+        return self.device.ec_run(p_data, p_ancilla, rounds, shots, seed, first_shot)
+
     def sample_errors(self, p, shots, seed=0, first_shot=0):
         """The error batch ``monte_carlo`` would draw, as ((shots, n), (shots, n)) uint8."""
         ex, ez = self.device.mc_sample(p, shots, seed, first_shot)

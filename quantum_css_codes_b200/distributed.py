@@ -70,6 +70,22 @@ def monte_carlo_sharded(code, p, total_shots, seed=0, rank=None, world_size=None
     return allreduce_tally(local)
 
 
+def error_correct_sharded(code, p_data, p_ancilla, rounds, total_shots, seed=0, rank=None, world_size=None,
+                          local_run=None):
+    """The repeated-error-correction Monte Carlo (``CSSCode.error_correct_monte_carlo``) sharded like
+    ``monte_carlo_sharded``: Philox streams are keyed by the global shot word, so the all-reduced tally
+    is the single-GPU tally of the same seed for any number of ranks."""
+    import torch.distributed as dist
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    first, shots = shard_range(total_shots, rank, world_size)
+    run = local_run if local_run is not None else code.error_correct_monte_carlo
+    local = run(p_data, p_ancilla, rounds, shots, seed, first) if shots > 0 else {k: 0 for k in TALLY_FIELDS}
+    return allreduce_tally(local)
+
+
 def bind_to_gpu_numa_node(device_index):
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers
     allocated afterwards are local to the GPU's PCIe root (host-to-device copies of the end-to-end

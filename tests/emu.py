@@ -36,10 +36,21 @@ class DecodeIO(ctypes.Structure):
                 ("use_gap", ctypes.c_uint32), ("gap_cdf", ctypes.c_uint32 * 32), ("gap_inv", ctypes.c_uint32)]
 
 
+class GapTable(ctypes.Structure):
+    _fields_ = [("cdf", ctypes.c_uint32 * 32), ("inv", ctypes.c_uint32)]
+
+
+class EcParams(ctypes.Structure):
+    _fields_ = [("tally", ctypes.c_void_p), ("words", ctypes.c_int64), ("tail_mask", ctypes.c_uint32),
+                ("rounds", ctypes.c_int32), ("seed", ctypes.c_uint64), ("first_word", ctypes.c_uint64),
+                ("thr_p", ctypes.c_uint32), ("thr_q", ctypes.c_uint32), ("gap_p", ctypes.c_uint32),
+                ("gap_q", ctypes.c_uint32), ("tab_p", GapTable), ("tab_q", GapTable)]
+
+
 def _needs_build():
     if not os.path.exists(LIB):
         return True
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("core.cuh", "decode.cuh", "named_codes.inc")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("core.cuh", "decode.cuh", "ec_rounds.cuh", "named_codes.inc")]
     return os.path.getmtime(LIB) < max(os.path.getmtime(p) for p in deps)
 
 
@@ -167,3 +178,28 @@ def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1,
     out["tally"] = dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
                         miss_x=int(tally[4]), miss_z=int(tally[5]))
     return out
+
+
+def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0, named_id=-1):
+    """Host emulation of qcss_ec_run (api.cu::launch_ec + ec_kernels.cu): returns the tally dict."""
+    from oracle import philox as _ophilox
+    L = lib()
+    assert L.emu_sizeof_ec() == ctypes.sizeof(EcParams)
+    ec = EcParams()
+    ec.words = (shots + 31) // 32
+    ec.tail_mask = (1 << (shots % 32)) - 1 if shots % 32 else 0xFFFFFFFF
+    ec.rounds, ec.seed, ec.first_word = rounds, seed, first_shot // 32
+    for tag, p in (("p", p_data), ("q", p_ancilla)):
+        setattr(ec, "thr_" + tag, _ophilox.threshold(p))
+        setattr(ec, "gap_" + tag, 1 if _ophilox.uses_gap_sampler(p) else 0)
+        cdf, inv = _ophilox.gap_table(p)
+        tab = getattr(ec, "tab_" + tag)
+        for k in range(32):
+            tab.cdf[k] = int(cdf[k])
+        tab.inv = inv
+    tally = np.zeros(6, dtype=np.uint64)
+    rc = L.emu_ec(ctypes.byref(side_x.c), ctypes.byref(side_z.c), ctypes.byref(ec), named_id,
+                  tally.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    assert rc == 0
+    return dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
+                miss_x=int(tally[4]), miss_z=int(tally[5]))

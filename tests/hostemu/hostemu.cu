@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../quantum_css_codes_b200/csrc/decode.cuh"
+#include "../../quantum_css_codes_b200/csrc/ec_rounds.cuh"
 #include "../../quantum_css_codes_b200/csrc/named_codes.inc"
 
 using namespace qcss;
@@ -48,9 +49,51 @@ void run_named(const GenericSide* x, const GenericSide* z, const DecodeIO& io, i
     else run<StaticPolicy<DX>, StaticPolicy<DZ>, 4, false>(px, pz, io, x, z, tally);
 }
 
+template <class PX, class PZ>
+void run_ec(const PX& px, const PZ& pz, const EcParams& ec, const GenericSide* gx, const GenericSide* gz,
+            uint64_t* tally) {
+    const SideLut lut_x{gx->lut_fm, gx->lut_corr, (const uint8_t*)gx->lut_e32};
+    const SideLut lut_z{gz->lut_fm, gz->lut_corr, (const uint8_t*)gz->lut_e32};
+    for (int64_t w = 0; w < ec.words; ++w) {
+        Counters c = {0, 0, 0, 0, 0};
+        process_ec_word<PX, PZ>(px, pz, ec, ec.tab_p, ec.tab_q, w, lut_x, lut_z, c);
+        tally[1] += c.fail_x; tally[2] += c.fail_z; tally[3] += c.fail_any;
+        tally[4] += c.miss_x; tally[5] += c.miss_z;
+    }
+}
+
+template <int NB, int MB>
+void run_ec_generic(const GenericSide* x, const GenericSide* z, const EcParams& ec, uint64_t* tally) {
+    GenericPolicy<NB, MB> px{x}, pz{z};
+    run_ec(px, pz, ec, x, z, tally);
+}
+
 }  // namespace
 
 extern "C" {
+
+__attribute__((visibility("default"))) int emu_sizeof_ec(void) { return (int)sizeof(EcParams); }
+
+// ec_kernels.cu::launch_ec_rounds, one word after the other on the host
+__attribute__((visibility("default")))
+int emu_ec(const GenericSide* x, const GenericSide* z, const EcParams* ec, int named_id, uint64_t* tally) {
+#define EMU_EC_CASE(ID, DX, DZ) \
+    if (named_id == ID) { run_ec(StaticPolicy<named::DX>{}, StaticPolicy<named::DZ>{}, *ec, x, z, tally); return 0; }
+    QCSS_FOR_EACH_NAMED(EMU_EC_CASE)
+#undef EMU_EC_CASE
+    const int m = x->m > z->m ? x->m : z->m;
+    const int mb = m <= kSlicedM ? kSlicedM : (m <= 8 ? 8 : 16);
+    if (x->n <= 16) {
+        if (mb == kSlicedM) run_ec_generic<16, kSlicedM>(x, z, *ec, tally);
+        else if (mb == 8) run_ec_generic<16, 8>(x, z, *ec, tally);
+        else run_ec_generic<16, 16>(x, z, *ec, tally);
+    } else {
+        if (mb == kSlicedM) run_ec_generic<32, kSlicedM>(x, z, *ec, tally);
+        else if (mb == 8) run_ec_generic<32, 8>(x, z, *ec, tally);
+        else run_ec_generic<32, 16>(x, z, *ec, tally);
+    }
+    return 0;
+}
 
 __attribute__((visibility("default"))) int emu_sizeof_side(void) { return (int)sizeof(GenericSide); }
 __attribute__((visibility("default"))) int emu_sizeof_io(void) { return (int)sizeof(DecodeIO); }

@@ -87,7 +87,11 @@ def test_normalize_gpu_golden(norm_golden):
 def test_normalize_gpu_random_vs_oracle(r, n, offset):
     """(768, 1600) rows fit shared memory (150 KB); see the next test for the global-memory path."""
     rng = np.random.default_rng(r * 1000 + n + offset)
-    a = random_full_rank(rng, r, n, offset) if n > offset + r else np.eye(r, dtype=np.int64)
+    if n > offset + r:
+        a = random_full_rank(rng, r, n, offset)
+    else:                                                    # no room for swaps: any invertible trailing block
+        a = rng.integers(0, 2, size=(r, n), dtype=np.int64)
+        a[:, offset:] = np.triu(rng.integers(0, 2, size=(r, r)), 1) + np.eye(r, dtype=np.int64)
     want, want_swaps = ocss.normalize_parity_check(a.copy(), offset)
     got, got_swaps = css_code.normalize_parity_check_gpu(a.copy(), offset)
     assert np.array_equal(got, want)

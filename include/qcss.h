@@ -117,6 +117,18 @@ QCSS_API int qcss_syndrome(qcss_code* code, int which, const uint64_t* e_planes,
 QCSS_API int qcss_syndrome_dev(qcss_code* code, int which, const uint64_t* d_e_planes, int64_t e_stride,
                       int64_t shots, uint64_t* d_s_planes, int64_t s_stride, void* stream);
 
+/* ---- The same syndrome idiom (css_code.py:728) on TILE-MAJOR batches, for the sparse any-size path
+ *      (codes beyond the lookup decoder's n <= 32 / m <= 16, e.g. hypergraph products):
+ *      e_tiles[tile][plane j][16 uint64] -- the n plane rows of one tile of 1024 shots are contiguous
+ *      (shot s of the batch = bit s % 64 of word (s % 1024) / 64 of row j of tile s / 1024); the last
+ *      tile is padded with zero bits.  s_tiles[tile][row i][16 uint64] likewise, row i = syndrome bit i
+ *      in the reference's row order.  ceil(shots / 1024) tiles each; 128-byte aligned.  One bulk copy
+ *      per part-tile instead of n separate 128-byte streams: see csrc/tiled_kernels.cu.
+ *      QCSS_ERR_UNSUPPORTED for codes served by the small or dense kernels. ------------------------- */
+QCSS_API int qcss_syndrome_tiles(qcss_code* code, int which, const uint64_t* e_tiles, int64_t shots, uint64_t* s_tiles);
+QCSS_API int qcss_syndrome_tiles_dev(qcss_code* code, int which, const uint64_t* d_e_tiles, int64_t shots,
+                            uint64_t* d_s_tiles, void* stream);
+
 /* Per-syndrome histogram (the tallies a multi-GPU run all-reduces): hist[key] += number of
  * shots whose syndrome has big-endian key `key` (bin_matrix.vec_to_int, bin_matrix.py:36-43);
  * hist has 2^m uint64 entries, m <= 24.  The device form accumulates into d_hist, the host form

@@ -71,6 +71,10 @@ PROTOTYPES = {
                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
     "qcss_syndrome_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "qcss_syndrome_tiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p]),
+    "qcss_syndrome_tiles_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                               ctypes.c_void_p, ctypes.c_void_p]),
     "qcss_syndrome_hist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_void_p]),
     "qcss_syndrome_hist_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
@@ -233,6 +237,20 @@ class DeviceCode:
         out = np.zeros((self.m(which), stride), dtype=np.uint64)
         check(self._lib.qcss_syndrome(self.handle, which, _ptr(e_planes), stride, shots, _ptr(out), stride))
         return out
+
+    def syndrome_tiles(self, e_tiles, shots, which):
+        """Tile-major batches: (tiles, n, 16) uint64 -> (tiles, m, 16) uint64 (qcss_syndrome_tiles)."""
+        e_tiles = np.ascontiguousarray(e_tiles, dtype=np.uint64)
+        tiles = (shots + 1023) // 1024
+        if e_tiles.shape != (tiles, self.n, 16):
+            raise ValueError("expected (ceil(shots / 1024), n, 16) uint64 tiles")
+        out = np.zeros((tiles, self.m(which), 16), dtype=np.uint64)
+        check(self._lib.qcss_syndrome_tiles(self.handle, which, _ptr(e_tiles), shots, _ptr(out)))
+        return out
+
+    def syndrome_tiles_dev(self, which, e_ptr, shots, s_ptr, stream=0):
+        check(self._lib.qcss_syndrome_tiles_dev(self.handle, which, ctypes.c_void_p(e_ptr), shots,
+                                                ctypes.c_void_p(s_ptr), ctypes.c_void_p(stream)))
 
     def syndrome_hist_planes(self, e_planes, shots, which):
         """uint64[2^m] counts of the big-endian syndrome keys of a batch of error planes."""

@@ -532,6 +532,53 @@ QCSS_API int qcss_syndrome_dev(qcss_code* c, int which, const uint64_t* d_e, int
     return launch_syndrome(c, which, d_e, e_stride, shots, d_s, s_stride, (cudaStream_t)stream);
 }
 
+// tile-major batches (sparse any-size path only): [tile][plane][16 uint64], tile = 1024 shots
+static int launch_syndrome_tiles_checked(qcss_code* c, int which, const uint64_t* d_e, int64_t shots, uint64_t* d_s,
+                                         cudaStream_t stream) {
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (!d_e || !d_s) return fail(QCSS_ERR_INVALID, "NULL tiles");
+    if ((((uintptr_t)d_e) | ((uintptr_t)d_s)) & 127u) return fail(QCSS_ERR_INVALID, "tiles must be 128-byte aligned");
+    if (c->small || ((which == 1) ? c->dense1 : c->dense2))
+        return fail(QCSS_ERR_UNSUPPORTED, "the tile-major layout serves the sparse any-size syndrome path "
+                                          "(n > %d or m > %d, sparse rows); use qcss_syndrome_dev", kMaxN, kMaxM);
+    if (shots == 0) return QCSS_OK;
+    const SparseRows& sp = (which == 1) ? c->sp1 : c->sp2;
+    cudaError_t e = launch_syndrome_tiles(sp, (const uint32_t*)d_e, (uint32_t*)d_s, (shots + 31) / 32,
+                                          tail_mask_for(shots), stream);
+    if (e == cudaErrorInvalidValue)
+        return fail(QCSS_ERR_UNSUPPORTED, "n = %d, m = %d does not fit the tile-major ring", c->n, sp.m);
+    QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_syndrome_tiles_dev(qcss_code* c, int which, const uint64_t* d_e_tiles, int64_t shots, uint64_t* d_s_tiles,
+                            void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    return launch_syndrome_tiles_checked(c, which, d_e_tiles, shots, d_s_tiles, (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_syndrome_tiles(qcss_code* c, int which, const uint64_t* e_tiles, int64_t shots, uint64_t* s_tiles) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!e_tiles || !s_tiles) return fail(QCSS_ERR_INVALID, "NULL tiles");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const int m = (which == 1) ? c->m1 : c->m2;
+    const size_t tiles = (size_t)((shots + 1023) / 1024);
+    const size_t eb = tiles * c->n * 128, sb = tiles * m * 128;
+    if (tiles == 0) return QCSS_OK;
+    QCSS_CUDA(c->buf_a.reserve(eb));
+    QCSS_CUDA(c->buf_b.reserve(sb));
+    QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_tiles, eb, cudaMemcpyHostToDevice, c->stream));
+    rc = launch_syndrome_tiles_checked(c, which, (const uint64_t*)c->buf_a.p, shots, (uint64_t*)c->buf_b.p, c->stream);
+    if (rc) return rc;
+    QCSS_CUDA(cudaMemcpyAsync(s_tiles, c->buf_b.p, sb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
 QCSS_API int qcss_decode_dev(qcss_code* c, const qcss_decode_io* io, int64_t shots, void* stream) {
     if (!c || !io) return fail(QCSS_ERR_INVALID, "code or io is NULL");
     return launch_decode(c, io, shots, (cudaStream_t)stream);

@@ -41,6 +41,10 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes,
                                   uint32_t* s_planes, int64_t s_stride, int64_t words,
                                   uint32_t tail_mask, cudaStream_t stream);
 
+// tile-major layout: e = [tiles][n][32 words], s = [tiles][m][32 words], tile = 1024 shots
+cudaError_t launch_syndrome_tiles(const SparseRows& h, const uint32_t* e_tiles, uint32_t* s_tiles, int64_t words,
+                                  uint32_t tail_mask, cudaStream_t stream);
+
 // ---- dense syndrome on tensor cores (dense_kernels.cu) ---------------------------------------
 size_t dense_h_bytes(int m, int n);
 void dense_h_layout(int m, int n, const uint8_t* H, uint8_t* out);      // host-side operand layout

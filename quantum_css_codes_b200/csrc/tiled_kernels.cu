@@ -339,22 +339,12 @@ inline size_t split_smem_bytes(int m, int nst, SplitShape shape) {
     return (size_t)nst * shape.pp * kSplitTW * sizeof(uint32_t) + split_csr_bytes(m, shape);
 }
 
-template <int RPT, int NST>
-__global__ void __launch_bounds__(kWideThreads, 1)
-k_syndrome_ring(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, int64_t e_stride,
-                uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ int wsum[32];
-    constexpr int TW = kSplitTW, kQ = TW / 4;
-    const int pp = shape.pp, parts = shape.parts, m = h.m;
-    const uint32_t stage_bytes = (uint32_t)pp * TW * sizeof(uint32_t);
-    uint16_t* const poff = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NST * stage_bytes);   // [parts * m + 1]
-    uint16_t* const pent = poff + (size_t)parts * m + 2;                                         // [nnz]
-    const int64_t tiles = (words + TW - 1) / TW;
-    const int64_t e_chunks = e_stride / 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // ---- one-time setup: supports bucketed by part (count, scan, fill) ---------------------------
+// Supports bucketed by part (count, scan, fill): poff[part * m + row] .. poff[part * m + row + 1] index pent[],
+// whose entries are local plane index * (row bytes / 16).  Shared by the plane-major and tile-major rings.
+__device__ __forceinline__ void ring_bucket_supports(const SparseRows& h, int parts, int pp, uint16_t* poff,
+                                                     uint16_t* pent, int* wsum) {
+    constexpr int TW = kSplitTW;
+    const int m = h.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) poff[0] = 0;
     for (int i = tid; i < m; i += kWideThreads) {
         int cnt[16];
@@ -416,6 +406,25 @@ k_syndrome_ring(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, 
             pent[poff[p * m + i] + pos] = (uint16_t)((c - p * pp) * (TW * 4 / 16));
         }
     }
+
+}
+
+template <int RPT, int NST>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_syndrome_ring(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, int64_t e_stride,
+                uint32_t* __restrict__ s, int64_t s_stride, int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int wsum[32];
+    constexpr int TW = kSplitTW, kQ = TW / 4;
+    const int pp = shape.pp, parts = shape.parts, m = h.m;
+    const uint32_t stage_bytes = (uint32_t)pp * TW * sizeof(uint32_t);
+    uint16_t* const poff = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NST * stage_bytes);   // [parts * m + 1]
+    uint16_t* const pent = poff + (size_t)parts * m + 2;                                         // [nnz]
+    const int64_t tiles = (words + TW - 1) / TW;
+    const int64_t e_chunks = e_stride / 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    ring_bucket_supports(h, parts, pp, poff, pent, wsum);
 
     const int q = tid % kQ, slot = tid / kQ;
     const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -506,6 +515,109 @@ k_syndrome_ring(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, 
 template <int RPT, int NST>
 cudaError_t launch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
                         int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream);
+
+// ---- tile-major ring: the same accumulate ring fed by bulk copies ---------------------------------------
+// Layout "tiles": a batch is stored as [tile][plane][32 words] -- the n plane rows (128 B each) of one tile
+// of 1024 shots are CONTIGUOUS (n x 128 B = 200 KB for n = 1600), padded to whole tiles with zero bits.
+// A part-tile is then one contiguous run of pp x 128 B, which a single thread moves with ONE
+// cp.async.bulk (the TMA unit's 1-D path) completing on the stage's mbarrier: no per-thread cp.async
+// address arithmetic, no 1600 separate 128-byte streams per SM spread over as many DRAM pages -- the two
+// things the plane-major ring is bounded by (QCSS_RING_DBG measurements above).  Syndromes are written in
+// the same layout, [tile][row][32 words]: the 1024 threads of a CTA store 16 KB contiguous per row group.
+// The XOR loop, the per-part support buckets and the register partial sums are the plane-major ring's.
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int RPT, int NST>
+__global__ void __launch_bounds__(kWideThreads, 1)
+k_syndrome_tiles(SparseRows h, SplitShape shape, const uint32_t* __restrict__ e, uint32_t* __restrict__ s, int64_t tiles,
+                 int64_t words, uint32_t tail_mask) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int wsum[32];
+    __shared__ __align__(8) uint64_t full_bar[NST];
+    constexpr int TW = kSplitTW, kQ = TW / 4;
+    const int pp = shape.pp, parts = shape.parts, m = h.m, n = h.n;
+    const uint32_t stage_bytes = (uint32_t)pp * TW * sizeof(uint32_t);
+    uint16_t* const poff = reinterpret_cast<uint16_t*>(smem_raw + (size_t)NST * stage_bytes);
+    uint16_t* const pent = poff + (size_t)parts * m + 2;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < NST; ++st) mbar_init(&full_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    ring_bucket_supports(h, parts, pp, poff, pent, wsum);
+    __syncthreads();
+
+    const int q = tid % kQ, slot = tid / kQ;
+    const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t steps = my_tiles * parts;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    // one thread, one bulk copy per part-tile
+    auto issue = [&](int64_t step) {
+        if (tid == 0 && step < steps) {
+            const int64_t t = blockIdx.x + (step / parts) * gridDim.x;
+            const int part = (int)(step % parts);
+            const int lo = part * pp;
+            const int cnt = (n - lo) < pp ? (n - lo) : pp;
+            const uint32_t bytes = (uint32_t)cnt * TW * sizeof(uint32_t);
+            const int st = (int)(step % NST);
+            mbar_expect_tx(&full_bar[st], bytes);
+            bulk_load_1d(smem_base + (uint32_t)st * stage_bytes, e + ((size_t)t * n + lo) * TW, bytes, &full_bar[st]);
+        }
+    };
+
+    uint4 acc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int st = 0; st < NST - 1; ++st) issue(st);
+    for (int64_t step = 0; step < steps; ++step) {
+        mbar_wait(&full_bar[step % NST], (unsigned)((step / NST) & 1));      // part-tile `step` has landed
+        __syncthreads();                       // part-tile step - 1 is consumed by every thread
+        issue(step + NST - 1);                 // refill the slot consumed in the previous step
+        const int part = (int)(step % parts);
+        const uint8_t* buf = smem_raw + (size_t)(step % NST) * stage_bytes + q * 16;
+        const uint16_t* po = poff + (size_t)part * m;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = slot + r * kSplitSlots;
+            if (i < m && shape.dbg != 1) {
+                const int o0 = po[i], o1 = po[i + 1];
+                for (int k = o0; k < o1; ++k) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(buf + ((uint32_t)pent[k] << 4));
+                    acc[r].x ^= v.x; acc[r].y ^= v.y; acc[r].z ^= v.z; acc[r].w ^= v.w;
+                }
+            }
+        }
+        if (part == parts - 1) {
+            const int64_t t = blockIdx.x + (step / parts) * gridDim.x;
+            const int64_t wq = t * TW + q * 4;
+            const bool ragged = wq + 4 > words - 1;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int i = slot + r * kSplitSlots;
+                if (i < m) {
+                    uint32_t out[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+                    if (ragged) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int64_t w = wq + v;
+                            if (w >= words) out[v] = 0u;
+                            else if (w == words - 1) out[v] &= tail_mask;
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(s + ((size_t)t * m + i) * TW + q * 4) = make_uint4(out[0], out[1], out[2], out[3]);
+                }
+                acc[r] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+}
 
 // ---- L1-resident gather (experiment, QCSS_TILED_L1=1) ----------------------------------------------
 // No staging at all: thread (row slot, 16-byte chunk q) gathers the chunk of every plane in its rows'
@@ -707,6 +819,32 @@ cudaError_t launch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e
     return cudaGetLastError();
 }
 
+template <int RPT, int NST>
+cudaError_t launch_tiles(const SparseRows& h, SplitShape shape, const uint32_t* e, uint32_t* s, int64_t words,
+                         uint32_t tail_mask, cudaStream_t stream) {
+    const size_t smem = split_smem_bytes(h.m, NST, shape);
+    cudaError_t err = cudaFuncSetAttribute(k_syndrome_tiles<RPT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+    if (err != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = device_info(&sms)) != cudaSuccess) return err;
+    const int64_t tiles = (words + kSplitTW - 1) / kSplitTW;
+    int64_t grid = sms < tiles ? sms : tiles;
+    if (grid < 1) grid = 1;
+    k_syndrome_tiles<RPT, NST><<<(unsigned)grid, kWideThreads, smem, stream>>>(h, shape, e, s, tiles, words, tail_mask);
+    return cudaGetLastError();
+}
+
+template <int NST>
+cudaError_t dispatch_tiles(const SparseRows& h, SplitShape shape, const uint32_t* e, uint32_t* s, int64_t words,
+                           uint32_t tail_mask, cudaStream_t stream) {
+    const int rpt = (h.m + kSplitSlots - 1) / kSplitSlots;
+    if (rpt <= 2) return launch_tiles<2, NST>(h, shape, e, s, words, tail_mask, stream);
+    if (rpt <= 4) return launch_tiles<4, NST>(h, shape, e, s, words, tail_mask, stream);
+    if (rpt <= 6) return launch_tiles<6, NST>(h, shape, e, s, words, tail_mask, stream);
+    return launch_tiles<8, NST>(h, shape, e, s, words, tail_mask, stream);
+}
+
 template <int NST>
 cudaError_t dispatch_ring(const SparseRows& h, SplitShape shape, const uint32_t* e, int64_t e_stride, uint32_t* s,
                           int64_t s_stride, int64_t words, uint32_t tail_mask, cudaStream_t stream) {
@@ -740,6 +878,34 @@ size_t tma_stage_bytes(int n, int tw) {
 }
 
 }  // namespace
+
+// Tile-major layout (see k_syndrome_tiles): e = [tiles][n][32 words], s = [tiles][m][32 words].
+// cudaErrorInvalidValue when the shape does not fit the ring (m > 1024 rows, > 65000 support entries, or no
+// (stages, parts) split fits shared memory).
+cudaError_t launch_syndrome_tiles(const SparseRows& h, const uint32_t* e, uint32_t* s, int64_t words,
+                                  uint32_t tail_mask, cudaStream_t stream) {
+    if (h.m > 8 * kSplitSlots || h.nnz > 65000) return cudaErrorInvalidValue;
+    const size_t cap = 226 * 1024;
+    const char* knob = getenv("QCSS_TILES");               // "NST,parts" (experiments)
+    int want_nst = 0, want_parts = 0;
+    if (knob != nullptr) sscanf(knob, "%d,%d", &want_nst, &want_parts);
+    const int nsts[3] = {2, 3, 4};
+    for (int a = 0; a < 3; ++a) {
+        const int nst = nsts[a];
+        if (want_nst != 0 && nst != want_nst) continue;
+        for (int parts = (want_parts ? want_parts : (nst == 2 ? 1 : nst)); parts <= 16; ++parts) {
+            const int pp = (h.n + parts - 1) / parts;
+            const SplitShape shape{parts, pp, h.nnz, getenv("QCSS_RING_DBG") ? atoi(getenv("QCSS_RING_DBG")) : 0};
+            if (pp * 8 <= 0xFFFF && split_smem_bytes(h.m, nst, shape) <= cap) {
+                if (nst == 4) return dispatch_tiles<4>(h, shape, e, s, words, tail_mask, stream);
+                if (nst == 3) return dispatch_tiles<3>(h, shape, e, s, words, tail_mask, stream);
+                return dispatch_tiles<2>(h, shape, e, s, words, tail_mask, stream);
+            }
+            if (want_parts) break;
+        }
+    }
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e, int64_t e_stride, uint32_t* s,
                                   int64_t s_stride, int64_t words, uint32_t tail_mask,

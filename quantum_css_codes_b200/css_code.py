@@ -441,3 +441,11 @@ class SyndromeCode:
         m = (self.parity_check_c1 if which == 1 else self.parity_check_c2).shape[0]
         s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
         return _planes.unpack_planes(s_planes, shots)[:, :m]
+
+    def syndromes_tiled(self, errors, which):
+        """The same result through the tile-major layout (``planes.pack_tiles`` -> ``qcss_syndrome_tiles``):
+        the layout the sparse any-size kernel streams fastest (one bulk copy per part-tile)."""
+        errors = np.asarray(errors)
+        shots = errors.shape[0]
+        s_tiles = self.device.syndrome_tiles(_planes.pack_tiles(errors), shots, which)
+        return _planes.unpack_tiles(s_tiles, shots)

@@ -41,3 +41,43 @@ def unpack_plane(plane, shots):
     """(stride,) uint64 -> (shots,) uint8."""
     plane = np.ascontiguousarray(plane, dtype=np.uint64)
     return np.unpackbits(plane.view(np.uint8), bitorder="little")[:shots]
+
+
+# ---- tile-major batches (sparse any-size syndrome path, qcss_syndrome_tiles) ---------------------------------
+# [tile][plane][16 uint64]: the n plane rows of one tile of 1024 shots are contiguous, so a kernel stages a
+# tile (or a contiguous run of its planes) with one bulk copy; the last tile is padded with zero bits.
+TILE_SHOTS = 1024
+TILE_WORDS = TILE_SHOTS // 64
+
+
+def pack_tiles(vectors):
+    """(shots, n) 0/1 array -> (ceil(shots / 1024), n, 16) uint64 tiles."""
+    vectors = np.asarray(vectors)
+    if vectors.ndim != 2:
+        raise ValueError("expected a (shots, n) array")
+    shots, n = vectors.shape
+    tiles = (shots + TILE_SHOTS - 1) // TILE_SHOTS
+    bits = np.zeros((n, tiles * TILE_SHOTS), dtype=np.uint8)
+    bits[:, :shots] = (vectors.T & 1)
+    words = np.packbits(bits, axis=1, bitorder="little").view(np.uint64).reshape(n, tiles, TILE_WORDS)
+    return np.ascontiguousarray(words.transpose(1, 0, 2))
+
+
+def unpack_tiles(tiles, shots):
+    """(tiles, rows, 16) uint64 -> (shots, rows) uint8."""
+    tiles = np.ascontiguousarray(tiles, dtype=np.uint64)
+    count, rows, _ = tiles.shape
+    words = np.ascontiguousarray(tiles.transpose(1, 0, 2)).reshape(rows, count * TILE_WORDS)
+    bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
+    return np.ascontiguousarray(bits[:, :shots].T)
+
+
+def planes_to_tiles(planes, shots):
+    """(n, stride) plane-major words -> tile-major (same bits)."""
+    planes = np.ascontiguousarray(planes, dtype=np.uint64)
+    n = planes.shape[0]
+    tiles = (shots + TILE_SHOTS - 1) // TILE_SHOTS
+    padded = np.zeros((n, tiles * TILE_WORDS), dtype=np.uint64)
+    take = min(planes.shape[1], tiles * TILE_WORDS)
+    padded[:, :take] = planes[:, :take]
+    return np.ascontiguousarray(padded.reshape(n, tiles, TILE_WORDS).transpose(1, 0, 2))

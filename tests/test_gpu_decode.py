@@ -280,6 +280,45 @@ def test_hgp1600_syndromes_golden_and_random(golden):
             assert np.array_equal(code.syndromes(errs, which), omc.syndromes_batch(h, errs))
 
 
+def test_hgp1600_tile_major_layout(golden):
+    """The tile-major entry point (qcss_syndrome_tiles: one bulk copy per part-tile) gives the same syndromes:
+    golden reference outputs, ragged and multi-tile batches, zero padding in the last tile."""
+    hx, hz = codes.hgp1600()
+    code = SyndromeCode(hx, hz)
+    errs = np.unpackbits(golden["hgp_errs"], axis=1, bitorder="little")[:, :1600]
+    for which, key in ((2, "hgp_synd_hz"), (1, "hgp_synd_hx")):
+        want = np.unpackbits(golden[key], axis=1, bitorder="little")[:, :768]
+        assert np.array_equal(code.syndromes_tiled(errs, which), want)
+    rng = np.random.default_rng(17)
+    for shots, p in ((1, 0.5), (1023, 0.5), (1024, 0.2), (1025, 0.5), (200 * 1024 + 77, 1e-3)):
+        errs = (rng.random((shots, 1600)) < p).astype(np.uint8)
+        for which, h in ((2, hz), (1, hx)):
+            tiles = code.device.syndrome_tiles(planes.pack_tiles(errs), shots, which)
+            assert np.array_equal(planes.unpack_tiles(tiles, shots), omc.syndromes_batch(h, errs))
+            pad = np.unpackbits(tiles[-1].view(np.uint8), axis=1, bitorder="little")[:, shots - (len(tiles) - 1) * 1024:]
+            assert not pad.any()
+    small, _ = pair("steane")
+    with pytest.raises(_native.NativeLibraryError, match="tile-major layout serves the sparse"):
+        small.device.syndrome_tiles(planes.pack_tiles(np.zeros((5, 7), dtype=np.uint8)), 5, 1)
+
+
+@pytest.mark.parametrize("n,m,row_w,shots", [(40, 20, 5, 3000), (300, 130, 9, 1025), (700, 1024, 3, 5000),
+                                             (3000, 900, 6, 2500)])
+def test_tile_major_random_sparse(n, m, row_w, shots):
+    """Shapes that take 1 part (whole tile per stage), several parts, and the full 1024 rows."""
+    rng = np.random.default_rng(n * 3 + m)
+    mats = []
+    for _ in range(2):
+        h = np.zeros((m, n), dtype=np.int64)
+        for i in range(m):
+            h[i, rng.choice(n, size=row_w, replace=False)] = 1
+        mats.append(h)
+    code = SyndromeCode(mats[0], mats[1])
+    errs = (rng.random((shots, n)) < 0.3).astype(np.uint8)
+    for which in (1, 2):
+        assert np.array_equal(code.syndromes_tiled(errs, which), omc.syndromes_batch(mats[which - 1], errs))
+
+
 @pytest.mark.parametrize("n,m,row_w,shots", [(40, 20, 5, 3000), (300, 130, 9, 1025), (3000, 900, 6, 700),
                                              (6000, 64, 30, 130)])
 def test_tiled_syndromes_random_sparse(n, m, row_w, shots):

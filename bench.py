@@ -368,9 +368,25 @@ def measure_other_configs(torch, peak_gbs):
         s = torch.empty((768, stride), dtype=torch.int64, device="cuda")
         ms = timed(lambda: dev.syndrome_dev(2, e.data_ptr(), stride, shots, s.data_ptr(), stride, stream))
         gbs = (1600 + 768) / 8 * shots / ms / 1e6
-        return {"workload": "hgp n=1600 m=768, 1e8 shots resident, syndromes of one Pauli type", "ms": ms,
+        out4 = {"workload": "hgp n=1600 m=768, 1e8 shots resident, syndromes of one Pauli type", "ms": ms,
                 "shots_per_s": shots / ms * 1e3, "bound": "hbm", "gbs": gbs, "frac": gbs / peak_gbs,
-                "kernel": dev.kernel_name()}
+                "kernel": dev.kernel_name(), "layout": "plane-major"}
+        del e, s
+        tiles = (shots + 1023) // 1024
+        e = torch.randint(-2**62, 2**62, (tiles, 1600, 16), dtype=torch.int64, device="cuda")
+        s = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
+        per_type = {}
+        for which in (1, 2):
+            ms_t = timed(lambda: dev.syndrome_tiles_dev(which, e.data_ptr(), shots, s.data_ptr(), stream))
+            per_type[which] = ms_t
+        ms_t = (per_type[1] + per_type[2]) / 2
+        gbs_t = (1600 + 768) / 8 * shots / ms_t / 1e6
+        out4["tile_major"] = {"workload": "same batch stored [tile of 1024 shots][plane][128 B] (qcss_syndrome_tiles_dev), "
+                                          "mean of the two Pauli types",
+                              "ms": ms_t, "ms_which1": per_type[1], "ms_which2": per_type[2],
+                              "shots_per_s": shots / ms_t * 1e3, "gbs": gbs_t, "frac": gbs_t / peak_gbs,
+                              "kernel": "tiled-ring(tile-major, cp.async.bulk)"}
+        return out4
 
     def c5():
         batch, m, n = 4096, 1024, 2048

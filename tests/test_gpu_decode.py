@@ -290,7 +290,7 @@ def test_hgp1600_tile_major_layout(golden):
         want = np.unpackbits(golden[key], axis=1, bitorder="little")[:, :768]
         assert np.array_equal(code.syndromes_tiled(errs, which), want)
     rng = np.random.default_rng(17)
-    for shots, p in ((1, 0.5), (1023, 0.5), (1024, 0.2), (1025, 0.5), (200 * 1024 + 77, 1e-3)):
+    for shots, p in ((1, 0.5), (1023, 0.5), (1024, 0.2), (1025, 0.5), (20 * 1024 + 77, 1e-3)):
         errs = (rng.random((shots, 1600)) < p).astype(np.uint8)
         for which, h in ((2, hz), (1, hx)):
             tiles = code.device.syndrome_tiles(planes.pack_tiles(errs), shots, which)

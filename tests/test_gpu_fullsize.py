@@ -109,6 +109,50 @@ def test_c4_hgp_1e8_shots_syndrome_map_is_linear():
     torch.cuda.empty_cache()
 
 
+def test_c4_hgp_1e8_shots_tile_major_equals_plane_major_and_is_linear():
+    """Config 4 in the tile-major layout: linear over all 768 x 1e8 syndrome bits, and bit-identical to the
+    plane-major kernel on the same batch (transposed on the device)."""
+    import torch
+    hx, hz = codes.hgp1600()
+    dev = SyndromeCode(hx, hz).device
+    shots = 100_000_000
+    tiles = (shots + 1023) // 1024
+    gen = torch.Generator(device="cuda").manual_seed(1601)
+    e1 = torch.randint(-2**62, 2**62, (tiles, 1600, 16), dtype=torch.int64, device="cuda", generator=gen)
+    e2 = torch.randint(-2**62, 2**62, (tiles, 1600, 16), dtype=torch.int64, device="cuda", generator=gen)
+    valid_last = shots - (tiles - 1) * 1024                      # padding bits of the last tile must be zero
+    word, bit = divmod(valid_last, 64)
+    for t in (e1, e2):
+        t[-1, :, word + 1:] = 0
+        t[-1, :, word] &= (1 << bit) - 1
+    s1 = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
+    s2 = torch.empty_like(s1)
+    s3 = torch.empty_like(s1)
+    for which in (1, 2):
+        dev.syndrome_tiles_dev(which, e1.data_ptr(), shots, s1.data_ptr(), 0)
+        dev.syndrome_tiles_dev(which, e2.data_ptr(), shots, s2.data_ptr(), 0)
+        e1 ^= e2
+        dev.syndrome_tiles_dev(which, e1.data_ptr(), shots, s3.data_ptr(), 0)
+        e1 ^= e2
+        torch.cuda.synchronize()
+        assert bool(torch.equal(s3, s1 ^ s2)), which
+        assert bool(s1.any())
+    del s2, s3, e2
+    torch.cuda.empty_cache()
+    # the same bits plane-major: (tiles, n, 16) -> (n, tiles * 16)
+    stride = tiles * 16
+    planes_e = e1.permute(1, 0, 2).contiguous().view(1600, stride)
+    del e1
+    planes_s = torch.zeros((768, stride), dtype=torch.int64, device="cuda")
+    dev.syndrome_dev(2, planes_e.data_ptr(), stride, shots, planes_s.data_ptr(), stride, 0)
+    torch.cuda.synchronize()
+    del planes_e
+    want = planes_s.view(768, tiles, 16).permute(1, 0, 2)
+    assert bool(torch.equal(s1, want))                           # s1 holds which = 2 from the loop above
+    del s1, planes_s
+    torch.cuda.empty_cache()
+
+
 def test_c5_4096_matrices_rref_idempotent_rank_and_nullspace():
     """Config 5: all 4096 random 1024 x 2048 matrices on the device.  RREF(RREF(A)) == RREF(A); rank ==
     number of non-zero rows; the pivot block of the RREF is the identity; A.N^T == 0 with N from

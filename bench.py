@@ -397,9 +397,18 @@ def measure_other_configs(torch, peak_gbs):
         ms = timed(lambda: _native.check(lib.qcss_gf2_rref_dev(mats.data_ptr(), batch, m, n, outm.data_ptr(),
                                                                rank.data_ptr(), piv.data_ptr(), stream)))
         ops = 2.52e7 * batch / ms * 1e3
-        return {"workload": "4096 x (1024 x 2048) GF(2) RREF + rank + pivots", "ms": ms,
-                "matrices_per_s": batch / ms * 1e3, "bound": "int", "xor_word_ops_per_s": ops,
-                "frac_of_lop3_peak_1.85e13": ops / 1.85e13, "full_rank": int((rank == m).sum().item())}
+        res = {"workload": "4096 x (1024 x 2048) GF(2) RREF + rank + pivots", "ms": ms,
+               "matrices_per_s": batch / ms * 1e3, "bound": "int", "xor_word_ops_per_s": ops,
+               "frac_of_lop3_peak_1.85e13": ops / 1.85e13, "full_rank": int((rank == m).sum().item())}
+        del outm, piv
+        rows = n - m + 8
+        basis = torch.empty((batch, rows, n // 64), dtype=torch.int64, device="cuda")
+        ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ms_ns = timed(lambda: _native.check(lib.qcss_gf2_nullspace_dev(mats.data_ptr(), batch, m, n, rows, basis.data_ptr(),
+                                                                       rank.data_ptr(), ovf.data_ptr(), stream)))
+        res["with_null_space"] = {"workload": "RREF + rank + null-space basis of every matrix", "ms": ms_ns,
+                                  "matrices_per_s": batch / ms_ns * 1e3, "overflow": int(ovf.item())}
+        return res
 
     guarded("c2_fused_sampler", c2_fused)
     guarded("c3_qrm15", c3("qrm15"))

@@ -75,6 +75,12 @@ PROTOTYPES = {
                                            ctypes.c_void_p]),
     "qcss_syndrome_tiles_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_sample_syndrome_tiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p]),
+    "qcss_sample_syndrome_tiles_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
+                                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                      ctypes.c_void_p, ctypes.c_void_p]),
     "qcss_syndrome_hist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_void_p]),
     "qcss_syndrome_hist_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
@@ -251,6 +257,24 @@ class DeviceCode:
     def syndrome_tiles_dev(self, which, e_ptr, shots, s_ptr, stream=0):
         check(self._lib.qcss_syndrome_tiles_dev(self.handle, which, ctypes.c_void_p(e_ptr), shots,
                                                 ctypes.c_void_p(s_ptr), ctypes.c_void_p(stream)))
+
+    def sample_syndrome_tiles(self, p, shots, seed=0, first_shot=0, errors=False):
+        """Fused sampler + sparse syndromes (qcss_sample_syndrome_tiles): returns (sx, sz) tile arrays, plus
+        (ex, ez) when ``errors`` is set."""
+        tiles = (shots + 1023) // 1024
+        sx = np.zeros((tiles, self.m2, 16), dtype=np.uint64)
+        sz = np.zeros((tiles, self.m1, 16), dtype=np.uint64)
+        ex = np.zeros((tiles, self.n, 16), dtype=np.uint64) if errors else None
+        ez = np.zeros((tiles, self.n, 16), dtype=np.uint64) if errors else None
+        check(self._lib.qcss_sample_syndrome_tiles(self.handle, float(p), int(shots), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                   int(first_shot), _ptr(sx), _ptr(sz), _ptr(ex), _ptr(ez)))
+        return (sx, sz, ex, ez) if errors else (sx, sz)
+
+    def sample_syndrome_tiles_dev(self, p, shots, seed, first_shot, sx_ptr, sz_ptr, ex_ptr=0, ez_ptr=0, stream=0):
+        check(self._lib.qcss_sample_syndrome_tiles_dev(self.handle, float(p), int(shots), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                       int(first_shot), ctypes.c_void_p(sx_ptr), ctypes.c_void_p(sz_ptr),
+                                                       ctypes.c_void_p(ex_ptr), ctypes.c_void_p(ez_ptr),
+                                                       ctypes.c_void_p(stream)))
 
     def syndrome_hist_planes(self, e_planes, shots, which):
         """uint64[2^m] counts of the big-endian syndrome keys of a batch of error planes."""

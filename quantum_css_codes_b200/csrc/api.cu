@@ -552,6 +552,63 @@ static int launch_syndrome_tiles_checked(qcss_code* c, int which, const uint64_t
     return QCSS_OK;
 }
 
+static int launch_sample_tiles_checked(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                                       uint64_t* d_sx, uint64_t* d_sz, uint64_t* d_ex, uint64_t* d_ez, cudaStream_t stream) {
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (first_shot < 0 || (first_shot & 1023)) return fail(QCSS_ERR_INVALID, "first_shot must be a multiple of 1024 (one tile)");
+    if (!d_sx && !d_sz && !d_ex && !d_ez) return fail(QCSS_ERR_INVALID, "no output requested");
+    if ((((uintptr_t)d_sx) | ((uintptr_t)d_sz) | ((uintptr_t)d_ex) | ((uintptr_t)d_ez)) & 15u)
+        return fail(QCSS_ERR_INVALID, "tiles must be 16-byte aligned");
+    uint32_t thr = 0;
+    int rc = threshold_from_p(p, &thr);
+    if (rc) return rc;
+    if (c->small) return fail(QCSS_ERR_UNSUPPORTED, "codes with n <= %d and m <= %d sample through qcss_mc_run / qcss_mc_sample", kMaxN, kMaxM);
+    if (shots == 0) return QCSS_OK;
+    GapTable gap;
+    gap_table_from_p(p, &gap);
+    const uint32_t use_gap = (thr < (1u << 25) && getenv("QCSS_SAMPLER_BITS") == nullptr) ? 1u : 0u;
+    cudaError_t e = launch_sample_syndrome_tiles(c->sp2, c->sp1, (uint32_t*)d_sx, (uint32_t*)d_sz, (uint32_t*)d_ex,
+                                                 (uint32_t*)d_ez, (shots + 31) / 32, tail_mask_for(shots), seed,
+                                                 (uint64_t)(first_shot / 32), thr, use_gap, gap, stream);
+    if (e == cudaErrorInvalidValue)
+        return fail(QCSS_ERR_UNSUPPORTED, "n = %d does not fit the fused sampler's shared-memory arrays", c->n);
+    QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_sample_syndrome_tiles_dev(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                                   uint64_t* d_sx_tiles, uint64_t* d_sz_tiles, uint64_t* d_ex_tiles,
+                                   uint64_t* d_ez_tiles, void* stream) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    return launch_sample_tiles_checked(c, p, shots, seed, first_shot, d_sx_tiles, d_sz_tiles, d_ex_tiles, d_ez_tiles,
+                                       (cudaStream_t)stream);
+}
+
+QCSS_API int qcss_sample_syndrome_tiles(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t first_shot,
+                               uint64_t* sx_tiles, uint64_t* sz_tiles, uint64_t* ex_tiles, uint64_t* ez_tiles) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    int rc = ensure_streams(c);
+    if (rc) return rc;
+    const size_t tiles = (size_t)((shots + 1023) / 1024);
+    if (tiles == 0) return QCSS_OK;
+    const size_t sxb = tiles * c->m2 * 128, szb = tiles * c->m1 * 128, eb = tiles * c->n * 128;
+    if (sx_tiles) QCSS_CUDA(c->buf_a.reserve(sxb));
+    if (sz_tiles) QCSS_CUDA(c->buf_b.reserve(szb));
+    if (ex_tiles) QCSS_CUDA(c->buf_c.reserve(eb));
+    if (ez_tiles) QCSS_CUDA(c->buf_d.reserve(eb));
+    rc = launch_sample_tiles_checked(c, p, shots, seed, first_shot, sx_tiles ? (uint64_t*)c->buf_a.p : nullptr,
+                                     sz_tiles ? (uint64_t*)c->buf_b.p : nullptr, ex_tiles ? (uint64_t*)c->buf_c.p : nullptr,
+                                     ez_tiles ? (uint64_t*)c->buf_d.p : nullptr, c->stream);
+    if (rc) return rc;
+    if (sx_tiles) QCSS_CUDA(cudaMemcpyAsync(sx_tiles, c->buf_a.p, sxb, cudaMemcpyDeviceToHost, c->stream));
+    if (sz_tiles) QCSS_CUDA(cudaMemcpyAsync(sz_tiles, c->buf_b.p, szb, cudaMemcpyDeviceToHost, c->stream));
+    if (ex_tiles) QCSS_CUDA(cudaMemcpyAsync(ex_tiles, c->buf_c.p, eb, cudaMemcpyDeviceToHost, c->stream));
+    if (ez_tiles) QCSS_CUDA(cudaMemcpyAsync(ez_tiles, c->buf_d.p, eb, cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
 QCSS_API int qcss_syndrome_tiles_dev(qcss_code* c, int which, const uint64_t* d_e_tiles, int64_t shots, uint64_t* d_s_tiles,
                             void* stream) {
     if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");

@@ -231,6 +231,20 @@ void sample_gap_rest(uint32_t k0, uint32_t k1, uint32_t g_lo, uint32_t g_hi, uin
     }
 }
 
+// The gap sampler after its first Philox block `buf` (block index 0 of counter (g, j)) -- split off so that a
+// caller can compute the first blocks of several site-words back to back (independent 10-round chains) before
+// looking at any of them.
+QCSS_HD void gap_finish(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t, uint32_t cdf31,
+                        const uint32_t (&buf)[4], uint32_t& x, uint32_t& z) {
+    x = 0u;
+    z = 0u;
+    if (buf[0] >= cdf31) return;                       // no error among the 32 lanes (cdf31 = t.cdf[31])
+    uint32_t pos = 0u;
+    gap_draw(t, buf[0], buf[1], pos, x, z);            // first error: inline (3 % of the words)
+    if (pos >= 32u || buf[2] >= t.cdf[31u - pos]) return;              // usually the only one
+    sample_gap_rest(px.k0, px.k1, g_lo, g_hi, j, t, pos, buf[2], buf[3], x, z);
+}
+
 QCSS_HD void sample_site_word_gap(uint64_t seed, uint64_t g, uint32_t j, const GapTable& t, uint32_t cdf31,
                                   uint32_t& x, uint32_t& z) {
     Philox px;
@@ -239,13 +253,7 @@ QCSS_HD void sample_site_word_gap(uint64_t seed, uint64_t g, uint32_t j, const G
     const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
     uint32_t buf[4];
     px.block(g_lo, g_hi, j, 0u, buf);
-    x = 0u;
-    z = 0u;
-    if (buf[0] >= cdf31) return;                       // no error among the 32 lanes (cdf31 = t.cdf[31])
-    uint32_t pos = 0u;
-    gap_draw(t, buf[0], buf[1], pos, x, z);            // first error: inline (3 % of the words)
-    if (pos >= 32u || buf[2] >= t.cdf[31u - pos]) return;              // usually the only one
-    sample_gap_rest(px.k0, px.k1, g_lo, g_hi, j, t, pos, buf[2], buf[3], x, z);
+    gap_finish(px, g_lo, g_hi, j, t, cdf31, buf, x, z);
 }
 
 QCSS_HD uint32_t popc32(uint32_t v) {

@@ -45,6 +45,12 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes,
 cudaError_t launch_syndrome_tiles(const SparseRows& h, const uint32_t* e_tiles, uint32_t* s_tiles, int64_t words,
                                   uint32_t tail_mask, cudaStream_t stream);
 
+// fused Philox sampler + sparse syndromes, tile-major outputs (sample_tiles.cu); hx acts on X errors, hz on Z errors
+cudaError_t launch_sample_syndrome_tiles(const SparseRows& hx, const SparseRows& hz, uint32_t* sx, uint32_t* sz,
+                                         uint32_t* ex, uint32_t* ez, int64_t words, uint32_t tail_mask, uint64_t seed,
+                                         uint64_t first_word, uint32_t thr, uint32_t use_gap, const GapTable& gap,
+                                         cudaStream_t stream);
+
 // ---- dense syndrome on tensor cores (dense_kernels.cu) ---------------------------------------
 size_t dense_h_bytes(int m, int n);
 void dense_h_layout(int m, int n, const uint8_t* H, uint8_t* out);      // host-side operand layout

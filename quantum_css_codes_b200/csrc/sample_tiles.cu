@@ -1,0 +1,179 @@
+// K3 for codes of any size: depolarising Philox sampler fused into the sparse syndrome kernel, so that the
+// 2 n error bits per shot of a large code (hypergraph product n = 1600: 400 B/shot) never exist in HBM --
+// only the 2 m syndrome bits leave the SM (tile-major, the layout qcss_syndrome_tiles uses).
+//
+// One CTA works on a sub-tile of 256 shots (8 words) at a time:
+//   sample   thread t draws site-words (qubit j, word w), j * 8 + w = t, t + 1024, ...: one call of the K3
+//            sampler (core.cuh: gap sampler below p = 1/128, bit-serial above; Philox counter = (global word,
+//            site = j, block), key = seed -- the stream of qcss_mc_sample with n > 32 sites) gives the X and
+//            the Z word, stored to two n x 32 B arrays in shared memory;
+//   XOR      thread (row slot, 16-byte chunk q) folds the rows of parity_check_c2 over the X array and of
+//            parity_check_c1 over the Z array (CSR supports in shared memory, one LDS.128 per entry) and
+//            writes 16 bytes of the syndrome tile per row; optionally the sampled errors are written too.
+// INT-bound by construction: one Philox block per 32 shots per qubit (~80 instructions) against 7 loads +
+// XORs per 128 shots per check.  Reading a resident batch instead costs (n + m) / 8 bytes per shot per type.
+#include <cuda_runtime.h>
+
+#include "launch.h"
+
+namespace qcss {
+
+namespace {
+
+constexpr int kSampleThreads = 1024;
+constexpr int kSubWords = 8;                       // words per sub-tile: 256 shots, 32-byte rows
+constexpr int kTileWords = 32;                     // tile-major layout: 1024 shots per tile
+constexpr int kSlots = kSampleThreads / 2;         // 512 row slots x 2 chunks of 16 bytes
+
+struct SampleArgs {
+    SparseRows hx;            // parity_check_c2: acts on X errors (which = 2)
+    SparseRows hz;            // parity_check_c1: acts on Z errors (which = 1)
+    uint32_t* sx;             // [tiles][hx.m][32] or null
+    uint32_t* sz;             // [tiles][hz.m][32] or null
+    uint32_t* ex;             // [tiles][n][32] or null
+    uint32_t* ez;
+    int64_t words;            // ceil(shots / 32)
+    uint32_t tail_mask;
+    uint64_t seed, first_word;
+    uint32_t thr, use_gap;
+    GapTable gap;
+};
+
+__device__ __forceinline__ void stage_csr(const SparseRows& h, uint16_t* ptr, uint16_t* cols) {
+    for (int i = threadIdx.x; i <= h.m; i += kSampleThreads) ptr[i] = (uint16_t)__ldg(h.row_ptr + i);
+    for (int k = threadIdx.x; k < h.nnz; k += kSampleThreads) cols[k] = __ldg(h.cols + k);
+}
+
+__device__ __forceinline__ void xor_rows(const SparseRows& h, const uint16_t* ptr, const uint16_t* cols,
+                                         const uint32_t* planes, uint32_t* out, int64_t tile, int sub, int64_t words,
+                                         uint32_t tail_mask) {
+    const int q = threadIdx.x & 1, slot = threadIdx.x >> 1;
+    const int64_t w0 = tile * kTileWords + sub * kSubWords + q * 4;          // first of this thread's 4 words
+    for (int i = slot; i < h.m; i += kSlots) {
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        const int o0 = ptr[i], o1 = ptr[i + 1];
+        for (int k = o0; k < o1; ++k) {
+            const uint4 v = *reinterpret_cast<const uint4*>(planes + (size_t)cols[k] * kSubWords + q * 4);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        uint32_t o[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (w0 + 4 > words - 1) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int64_t w = w0 + v;
+                if (w >= words) o[v] = 0u;
+                else if (w == words - 1) o[v] &= tail_mask;
+            }
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)tile * h.m + i) * kTileWords + sub * kSubWords + q * 4) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kSampleThreads, 1)
+k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = a.hx.n;
+    uint32_t* const px = reinterpret_cast<uint32_t*>(smem);                  // [n][8]
+    uint32_t* const pz = px + (size_t)n * kSubWords;
+    uint16_t* const ptr_x = reinterpret_cast<uint16_t*>(pz + (size_t)n * kSubWords);
+    uint16_t* const cols_x = ptr_x + ((a.hx.m + 2) & ~1);
+    uint16_t* const ptr_z = cols_x + ((a.hx.nnz + 1) & ~1);
+    uint16_t* const cols_z = ptr_z + ((a.hz.m + 2) & ~1);
+    __shared__ GapTable s_gap;
+    if (threadIdx.x < 32) s_gap.cdf[threadIdx.x] = a.gap.cdf[threadIdx.x];
+    if (threadIdx.x == 32) s_gap.inv = a.gap.inv;
+    if (a.sx != nullptr) stage_csr(a.hx, ptr_x, cols_x);
+    if (a.sz != nullptr) stage_csr(a.hz, ptr_z, cols_z);
+    __syncthreads();
+    const uint32_t cdf31 = s_gap.cdf[31];
+    const int64_t tiles = (a.words + kTileWords - 1) / kTileWords;
+    const int64_t subs = tiles * (kTileWords / kSubWords);
+    for (int64_t st = blockIdx.x; st < subs; st += gridDim.x) {
+        const int64_t tile = st / (kTileWords / kSubWords);
+        const int sub = (int)(st % (kTileWords / kSubWords));
+        const int64_t wbase = tile * kTileWords + sub * kSubWords;
+        auto put = [&](int idx, uint32_t x, uint32_t z, int64_t gw) {
+            if (gw == a.words - 1) { x &= a.tail_mask; z &= a.tail_mask; }
+            px[idx] = x;
+            pz[idx] = z;
+            const int j = idx / kSubWords, w = idx % kSubWords;
+            if (a.ex != nullptr) a.ex[((size_t)tile * n + j) * kTileWords + sub * kSubWords + w] = x;
+            if (a.ez != nullptr) a.ez[((size_t)tile * n + j) * kTileWords + sub * kSubWords + w] = z;
+        };
+        const int w = threadIdx.x % kSubWords;              // 1024 % 8 == 0: a thread keeps its word column
+        const int64_t gw = wbase + w;
+        const int total = n * kSubWords;
+        if (gw >= a.words) {
+            for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) put(idx, 0u, 0u, gw);
+        } else if (a.use_gap) {
+            // two site-words per iteration: both first Philox blocks are computed before either is examined,
+            // so the two 10-round chains overlap (one chain per warp left the INT pipe waiting on itself)
+            Philox ph;
+            ph.k0 = (uint32_t)a.seed;
+            ph.k1 = (uint32_t)(a.seed >> 32);
+            const uint64_t g = a.first_word + (uint64_t)gw;
+            const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+            int idx = threadIdx.x;
+            for (; idx + kSampleThreads < total; idx += 2 * kSampleThreads) {
+                const uint32_t j0 = (uint32_t)(idx / kSubWords), j1 = (uint32_t)((idx + kSampleThreads) / kSubWords);
+                uint32_t b0[4], b1[4], x0, z0, x1, z1;
+                ph.block(g_lo, g_hi, j0, 0u, b0);
+                ph.block(g_lo, g_hi, j1, 0u, b1);
+                gap_finish(ph, g_lo, g_hi, j0, s_gap, cdf31, b0, x0, z0);
+                gap_finish(ph, g_lo, g_hi, j1, s_gap, cdf31, b1, x1, z1);
+                put(idx, x0, z0, gw);
+                put(idx + kSampleThreads, x1, z1, gw);
+            }
+            if (idx < total) {
+                uint32_t x, z;
+                sample_site_word_gap(a.seed, g, (uint32_t)(idx / kSubWords), s_gap, cdf31, x, z);
+                put(idx, x, z, gw);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) {
+                uint32_t x, z;
+                sample_site_word(a.seed, a.first_word + (uint64_t)gw, (uint32_t)(idx / kSubWords), a.thr, x, z);
+                put(idx, x, z, gw);
+            }
+        }
+        __syncthreads();
+        if (a.sx != nullptr) xor_rows(a.hx, ptr_x, cols_x, px, a.sx, tile, sub, a.words, a.tail_mask);
+        if (a.sz != nullptr) xor_rows(a.hz, ptr_z, cols_z, pz, a.sz, tile, sub, a.words, a.tail_mask);
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// cudaErrorInvalidValue when the two error arrays and the supports do not fit shared memory (n > ~3000).
+cudaError_t launch_sample_syndrome_tiles(const SparseRows& hx, const SparseRows& hz, uint32_t* sx, uint32_t* sz,
+                                         uint32_t* ex, uint32_t* ez, int64_t words, uint32_t tail_mask, uint64_t seed,
+                                         uint64_t first_word, uint32_t thr, uint32_t use_gap, const GapTable& gap,
+                                         cudaStream_t stream) {
+    if (hx.n != hz.n || hx.nnz > 65535 || hz.nnz > 65535 || hx.m > 65534 || hz.m > 65534) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * hx.n * kSubWords * 4 +
+                        2 * (size_t)(((hx.m + 2) & ~1) + ((hx.nnz + 1) & ~1) + ((hz.m + 2) & ~1) + ((hz.nnz + 1) & ~1));
+    if (smem > 226 * 1024) return cudaErrorInvalidValue;
+    cudaError_t err = cudaFuncSetAttribute(k_sample_syndrome_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 0;
+    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+    int per_sm = 1;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_syndrome_tiles, kSampleThreads, smem)) !=
+        cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t subs = ((words + kTileWords - 1) / kTileWords) * (kTileWords / kSubWords);
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > subs) grid = subs;
+    if (grid < 1) grid = 1;
+    SampleArgs a;
+    a.hx = hx; a.hz = hz; a.sx = sx; a.sz = sz; a.ex = ex; a.ez = ez;
+    a.words = words; a.tail_mask = tail_mask; a.seed = seed; a.first_word = first_word;
+    a.thr = thr; a.use_gap = use_gap; a.gap = gap;
+    k_sample_syndrome_tiles<<<(unsigned)grid, kSampleThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace qcss

@@ -442,6 +442,15 @@ class SyndromeCode:
         s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
         return _planes.unpack_planes(s_planes, shots)[:, :m]
 
+    def sample_syndromes(self, p, shots, seed=0, first_shot=0, return_errors=False):
+        """Depolarising(p) errors drawn on the device and turned into syndromes in the same kernel
+        (``qcss_sample_syndrome_tiles``: the sampled errors never leave shared memory).  Returns
+        ``(s_x, s_z)`` -- (shots, m2) syndromes of the X errors under parity_check_c2 and (shots, m1) of the
+        Z errors under parity_check_c1 -- and with ``return_errors`` also ``(e_x, e_z)`` as (shots, n)."""
+        out = self.device.sample_syndrome_tiles(p, shots, seed, first_shot, errors=return_errors)
+        res = tuple(_planes.unpack_tiles(t, shots) for t in out)
+        return res
+
     def syndromes_tiled(self, errors, which):
         """The same result through the tile-major layout (``planes.pack_tiles`` -> ``qcss_syndrome_tiles``):
         the layout the sparse any-size kernel streams fastest (one bulk copy per part-tile)."""

@@ -302,6 +302,47 @@ def test_hgp1600_tile_major_layout(golden):
         small.device.syndrome_tiles(planes.pack_tiles(np.zeros((5, 7), dtype=np.uint8)), 5, 1)
 
 
+@pytest.mark.parametrize("p", [1e-3, 0.05])
+def test_hgp1600_fused_sampler(p):
+    """K3 for large codes (qcss_sample_syndrome_tiles): the errors drawn inside the syndrome kernel are the
+    oracle sampler's (same Philox streams, n = 1600 sites), the syndromes are H.e of exactly those errors, and a
+    sharded run reproduces the whole run."""
+    hx, hz = codes.hgp1600()
+    code = SyndromeCode(hx, hz)
+    shots, seed, first = 3000, 0xC0FFEE, 2048
+    s_x, s_z, e_x, e_z = code.sample_syndromes(p, shots, seed=seed, first_shot=first, return_errors=True)
+    want_x, want_z = ophilox.sample_bits(seed, first, shots, 1600, p)
+    assert np.array_equal(e_x, want_x) and np.array_equal(e_z, want_z)
+    assert np.array_equal(s_x, omc.syndromes_batch(hz, want_x))          # which = 2: parity_check_c2 on X errors
+    assert np.array_equal(s_z, omc.syndromes_batch(hx, want_z))          # which = 1: parity_check_c1 on Z errors
+    only_x, only_z = code.sample_syndromes(p, shots, seed=seed, first_shot=first)
+    assert np.array_equal(only_x, s_x) and np.array_equal(only_z, s_z)
+    part_x, part_z = code.sample_syndromes(p, 1024 + 7, seed=seed, first_shot=first + 1024)
+    assert np.array_equal(part_x, s_x[1024:2048 + 7]) and np.array_equal(part_z, s_z[1024:2048 + 7])
+    with pytest.raises(ValueError, match="multiple of 1024"):
+        code.sample_syndromes(p, 10, first_shot=512)
+    small, _ = pair("steane")
+    with pytest.raises(_native.NativeLibraryError, match="sample through qcss_mc_run"):
+        small.device.sample_syndrome_tiles(p, 10)
+
+
+def test_fused_sampler_midsize_code():
+    rng = np.random.default_rng(301)
+    mats = []
+    for m in (130, 77):
+        h = np.zeros((m, 300), dtype=np.int64)
+        for i in range(m):
+            h[i, rng.choice(300, size=9, replace=False)] = 1
+        mats.append(h)
+    code = SyndromeCode(mats[0], mats[1])
+    for p, shots in ((0.004, 5000), (0.3, 1500)):
+        s_x, s_z, e_x, e_z = code.sample_syndromes(p, shots, seed=5, return_errors=True)
+        want_x, want_z = ophilox.sample_bits(5, 0, shots, 300, p)
+        assert np.array_equal(e_x, want_x) and np.array_equal(e_z, want_z)
+        assert np.array_equal(s_x, omc.syndromes_batch(mats[1], want_x))
+        assert np.array_equal(s_z, omc.syndromes_batch(mats[0], want_z))
+
+
 @pytest.mark.parametrize("n,m,row_w,shots", [(40, 20, 5, 3000), (300, 130, 9, 1025), (700, 1024, 3, 5000),
                                              (3000, 900, 6, 2500)])
 def test_tile_major_random_sparse(n, m, row_w, shots):

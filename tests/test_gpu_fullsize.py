@@ -153,6 +153,49 @@ def test_c4_hgp_1e8_shots_tile_major_equals_plane_major_and_is_linear():
     torch.cuda.empty_cache()
 
 
+def test_c4_hgp_1e8_shots_fused_sampler_equals_unfused():
+    """Config 4 with the sampler fused in: 1e8 shots at p = 1e-3.  The syndromes written by the fused kernel equal
+    the syndromes the tile-major kernel computes from the errors the same call wrote out (all 2 x 768 x 1e8 bits),
+    and the sampled error rate is p within binomial noise."""
+    import torch
+    hx, hz = codes.hgp1600()
+    dev = SyndromeCode(hx, hz).device
+    shots, p = 100_000_000, 1e-3
+    tiles = (shots + 1023) // 1024
+    ex = torch.empty((tiles, 1600, 16), dtype=torch.int64, device="cuda")
+    ez = torch.empty_like(ex)
+    sx = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
+    sz = torch.empty_like(sx)
+    dev.sample_syndrome_tiles_dev(p, shots, 0x5EED, 0, sx.data_ptr(), sz.data_ptr(), ex.data_ptr(), ez.data_ptr(), 0)
+    want = torch.empty_like(sx)
+    dev.syndrome_tiles_dev(2, ex.data_ptr(), shots, want.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(sx, want))
+    dev.syndrome_tiles_dev(1, ez.data_ptr(), shots, want.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(sz, want))
+    assert bool(sx.any()) and bool(sz.any())
+    # a second call without error outputs gives the same syndromes
+    dev.sample_syndrome_tiles_dev(p, shots, 0x5EED, 0, want.data_ptr(), 0, 0, 0, 0)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(sx, want))
+    del want, sx, sz
+    any_err = ex | ez
+    del ex, ez
+    count = 0
+    for chunk in torch.chunk(any_err.view(-1), 64):                   # popcount without a 20 GB temporary
+        v = chunk.clone()
+        v = (v & 0x5555555555555555) + ((v >> 1) & 0x5555555555555555)
+        v = (v & 0x3333333333333333) + ((v >> 2) & 0x3333333333333333)
+        v = (v + (v >> 4)) & 0x0F0F0F0F0F0F0F0F
+        count += int(((v * 0x0101010101010101) >> 56 & 0xFF).sum().item())
+    total = shots * 1600
+    sigma = (total * p * (1 - p)) ** 0.5
+    assert abs(count - total * p) < 6 * sigma, (count, total * p)
+    del any_err
+    torch.cuda.empty_cache()
+
+
 def test_c5_4096_matrices_rref_idempotent_rank_and_nullspace():
     """Config 5: all 4096 random 1024 x 2048 matrices on the device.  RREF(RREF(A)) == RREF(A); rank ==
     number of non-zero rows; the pivot block of the RREF is the identity; A.N^T == 0 with N from

@@ -47,3 +47,10 @@ for which in (1, 2):
     ms = timed(lambda: dev.syndrome_dev(which, ep.data_ptr(), stride, shots, sp.data_ptr(), stride, stream))
     print(json.dumps(dict(probe="hgp_planes", which=which, shots=shots, ms=ms, shots_per_s=shots / (ms * 1e-3),
                           gbs=bytes_per_shot * shots / (ms * 1e-3) / 1e9)), flush=True)
+
+# fused sampler + syndromes of both Pauli types (no HBM input)
+sx = torch.empty((tiles, m, 16), dtype=torch.int64, device="cuda")
+for p in (1e-3, 0.05):
+    ms = timed(lambda: dev.sample_syndrome_tiles_dev(p, shots, 7, 0, sx.data_ptr(), s.data_ptr(), 0, 0, stream), reps=3)
+    print(json.dumps(dict(probe="hgp_fused_sampler", p=p, shots=shots, ms=ms, shots_per_s=shots / (ms * 1e-3),
+                          site_words_per_s=shots / 32 * n / (ms * 1e-3))), flush=True)

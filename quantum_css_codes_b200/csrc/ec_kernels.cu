@@ -58,8 +58,10 @@ k_ec_generic(const __grid_constant__ EcGenericArgs a) {
     run_ec(px, pz, a.ec, tx, tz);
 }
 
+// 3 CTAs/SM when both sides decode by mux tree (Steane: 4.45 -> 4.12 ms per 1e9 shot-rounds); with a table side
+// the 80-register cap spills (QRM-15: 22.3 -> 33.3 ms), so those stay at 2.
 template <class DX, class DZ>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (DX::kSliced && DZ::kSliced) ? 3 : 2)
 k_ec_named(const __grid_constant__ EcNamedArgs a) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;

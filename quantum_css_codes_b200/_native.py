@@ -251,6 +251,9 @@ class DeviceCode:
         if e_tiles.shape != (tiles, self.n, 16):
             raise ValueError("expected (ceil(shots / 1024), n, 16) uint64 tiles")
         out = np.zeros((tiles, self.m(which), 16), dtype=np.uint64)
+        if tiles == 0:
+            load()                                   # an empty batch still needs the library (no silent CPU path)
+            return out
         check(self._lib.qcss_syndrome_tiles(self.handle, which, _ptr(e_tiles), shots, _ptr(out)))
         return out
 
@@ -266,6 +269,10 @@ class DeviceCode:
         sz = np.zeros((tiles, self.m1, 16), dtype=np.uint64)
         ex = np.zeros((tiles, self.n, 16), dtype=np.uint64) if errors else None
         ez = np.zeros((tiles, self.n, 16), dtype=np.uint64) if errors else None
+        if tiles == 0:
+            if first_shot % 1024:
+                raise ValueError("first_shot must be a multiple of 1024 (one tile)")
+            return (sx, sz, ex, ez) if errors else (sx, sz)
         check(self._lib.qcss_sample_syndrome_tiles(self.handle, float(p), int(shots), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                                    int(first_shot), _ptr(sx), _ptr(sz), _ptr(ex), _ptr(ez)))
         return (sx, sz, ex, ez) if errors else (sx, sz)

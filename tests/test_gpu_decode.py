@@ -326,6 +326,15 @@ def test_hgp1600_fused_sampler(p):
         small.device.sample_syndrome_tiles(p, 10)
 
 
+def test_tile_major_empty_batches():
+    hx, hz = codes.hgp1600()
+    code = SyndromeCode(hx, hz)
+    assert code.syndromes_tiled(np.zeros((0, 1600), dtype=np.uint8), 1).shape == (0, 768)
+    s_x, s_z = code.sample_syndromes(1e-3, 0)
+    assert s_x.shape == (0, 768) and s_z.shape == (0, 768)
+    assert planes.pack_tiles(np.zeros((0, 5), dtype=np.uint8)).shape == (0, 5, 16)
+
+
 def test_fused_sampler_midsize_code():
     rng = np.random.default_rng(301)
     mats = []

@@ -151,3 +151,22 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
     for f in ("bin_matrix.py", "css_code.py", "errors.py"):
         assert "oracle" not in open(os.path.join(REPO, f)).read()
+
+
+def test_tile_major_pack_helpers_round_trip():
+    """planes.pack_tiles / unpack_tiles / planes_to_tiles (host-side layout helpers, no GPU): round trip, zero
+    padding of the last tile, agreement with the plane-major packing."""
+    from quantum_css_codes_b200 import planes
+    rng = np.random.default_rng(12)
+    for shots, n in ((0, 5), (1, 3), (1023, 9), (1024, 9), (2500, 9), (4096, 40)):
+        v = (rng.random((shots, n)) < 0.3).astype(np.uint8)
+        tiles = planes.pack_tiles(v)
+        assert tiles.shape == ((shots + 1023) // 1024, n, 16) and tiles.dtype == np.uint64
+        assert np.array_equal(planes.unpack_tiles(tiles, shots), v)
+        assert np.array_equal(planes.planes_to_tiles(planes.pack_planes(v), shots), tiles)
+        if shots % 1024:
+            bits = np.unpackbits(tiles[-1].view(np.uint8), axis=1, bitorder="little")
+            assert not bits[:, shots % 1024:].any()
+    one = np.zeros((1030, 2), dtype=np.uint8)
+    one[1029, 1] = 1                                           # shot 1029 = tile 1, bit 5 of word 0 of plane 1
+    assert planes.pack_tiles(one)[1, 1, 0] == np.uint64(1 << 5)

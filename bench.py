@@ -270,7 +270,7 @@ def run_b200(args):
             others = measure_other_configs(torch, peak)
         cpu = None
         if not args.no_cpu and world == 1:
-            rate, total = cpu_baseline(args.code, 1, steps=4)
+            rate, total = cpu_baseline(args.code, 1, steps=16)      # ~11 s of single-core decode
             cpu = {"value": rate, "unit": "shots/s", "cores": 1, "kind": "port",
                    "sample": f"{total} shots (numpy batched oracle: syndrome+key+table gather+logical check, X and Z)"}
         line = {

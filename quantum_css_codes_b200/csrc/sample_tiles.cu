@@ -3,10 +3,11 @@
 // only the 2 m syndrome bits leave the SM (tile-major, the layout qcss_syndrome_tiles uses).
 //
 // One CTA works on a sub-tile of 256 shots (8 words) at a time:
-//   sample   thread t draws site-words (qubit j, word w), j * 8 + w = t, t + 1024, ...: one call of the K3
-//            sampler (core.cuh: gap sampler below p = 1/128, bit-serial above; Philox counter = (global word,
-//            site = j, block), key = seed -- the stream of qcss_mc_sample with n > 32 sites) gives the X and
-//            the Z word, stored to two n x 32 B arrays in shared memory;
+//   sample   thread t draws site-words (qubit j, word w), j * 8 + w = t, t + 1024, ... with the K3 sampler
+//            (core.cuh: gap sampler below p = 1/128, bit-serial above; Philox counter = (global word, site = j,
+//            block), key = seed -- the stream of qcss_mc_sample with n > 32 sites) into two n x 32 B arrays (X
+//            and Z words) in shared memory; on the gap path in two phases -- first blocks for everyone, a queue
+//            for the few site-words that hold an error, one queued item per lane (see the kernel);
 //   XOR      thread (row slot, 16-byte chunk q) folds the rows of parity_check_c2 over the X array and of
 //            parity_check_c1 over the Z array (CSR supports in shared memory, one LDS.128 per entry) and
 //            writes 16 bytes of the syndrome tile per row; optionally the sampled errors are written too.
@@ -80,7 +81,10 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
     uint16_t* const cols_x = ptr_x + ((a.hx.m + 2) & ~1);
     uint16_t* const ptr_z = cols_x + ((a.hx.nnz + 1) & ~1);
     uint16_t* const cols_z = ptr_z + ((a.hz.m + 2) & ~1);
+    uint16_t* const queue = cols_z + ((a.hz.nnz + 1) & ~1);                  // [n * 8] site-words with an error
     __shared__ GapTable s_gap;
+    __shared__ int q_count;
+    if (threadIdx.x == 0) q_count = 0;
     if (threadIdx.x < 32) s_gap.cdf[threadIdx.x] = a.gap.cdf[threadIdx.x];
     if (threadIdx.x == 32) s_gap.inv = a.gap.inv;
     if (a.sx != nullptr) stage_csr(a.hx, ptr_x, cols_x);
@@ -104,31 +108,51 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
         const int w = threadIdx.x % kSubWords;              // 1024 % 8 == 0: a thread keeps its word column
         const int64_t gw = wbase + w;
         const int total = n * kSubWords;
+        if (a.use_gap) {
+            // gap path: everything starts as "no error" (16-byte stores; px and pz are contiguous)
+            uint4* const z4 = reinterpret_cast<uint4*>(px);
+            for (int i = threadIdx.x; i < 2 * total / 4; i += kSampleThreads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (a.ex != nullptr || a.ez != nullptr) {
+                for (int i = threadIdx.x; i < total / 4; i += kSampleThreads) {
+                    const int j = i / (kSubWords / 4), c = i % (kSubWords / 4);
+                    const size_t off = ((size_t)tile * n + j) * kTileWords + sub * kSubWords + c * 4;
+                    if (a.ex != nullptr) *reinterpret_cast<uint4*>(a.ex + off) = make_uint4(0u, 0u, 0u, 0u);
+                    if (a.ez != nullptr) *reinterpret_cast<uint4*>(a.ez + off) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            // (phase 2, which overwrites single words of these, comes after the barrier that ends phase 1)
+        }
         if (gw >= a.words) {
-            for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) put(idx, 0u, 0u, gw);
+            if (!a.use_gap)
+                for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) put(idx, 0u, 0u, gw);
         } else if (a.use_gap) {
-            // two site-words per iteration: both first Philox blocks are computed before either is examined,
-            // so the two 10-round chains overlap (one chain per warp left the INT pipe waiting on itself)
+            // Phase 1: first Philox block of every site-word (two per iteration: independent 10-round chains); 97 %
+            // of them (p = 1e-3) hold no error and are done after one compare.  The others are QUEUED instead of
+            // being finished in place: with ~1 erring lane per warp-instruction, finishing in place makes every
+            // warp pay the gap logic for one useful lane (65 % of the warps at p = 1e-3; ncu: the logic was
+            // most of the 161 instructions per site-word).  Phase 2 hands the queue out one item per lane.
             Philox ph;
             ph.k0 = (uint32_t)a.seed;
             ph.k1 = (uint32_t)(a.seed >> 32);
             const uint64_t g = a.first_word + (uint64_t)gw;
             const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+            // (the arrays were zeroed with 16-byte stores before this phase; a clean site-word costs nothing more.
+            //  One shared atomic per erring lane: a warp-aggregated push cost 17 % of all instructions.)
+            auto first_look = [&](int idx, const uint32_t (&b)[4]) {
+                if (b[0] < cdf31) queue[atomicAdd(&q_count, 1)] = (uint16_t)idx;
+            };
             int idx = threadIdx.x;
             for (; idx + kSampleThreads < total; idx += 2 * kSampleThreads) {
-                const uint32_t j0 = (uint32_t)(idx / kSubWords), j1 = (uint32_t)((idx + kSampleThreads) / kSubWords);
-                uint32_t b0[4], b1[4], x0, z0, x1, z1;
-                ph.block(g_lo, g_hi, j0, 0u, b0);
-                ph.block(g_lo, g_hi, j1, 0u, b1);
-                gap_finish(ph, g_lo, g_hi, j0, s_gap, cdf31, b0, x0, z0);
-                gap_finish(ph, g_lo, g_hi, j1, s_gap, cdf31, b1, x1, z1);
-                put(idx, x0, z0, gw);
-                put(idx + kSampleThreads, x1, z1, gw);
+                uint32_t b0[4], b1[4];
+                ph.block(g_lo, g_hi, (uint32_t)(idx / kSubWords), 0u, b0);
+                ph.block(g_lo, g_hi, (uint32_t)((idx + kSampleThreads) / kSubWords), 0u, b1);
+                first_look(idx, b0);
+                first_look(idx + kSampleThreads, b1);
             }
             if (idx < total) {
-                uint32_t x, z;
-                sample_site_word_gap(a.seed, g, (uint32_t)(idx / kSubWords), s_gap, cdf31, x, z);
-                put(idx, x, z, gw);
+                uint32_t b0[4];
+                ph.block(g_lo, g_hi, (uint32_t)(idx / kSubWords), 0u, b0);
+                first_look(idx, b0);
             }
         } else {
             for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) {
@@ -138,6 +162,18 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
             }
         }
         __syncthreads();
+        if (a.use_gap) {
+            const int count = q_count;
+            for (int k = threadIdx.x; k < count; k += kSampleThreads) {
+                const int idx = queue[k];
+                const int64_t qw = wbase + idx % kSubWords;
+                uint32_t x, z;
+                sample_site_word_gap(a.seed, a.first_word + (uint64_t)qw, (uint32_t)(idx / kSubWords), s_gap, cdf31, x, z);
+                put(idx, x, z, qw);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) q_count = 0;
+        }
         if (a.sx != nullptr) xor_rows(a.hx, ptr_x, cols_x, px, a.sx, tile, sub, a.words, a.tail_mask);
         if (a.sz != nullptr) xor_rows(a.hz, ptr_z, cols_z, pz, a.sz, tile, sub, a.words, a.tail_mask);
         __syncthreads();
@@ -151,9 +187,10 @@ cudaError_t launch_sample_syndrome_tiles(const SparseRows& hx, const SparseRows&
                                          uint32_t* ex, uint32_t* ez, int64_t words, uint32_t tail_mask, uint64_t seed,
                                          uint64_t first_word, uint32_t thr, uint32_t use_gap, const GapTable& gap,
                                          cudaStream_t stream) {
-    if (hx.n != hz.n || hx.nnz > 65535 || hz.nnz > 65535 || hx.m > 65534 || hz.m > 65534) return cudaErrorInvalidValue;
+    if (hx.n != hz.n || hx.n * kSubWords > 65535 || hx.nnz > 65535 || hz.nnz > 65535 || hx.m > 65534 || hz.m > 65534) return cudaErrorInvalidValue;
     const size_t smem = (size_t)2 * hx.n * kSubWords * 4 +
-                        2 * (size_t)(((hx.m + 2) & ~1) + ((hx.nnz + 1) & ~1) + ((hz.m + 2) & ~1) + ((hz.nnz + 1) & ~1));
+                        2 * (size_t)(((hx.m + 2) & ~1) + ((hx.nnz + 1) & ~1) + ((hz.m + 2) & ~1) + ((hz.nnz + 1) & ~1)) +
+                        2 * (size_t)hx.n * kSubWords;                              // + the queue of erring site-words
     if (smem > 226 * 1024) return cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(k_sample_syndrome_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "decode.cuh"
 #include "launch.h"
 
@@ -132,6 +134,131 @@ k_small_named(const __grid_constant__ NamedArgs a) {
     StaticPolicy<DZ> pz;
     const SideTables tx{a.fm_x, a.co_x, a.e32_x}, tz{a.fm_z, a.co_z, a.e32_z};
     run_small<StaticPolicy<DX>, StaticPolicy<DZ>, VEC, SAMPLE, FAST>(px, pz, a.io, tx, tz);
+}
+
+// ---- fused gap sampler, CTA-wide two-phase form (Monte-Carlo tallies of the static kernels, p < 1/128) ----------
+// k_small_named finishes every draw in place: thread = one 32-shot word, loop over the n qubits, and whenever ANY
+// lane of the warp holds an error at that qubit (65 % of the warp-instructions at p = 1e-3, for one useful lane on
+// average) the whole warp walks the gap logic -- ncu: 92 instructions per site-word of which the Philox rounds are
+// 35 (profiles/r01_mc_fused_steane_gap_ncu_summary.txt).  Here a CTA iteration has three phases:
+//   1  every thread computes the first Philox block of each of its n site-words and pushes the few that hold an
+//      error (3 %) to a shared-memory queue as (thread, qubit); nothing else is kept;
+//   2  the queue is handed out one item per lane: redo the block, finish the draw (same streams => same bits), and
+//      XOR the error word into the owning thread's syndrome / logical accumulators in shared memory
+//      (acc[row][thread]; rows of H and L are compile-time masks, the qubit index is the only runtime operand);
+//   3  every thread reads its accumulators back, clears them, decodes and tallies as before.
+// Bit-identical to the in-place kernel (tests compare both with the oracle); QCSS_GAPQ=0 selects the in-place one.
+// Words per thread per CTA iteration: as many as keep the accumulators within ~48 KB (the three block barriers of
+// an iteration are amortised over W * n site-words per thread: Steane 4, QRM-15 2, Golay-23 1).
+template <class DX, class DZ>
+struct GapqShape {
+    static constexpr int kRows = DX::MB + DZ::MB + 2;
+    static constexpr int kW = (kRows * 4 * kThreads * 4 <= 36 * 1024) ? 4 : ((kRows * 2 * kThreads * 4 <= 48 * 1024) ? 2 : 1);
+    static constexpr size_t kSmem = (size_t)kRows * kW * kThreads * 4 + (size_t)kThreads * kW * DX::N * 2;
+};
+
+template <class DX, class DZ>
+__global__ void __launch_bounds__(kThreads, 3)
+k_small_named_gapq(const __grid_constant__ NamedArgs a) {
+    using PX = StaticPolicy<DX>;
+    using PZ = StaticPolicy<DZ>;
+    constexpr int MBX = PX::MB, MBZ = PZ::MB, ROWS = GapqShape<DX, DZ>::kRows, W = GapqShape<DX, DZ>::kW, N = DX::N;
+    static_assert(DX::N == DZ::N && N <= 32 && kThreads <= 256 && W <= 4, "queue items are (thread:8, word:2, qubit:5)");
+    PX px;
+    PZ pz;
+    const DecodeIO& io = a.io;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* cursor = smem;
+    const SideLut lut_x = stage_side<PX, true>(px, SideTables{a.fm_x, a.co_x, a.e32_x}, cursor);
+    const SideLut lut_z = stage_side<PZ, true>(pz, SideTables{a.fm_z, a.co_z, a.e32_z}, cursor);
+    uint32_t* const acc = reinterpret_cast<uint32_t*>(cursor);                      // [ROWS][W][kThreads]
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * W * kThreads);  // [kThreads * W * N]
+    __shared__ GapTable s_gap;
+    __shared__ int q_count[2];
+    const int tid = threadIdx.x;
+    if (tid < 32) s_gap.cdf[tid] = io.gap.cdf[tid];
+    if (tid == 32) s_gap.inv = io.gap.inv;
+    if (tid < 2) q_count[tid] = 0;
+    for (int i = tid; i < ROWS * W * kThreads; i += kThreads) acc[i] = 0u;
+    __syncthreads();
+    const uint32_t cdf31 = s_gap.cdf[31];
+    Philox ph;
+    ph.k0 = (uint32_t)io.seed;
+    ph.k1 = (uint32_t)(io.seed >> 32);
+
+    Counters c = {0u, 0u, 0u, 0u, 0u};
+    const int64_t units = io.words / W;                      // FAST: whole units only; thread-unit u = words W u .. W u + W - 1
+    const int64_t step = (int64_t)gridDim.x * kThreads;
+    const int64_t cta0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t iters = cta0 < units ? (units - cta0 + step - 1) / step : 0;      // uniform over the CTA
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t ubase = cta0 + it * step;
+        const int64_t u = ubase + tid;
+        const bool active = u < units;
+        int* const qc = &q_count[it & 1];
+        // ---- 1: first blocks ----
+        if (active) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const uint64_t g = io.first_word + (uint64_t)(u * W + w);
+                const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    uint32_t b[4];
+                    ph.block(g_lo, g_hi, (uint32_t)j, 0u, b);
+                    if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 2: finish the queued draws, one per lane ----
+        const int count = *qc;
+        if (tid == 0) q_count[(it + 1) & 1] = 0;             // the other counter: untouched until the next phase 1
+        for (int k = tid; k < count; k += kThreads) {
+            const int item = queue[k], owner = item >> 7, w = (item >> 5) & 3, j = item & 31;
+            uint32_t x, z;
+            sample_site_word_gap(io.seed, io.first_word + (uint64_t)((ubase + owner) * W + w), (uint32_t)j, s_gap, cdf31, x, z);
+            uint32_t* const mine = acc + w * kThreads + owner;                       // + row * W * kThreads
+            if (x != 0u) {
+#pragma unroll
+                for (int t = 0; t < MBX; ++t)
+                    if ((DX::row(t) >> j) & 1u) atomicXor(mine + t * W * kThreads, x);
+                if ((DX::kL >> j) & 1u) atomicXor(mine + MBX * W * kThreads, x);
+            }
+            if (z != 0u) {
+#pragma unroll
+                for (int t = 0; t < MBZ; ++t)
+                    if ((DZ::row(t) >> j) & 1u) atomicXor(mine + (MBX + 1 + t) * W * kThreads, z);
+                if ((DZ::kL >> j) & 1u) atomicXor(mine + (MBX + 1 + MBZ) * W * kThreads, z);
+            }
+        }
+        __syncthreads();
+        // ---- 3: decode and tally ----
+        if (active) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                uint32_t* const mine = acc + w * kThreads + tid;
+                uint32_t sx[MBX], sz[MBZ];
+#pragma unroll
+                for (int t = 0; t < MBX; ++t) { sx[t] = mine[t * W * kThreads]; mine[t * W * kThreads] = 0u; }
+                const uint32_t lex = mine[MBX * W * kThreads];
+                mine[MBX * W * kThreads] = 0u;
+#pragma unroll
+                for (int t = 0; t < MBZ; ++t) { sz[t] = mine[(MBX + 1 + t) * W * kThreads]; mine[(MBX + 1 + t) * W * kThreads] = 0u; }
+                const uint32_t lez = mine[(MBX + 1 + MBZ) * W * kThreads];
+                mine[(MBX + 1 + MBZ) * W * kThreads] = 0u;
+                const int64_t word = u * W + w;
+                const WordOut ox = finish_side<true>(px, sx, lex, lut_x, nullptr, 0, nullptr, 0, nullptr, nullptr, word, 0xFFFFFFFFu);
+                const WordOut oz = finish_side<true>(pz, sz, lez, lut_z, nullptr, 0, nullptr, 0, nullptr, nullptr, word, 0xFFFFFFFFu);
+                c.fail_x += popc32(ox.flip);
+                c.fail_z += popc32(oz.flip);
+                c.fail_any += popc32(ox.flip | oz.flip);
+                c.miss_x += popc32(ox.miss);
+                c.miss_z += popc32(oz.miss);
+            }
+        }
+    }
+    block_tally(c, io.tally);
 }
 
 // ---- launch plumbing --------------------------------------------------------------------------
@@ -262,6 +389,11 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
     // thread keeps 4x fewer syndrome accumulators live and 4x fewer unrolled sampler sites (measured on
     // Golay-23 with VEC = 4: the first-error path inlined at 92 sites ran at 4.2e10 shots/s).
     constexpr int SVEC = 1;
+    if (l.sample && l.io.use_gap && !(getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0)) {
+        // Monte-Carlo tallies below p = 1/128: the CTA-wide two-phase gap sampler for the whole words
+        return launch_split<GapqShape<DX, DZ>::kW>(k_small_named_gapq<DX, DZ>, k_small_named<DX, DZ, SVEC, true, false>, a, l,
+                                                   smem_fast + GapqShape<DX, DZ>::kSmem, smem, stream);
+    }
     if (l.sample)
         return launch_split<SVEC>(k_small_named<DX, DZ, SVEC, true, true>, k_small_named<DX, DZ, SVEC, true, false>,
                                   a, l, smem_fast, smem, stream);

@@ -225,6 +225,23 @@ def test_fused_sampler_bit_exact_vs_oracle(name, p):
     assert code.monte_carlo(p, shots, seed, first) == omc.tally_xz(ref, ox, oz)
 
 
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("p,shots", [(1e-3, 300_000_077), (5e-3, 50_000_000), (0.0078, 20_000_033), (1e-5, 100_000_000)])
+def test_gap_sampler_queue_kernel_equals_in_place_kernel(name, p, shots, monkeypatch):
+    """The CTA-wide two-phase gap sampler (k_small_named_gapq, default below p = 1/128) and the in-place kernel
+    (QCSS_GAPQ=0) draw from the same Philox streams: identical tallies, at sizes that give every CTA many
+    iterations, queue loads from almost empty (p = 1e-5) to ~22 % of the site-words (p just below 1/128), and a
+    ragged tail; a non-aligned first_shot shard as well."""
+    code, _ = pair(name)
+    monkeypatch.setenv("QCSS_GAPQ", "0")
+    want = code.monte_carlo(p, shots, seed=0xA11CE)
+    want_shard = code.monte_carlo(p, 1_000_001, seed=0xA11CE, first_shot=128 * 12345)
+    monkeypatch.delenv("QCSS_GAPQ")
+    assert code.monte_carlo(p, shots, seed=0xA11CE) == want
+    assert code.monte_carlo(p, 1_000_001, seed=0xA11CE, first_shot=128 * 12345) == want_shard
+    assert want["fail_any"] > 0 or p < 1e-4
+
+
 def test_monte_carlo_independent_of_sharding():
     code, _ = pair("steane")
     whole = code.monte_carlo(0.05, 1 << 20, seed=11)

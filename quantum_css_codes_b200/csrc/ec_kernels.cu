@@ -2,6 +2,8 @@
 // One thread owns one 32-shot word for all rounds: the state is 2 (m + 1) registers, nothing is read from
 // or written to HBM except the six tallies, and the grid is one full wave striding over words.  Static
 // instantiations for the three benchmark descriptors, generic (runtime H in the parameter block) otherwise.
+#include <cstdlib>
+
 #include "named_codes.inc"
 #include "small_common.cuh"
 #include "ec_rounds.cuh"
@@ -69,6 +71,144 @@ k_ec_named(const __grid_constant__ EcNamedArgs a) {
     run_ec(px, pz, a.ec, tx, tz);
 }
 
+// ---- CTA-wide two-phase form (both error rates below 1/128, static descriptors) ------------------------------
+// Same idea as small_common.cuh::k_small_named_gapq: in the in-place kernel a warp walks the gap logic whenever any
+// of its lanes holds an error, three draws per qubit per round.  Here, per round: (1) every thread computes the
+// first Philox block of its 3 n site-words and queues those with an error as (thread, stream, qubit); (2) the queue
+// is handed out one item per lane, the draw finished and its error words XORed into the owner's DELTA rows in shared
+// memory -- [dS_x | dl_x | dS_z | dl_z | H.a_x | H.b_x | L.b_x | H.b_z], the five places ec_rounds.cuh folds a
+// draw into; (3) the owner applies the deltas to its register state (S, l), clears them and performs the two
+// measurements exactly as process_ec_word does.  Two block barriers per round.
+template <class DX, class DZ>
+struct EcqShape {
+    static constexpr int kRows = 3 * DX::MB + 2 * DZ::MB + 3;
+    static constexpr size_t kSmem = (size_t)kRows * kThreads * 4 + (size_t)kThreads * 3 * DX::N * 2;
+};
+
+template <class DX, class DZ>
+__global__ void __launch_bounds__(kThreads, 2)
+k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
+    using PX = StaticPolicy<DX>;
+    using PZ = StaticPolicy<DZ>;
+    constexpr int MBX = PX::MB, MBZ = PZ::MB, N = DX::N, ROWS = EcqShape<DX, DZ>::kRows;
+    // delta rows
+    constexpr int R_SX = 0, R_LX = MBX, R_SZ = MBX + 1, R_LZ = MBX + 1 + MBZ, R_AX = R_LZ + 1, R_BX = R_AX + MBX,
+                  R_BXL = R_BX + MBX, R_BZ = R_BXL + 1;
+    static_assert(R_BZ + MBZ == ROWS, "row map");
+    PX px;
+    PZ pz;
+    const EcParams& ec = a.ec;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* cursor = smem;
+    const SideLut lut_x = small::stage_side<PX, true>(px, SideTables{a.fm_x, a.co_x, a.e32_x}, cursor);
+    const SideLut lut_z = small::stage_side<PZ, true>(pz, SideTables{a.fm_z, a.co_z, a.e32_z}, cursor);
+    uint32_t* const acc = reinterpret_cast<uint32_t*>(cursor);                  // [ROWS][kThreads]
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * kThreads);  // [kThreads * 3 * N]
+    __shared__ GapTable s_tab[2];
+    __shared__ int q_count[2];
+    const int tid = threadIdx.x;
+    if (tid < 32) { s_tab[0].cdf[tid] = ec.tab_p.cdf[tid]; s_tab[1].cdf[tid] = ec.tab_q.cdf[tid]; }
+    if (tid == 32) { s_tab[0].inv = ec.tab_p.inv; s_tab[1].inv = ec.tab_q.inv; }
+    if (tid < 2) q_count[tid] = 0;
+    for (int i = tid; i < ROWS * kThreads; i += kThreads) acc[i] = 0u;
+    __syncthreads();
+    const uint32_t cdf31_p = s_tab[0].cdf[31], cdf31_q = s_tab[1].cdf[31];
+    Philox ph;
+    ph.k0 = (uint32_t)ec.seed;
+    ph.k1 = (uint32_t)(ec.seed >> 32);
+
+    Counters c = {0u, 0u, 0u, 0u, 0u};
+    const int64_t step = (int64_t)gridDim.x * kThreads;
+    const int64_t cta0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t iters = cta0 < ec.words ? (ec.words - cta0 + step - 1) / step : 0;     // uniform over the CTA
+    int phase = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t wbase = cta0 + it * step;
+        const int64_t w = wbase + tid;
+        const bool active = w < ec.words;
+        const uint64_t g = ec.first_word + (uint64_t)w;
+        const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+        uint32_t sx[MBX], sz[MBZ], lx = 0u, lz = 0u;
+#pragma unroll
+        for (int t = 0; t < MBX; ++t) sx[t] = 0u;
+#pragma unroll
+        for (int t = 0; t < MBZ; ++t) sz[t] = 0u;
+#pragma unroll 1
+        for (int r = 0; r < ec.rounds; ++r, phase ^= 1) {
+            const uint32_t base = (uint32_t)(3 * r) << 5;
+            int* const qc = &q_count[phase];
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t cdf31 = k == 0 ? cdf31_p : cdf31_q;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        uint32_t b[4];
+                        ph.block(g_lo, g_hi, base + 32u * k + (uint32_t)j, 0u, b);
+                        if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (k << 5) | j);
+                    }
+                }
+            }
+            __syncthreads();
+            const int count = *qc;
+            if (tid == 0) q_count[phase ^ 1] = 0;
+            for (int i = tid; i < count; i += kThreads) {
+                const int item = queue[i], owner = item >> 7, k = (item >> 5) & 3, j = item & 31;
+                const GapTable& tab = s_tab[k == 0 ? 0 : 1];
+                uint32_t x, z;
+                sample_site_word_gap(ec.seed, ec.first_word + (uint64_t)(wbase + owner), base + 32u * k + (uint32_t)j, tab,
+                                     tab.cdf[31], x, z);
+                uint32_t* const mine = acc + owner;
+                // where a draw goes (ec_rounds.cuh): data -> S_x, l_x, S_z, l_z; ancilla A -> H.a_x and (back-action)
+                // S_z, l_z; ancilla B -> H.b_x, L.b_x (applied after the X measurement) and H.b_z
+                const int rx = k == 0 ? R_SX : (k == 1 ? R_AX : R_BX);
+                const int rz = k == 2 ? R_BZ : R_SZ;
+                if (x != 0u) {
+#pragma unroll
+                    for (int t = 0; t < MBX; ++t)
+                        if ((DX::row(t) >> j) & 1u) atomicXor(mine + (rx + t) * kThreads, x);
+                    if (k != 1 && ((DX::kL >> j) & 1u)) atomicXor(mine + (k == 0 ? R_LX : R_BXL) * kThreads, x);
+                }
+                if (z != 0u) {
+#pragma unroll
+                    for (int t = 0; t < MBZ; ++t)
+                        if ((DZ::row(t) >> j) & 1u) atomicXor(mine + (rz + t) * kThreads, z);
+                    if (k != 2 && ((DZ::kL >> j) & 1u)) atomicXor(mine + R_LZ * kThreads, z);
+                }
+            }
+            __syncthreads();
+            if (active) {
+                uint32_t* const mine = acc + tid;
+                auto take = [&](int row) { const uint32_t v = mine[row * kThreads]; mine[row * kThreads] = 0u; return v; };
+                uint32_t ax[MBX], bx[MBX], bz[MBZ];
+#pragma unroll
+                for (int t = 0; t < MBX; ++t) { sx[t] ^= take(R_SX + t); ax[t] = take(R_AX + t); bx[t] = take(R_BX + t); }
+#pragma unroll
+                for (int t = 0; t < MBZ; ++t) { sz[t] ^= take(R_SZ + t); bz[t] = take(R_BZ + t); }
+                lx ^= take(R_LX);
+                lz ^= take(R_LZ);
+                const uint32_t bxl = take(R_BXL);
+                ec_measure(px, sx, lx, ax, lut_x, w);
+#pragma unroll
+                for (int t = 0; t < MBX; ++t) sx[t] ^= bx[t];
+                lx ^= bxl;
+                ec_measure(pz, sz, lz, bz, lut_z, w);
+            }
+        }
+        if (active) {
+            const uint32_t valid = (w == ec.words - 1) ? ec.tail_mask : 0xFFFFFFFFu;
+            const WordOut ox = finish_side<true>(px, sx, lx, lut_x, nullptr, 0, nullptr, 0, nullptr, nullptr, w, 0xFFFFFFFFu);
+            const WordOut oz = finish_side<true>(pz, sz, lz, lut_z, nullptr, 0, nullptr, 0, nullptr, nullptr, w, 0xFFFFFFFFu);
+            c.fail_x += popc32(ox.flip & valid);
+            c.fail_z += popc32(oz.flip & valid);
+            c.fail_any += popc32((ox.flip | oz.flip) & valid);
+            c.miss_x += popc32(ox.miss & valid);
+            c.miss_z += popc32(oz.miss & valid);
+        }
+    }
+    small::block_tally(c, ec.tally);
+}
+
 template <int NB, int MB>
 cudaError_t launch_generic(const EcLaunch& l, cudaStream_t stream) {
     EcGenericArgs a;
@@ -89,8 +229,11 @@ cudaError_t launch_named(const EcLaunch& l, cudaStream_t stream) {
     a.co_z = l.z->lut_corr;
     a.e32_z = l.z->lut_e32;
     a.ec = l.ec;
-    return small::launch_one(k_ec_named<DX, DZ>, a, l.ec.words,
-                             small::lut_smem(*l.x, *l.z, !DX::kSliced, !DZ::kSliced, true), stream);
+    const size_t lut = small::lut_smem(*l.x, *l.z, !DX::kSliced, !DZ::kSliced, true);
+    const bool gapq_off = getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0;
+    if (l.ec.gap_p && l.ec.gap_q && !gapq_off && lut + EcqShape<DX, DZ>::kSmem <= 200 * 1024)
+        return small::launch_one(k_ec_named_q<DX, DZ>, a, l.ec.words, lut + EcqShape<DX, DZ>::kSmem, stream);
+    return small::launch_one(k_ec_named<DX, DZ>, a, l.ec.words, lut, stream);
 }
 
 }  // namespace

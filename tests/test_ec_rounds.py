@@ -22,7 +22,8 @@ from quantum_css_codes_b200 import codes, distributed as qdist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMED = {"steane": 0, "qrm15": 1, "golay23": 2}
 CASES = [(0.05, 0.0, 1, 999), (0.03, 0.02, 3, 1000), (1e-3, 5e-3, 4, 2048), (0.2, 1e-3, 2, 333),
-         (0.0, 0.1, 2, 640), (0.004, 0.3, 2, 500), (0.05, 0.05, 0, 256)]
+         (0.0, 0.1, 2, 640), (0.004, 0.3, 2, 500), (0.05, 0.05, 0, 256),
+         (2e-3, 3e-3, 3, 5000), (0.0, 5e-3, 2, 3000), (5e-3, 0.0, 2, 1000), (7e-3, 7e-3, 6, 9000)]
 _cache = {}
 
 
@@ -171,6 +172,22 @@ def test_gpu_sharding_invariance_and_rates():
     # the first 4e6 shots as computed in the build container by the host emulation of the same device code
     assert dev.error_correct_monte_carlo(*args, 4_000_000, seed=8) == dict(
         shots=4000000, fail_x=4841, fail_z=4805, fail_any=8837, miss_x=0, miss_z=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["steane", "qrm15", "golay23"])
+def test_gpu_queue_kernel_equals_in_place_kernel(name, monkeypatch):
+    """Both error rates below 1/128: the CTA-wide two-phase kernel (k_ec_named_q) against the in-place one
+    (QCSS_GAPQ=0) on the same Philox streams, many CTA iterations, ragged tail, offset shard."""
+    dev = device_code(name)
+    runs = [((1e-3, 1e-3, 10, 30_000_017), {}), ((5e-3, 2e-3, 3, 10_000_000), {}),
+            ((1e-4, 7e-3, 7, 3_000_001), dict(first_shot=128 * 999))]
+    monkeypatch.setenv("QCSS_GAPQ", "0")
+    want = [dev.error_correct_monte_carlo(*args, seed=0xEC, **kw) for args, kw in runs]
+    monkeypatch.delenv("QCSS_GAPQ")
+    got = [dev.error_correct_monte_carlo(*args, seed=0xEC, **kw) for args, kw in runs]
+    assert got == want
+    assert want[0]["fail_any"] > 0
 
 
 @pytest.mark.gpu

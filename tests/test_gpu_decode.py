@@ -200,6 +200,7 @@ def test_specialize_through_csscode_and_cache():
     code, again = CSSCode(hx, hz), CSSCode(hx, hz)
     ref = ocss.build_css(hx, hz)
     assert code.device.kernel_name().startswith("small-generic")
+    generic_low_p = code.monte_carlo(2e-3, 5_000_011, seed=6)            # generic kernels: in-place gap sampler
     name = code.specialize()
     assert name.startswith("small-static(jit:") and again.specialize() == name
     so = [f for f in os.listdir(specialize.JIT_DIR) if name[len("small-static(jit:"):-1] in f]
@@ -209,6 +210,11 @@ def test_specialize_through_csscode_and_cache():
     assert code.decode_xz(ex, ez) == omc.tally_xz(ref, ex, ez)
     got = code.monte_carlo(0.05, 1 << 16, seed=3)
     sx, sz = ophilox.sample_bits(3, 0, 1 << 16, code.n, 0.05)
+    assert got == omc.tally_xz(ref, sx, sz)
+    # the specialised kernels sample low error rates with the CTA-wide two-phase gap sampler: same streams
+    assert code.monte_carlo(2e-3, 5_000_011, seed=6) == generic_low_p
+    got = code.monte_carlo(2e-3, 40_000, seed=7)
+    sx, sz = ophilox.sample_bits(7, 0, 40_000, code.n, 2e-3)
     assert got == omc.tally_xz(ref, sx, sz)
 
 

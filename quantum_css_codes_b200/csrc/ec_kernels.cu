@@ -86,7 +86,7 @@ struct EcqShape {
 };
 
 template <class DX, class DZ>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (DX::kSliced && DZ::kSliced) ? 3 : 2)
 k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
     using PX = StaticPolicy<DX>;
     using PZ = StaticPolicy<DZ>;

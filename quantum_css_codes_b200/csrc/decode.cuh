@@ -116,6 +116,9 @@ struct GenericPolicy {
         for (int t = 0; t < MB; ++t) s[t] ^= e & p->mask[t][j];
         le ^= e & p->lexp[j];
     }
+    // runtime qubit index (two-phase gap sampler): does key-bit row t / the logical row contain qubit j
+    QCSS_HD bool rowbit(int t, int j) const { return (p->mask[t][j] & 1u) != 0u; }
+    QCSS_HD bool lbit(int j) const { return (p->lexp[j] & 1u) != 0u; }
 };
 
 // Static: everything about H, L (and, for sliced sides, the truth tables) is a compile-time
@@ -139,6 +142,8 @@ struct StaticPolicy {
             if ((D::row(t) >> j) & 1u) s[t] ^= e;
         if ((D::kL >> j) & 1u) le ^= e;
     }
+    QCSS_HD bool rowbit(int t, int j) const { return ((D::row(t) >> j) & 1u) != 0u; }
+    QCSS_HD bool lbit(int j) const { return ((D::kL >> j) & 1u) != 0u; }
 };
 
 // ---- finish one word of one side ---------------------------------------------------------------

@@ -150,27 +150,23 @@ k_small_named(const __grid_constant__ NamedArgs a) {
 // Bit-identical to the in-place kernel (tests compare both with the oracle); QCSS_GAPQ=0 selects the in-place one.
 // Words per thread per CTA iteration: as many as keep the accumulators within ~48 KB (the three block barriers of
 // an iteration are amortised over W * n site-words per thread: Steane 4, QRM-15 2, Golay-23 1).
-template <class DX, class DZ>
+template <class PX, class PZ>
 struct GapqShape {
-    static constexpr int kRows = DX::MB + DZ::MB + 2;
+    static constexpr int kRows = PX::MB + PZ::MB + 2;
     static constexpr int kW = (kRows * 4 * kThreads * 4 <= 36 * 1024) ? 4 : ((kRows * 2 * kThreads * 4 <= 48 * 1024) ? 2 : 1);
-    static constexpr size_t kSmem = (size_t)kRows * kW * kThreads * 4 + (size_t)kThreads * kW * DX::N * 2;
+    static constexpr size_t kSmem = (size_t)kRows * kW * kThreads * 4 + (size_t)kThreads * kW * PX::NB * 2;
 };
 
-template <class DX, class DZ>
-__global__ void __launch_bounds__(kThreads, 3)
-k_small_named_gapq(const __grid_constant__ NamedArgs a) {
-    using PX = StaticPolicy<DX>;
-    using PZ = StaticPolicy<DZ>;
-    constexpr int MBX = PX::MB, MBZ = PZ::MB, ROWS = GapqShape<DX, DZ>::kRows, W = GapqShape<DX, DZ>::kW, N = DX::N;
-    static_assert(DX::N == DZ::N && N <= 32 && kThreads <= 256 && W <= 4, "queue items are (thread:8, word:2, qubit:5)");
-    PX px;
-    PZ pz;
-    const DecodeIO& io = a.io;
+template <class PX, class PZ>
+__device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const DecodeIO& io, const SideTables& tx,
+                                               const SideTables& tz) {
+    constexpr int MBX = PX::MB, MBZ = PZ::MB, ROWS = GapqShape<PX, PZ>::kRows, W = GapqShape<PX, PZ>::kW, N = PX::NB;
+    static_assert(PX::NB == PZ::NB && N <= 32 && kThreads <= 256 && W <= 4, "queue items are (thread:8, word:2, qubit:5)");
+    const int n = px.n();
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* cursor = smem;
-    const SideLut lut_x = stage_side<PX, true>(px, SideTables{a.fm_x, a.co_x, a.e32_x}, cursor);
-    const SideLut lut_z = stage_side<PZ, true>(pz, SideTables{a.fm_z, a.co_z, a.e32_z}, cursor);
+    const SideLut lut_x = stage_side<PX, true>(px, tx, cursor);
+    const SideLut lut_z = stage_side<PZ, true>(pz, tz, cursor);
     uint32_t* const acc = reinterpret_cast<uint32_t*>(cursor);                      // [ROWS][W][kThreads]
     uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * W * kThreads);  // [kThreads * W * N]
     __shared__ GapTable s_gap;
@@ -204,9 +200,11 @@ k_small_named_gapq(const __grid_constant__ NamedArgs a) {
                 const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    uint32_t b[4];
-                    ph.block(g_lo, g_hi, (uint32_t)j, 0u, b);
-                    if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
+                    if (j < n) {
+                        uint32_t b[4];
+                        ph.block(g_lo, g_hi, (uint32_t)j, 0u, b);
+                        if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
+                    }
                 }
             }
         }
@@ -222,14 +220,14 @@ k_small_named_gapq(const __grid_constant__ NamedArgs a) {
             if (x != 0u) {
 #pragma unroll
                 for (int t = 0; t < MBX; ++t)
-                    if ((DX::row(t) >> j) & 1u) atomicXor(mine + t * W * kThreads, x);
-                if ((DX::kL >> j) & 1u) atomicXor(mine + MBX * W * kThreads, x);
+                    if (px.rowbit(t, j)) atomicXor(mine + t * W * kThreads, x);
+                if (px.lbit(j)) atomicXor(mine + MBX * W * kThreads, x);
             }
             if (z != 0u) {
 #pragma unroll
                 for (int t = 0; t < MBZ; ++t)
-                    if ((DZ::row(t) >> j) & 1u) atomicXor(mine + (MBX + 1 + t) * W * kThreads, z);
-                if ((DZ::kL >> j) & 1u) atomicXor(mine + (MBX + 1 + MBZ) * W * kThreads, z);
+                    if (pz.rowbit(t, j)) atomicXor(mine + (MBX + 1 + t) * W * kThreads, z);
+                if (pz.lbit(j)) atomicXor(mine + (MBX + 1 + MBZ) * W * kThreads, z);
             }
         }
         __syncthreads();
@@ -259,6 +257,22 @@ k_small_named_gapq(const __grid_constant__ NamedArgs a) {
         }
     }
     block_tally(c, io.tally);
+}
+
+template <class DX, class DZ>
+__global__ void __launch_bounds__(kThreads, 3)
+k_small_named_gapq(const __grid_constant__ NamedArgs a) {
+    StaticPolicy<DX> px;
+    StaticPolicy<DZ> pz;
+    run_small_gapq(px, pz, a.io, SideTables{a.fm_x, a.co_x, a.e32_x}, SideTables{a.fm_z, a.co_z, a.e32_z});
+}
+
+template <int NB, int MB>
+__global__ void __launch_bounds__(kThreads, 2)
+k_small_generic_gapq(const __grid_constant__ GenericArgs a) {
+    GenericPolicy<NB, MB> px{&a.x}, pz{&a.z};
+    run_small_gapq(px, pz, a.io, SideTables{a.x.lut_fm, a.x.lut_corr, a.x.lut_e32},
+                   SideTables{a.z.lut_fm, a.z.lut_corr, a.z.lut_e32});
 }
 
 // ---- launch plumbing --------------------------------------------------------------------------
@@ -365,6 +379,11 @@ cudaError_t launch_generic(const SmallLaunch& l, cudaStream_t stream) {
     const bool lut = (MB != kSlicedM);
     const size_t smem = lut_smem(*l.x, *l.z, lut, lut, false), smem_fast = lut_smem(*l.x, *l.z, lut, lut, true);
     constexpr int SVEC = 1;                          // sampling kernels: one word per thread (see launch_named)
+    if (l.sample && l.io.use_gap && !(getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0)) {
+        using Shape = GapqShape<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>>;
+        return launch_split<Shape::kW>(k_small_generic_gapq<NB, MB>, k_small_generic<NB, MB, SVEC, true, false>, a, l,
+                                       smem_fast + Shape::kSmem, smem, stream);
+    }
     if (l.sample)
         return launch_split<SVEC>(k_small_generic<NB, MB, SVEC, true, true>, k_small_generic<NB, MB, SVEC, true, false>,
                                   a, l, smem_fast, smem, stream);
@@ -391,8 +410,9 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
     constexpr int SVEC = 1;
     if (l.sample && l.io.use_gap && !(getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0)) {
         // Monte-Carlo tallies below p = 1/128: the CTA-wide two-phase gap sampler for the whole words
-        return launch_split<GapqShape<DX, DZ>::kW>(k_small_named_gapq<DX, DZ>, k_small_named<DX, DZ, SVEC, true, false>, a, l,
-                                                   smem_fast + GapqShape<DX, DZ>::kSmem, smem, stream);
+        using Shape = GapqShape<StaticPolicy<DX>, StaticPolicy<DZ>>;
+        return launch_split<Shape::kW>(k_small_named_gapq<DX, DZ>, k_small_named<DX, DZ, SVEC, true, false>, a, l,
+                                       smem_fast + Shape::kSmem, smem, stream);
     }
     if (l.sample)
         return launch_split<SVEC>(k_small_named<DX, DZ, SVEC, true, true>, k_small_named<DX, DZ, SVEC, true, false>,

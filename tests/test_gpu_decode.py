@@ -248,6 +248,25 @@ def test_gap_sampler_queue_kernel_equals_in_place_kernel(name, p, shots, monkeyp
     assert want["fail_any"] > 0 or p < 1e-4
 
 
+@pytest.mark.parametrize("make", ["shor9", "surface3", "surface5"])
+def test_gap_sampler_queue_kernel_generic_codes(make, monkeypatch):
+    """The same A/B for codes without a static descriptor (generic kernels: runtime H in the parameter block,
+    buckets n <= 16 / 32 and m <= 5 / 8 / 16), and against the oracle sampler on a small run."""
+    hx, hz = {"shor9": codes.shor9, "surface3": lambda: codes.rotated_surface(3),
+              "surface5": lambda: codes.rotated_surface(5)}[make]()
+    code = CSSCode(np.array(hx), np.array(hz))
+    ref = ocss.build_css(np.array(hx), np.array(hz))
+    assert code.device.kernel_name().startswith("small-generic")
+    for p, shots in ((1e-3, 40_000_077), (6e-3, 8_000_000)):
+        monkeypatch.setenv("QCSS_GAPQ", "0")
+        want = code.monte_carlo(p, shots, seed=0xBEEF)
+        monkeypatch.delenv("QCSS_GAPQ")
+        assert code.monte_carlo(p, shots, seed=0xBEEF) == want
+    got = code.monte_carlo(3e-3, 30_000, seed=12, first_shot=256)
+    sx, sz = ophilox.sample_bits(12, 256, 30_000, code.n, 3e-3)
+    assert got == omc.tally_xz(ref, sx, sz)
+
+
 def test_monte_carlo_independent_of_sharding():
     code, _ = pair("steane")
     whole = code.monte_carlo(0.05, 1 << 20, seed=11)

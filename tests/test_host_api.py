@@ -140,6 +140,29 @@ def test_no_cpu_fallback_without_gpu():
         steane.syndromes(np.zeros((2, 7), dtype=np.uint8), 1)
     with pytest.raises(_native.NativeLibraryError):
         bin_matrix.reduced_row_echelon_form(np.eye(3, dtype=int))
+    # every entry point added since: decode, Monte Carlo, EC rounds, device construction, tiles, null space
+    import css_code
+    from quantum_css_codes_b200 import SyndromeCode
+    h = np.array(codes.hamming_7_4())
+    big = SyndromeCode(np.eye(40, 60, dtype=int), np.eye(40, 60, dtype=int))
+    calls = [
+        lambda: steane.decode(np.zeros((2, 7), dtype=np.uint8), 2),
+        lambda: steane.decode_xz(np.zeros((2, 7), dtype=np.uint8), np.zeros((2, 7), dtype=np.uint8)),
+        lambda: steane.monte_carlo(1e-3, 1000),
+        lambda: steane.error_correct_monte_carlo(1e-3, 1e-3, 2, 1000),
+        lambda: steane.syndrome_histogram(np.zeros((2, 7), dtype=np.uint8), 1),
+        lambda: css_code.normalize_parity_check_gpu(h.copy(), 0),
+        lambda: CSSCode(h, h, standard_form="gpu"),
+        lambda: css_code.syndrome_table_gpu(h),
+        lambda: big.syndromes_tiled(np.zeros((5, 60), dtype=np.uint8), 1),
+        lambda: big.syndromes_tiled(np.zeros((0, 60), dtype=np.uint8), 1),
+        lambda: big.sample_syndromes(1e-3, 100),
+        lambda: bin_matrix.null_space(np.eye(3, 5, dtype=int)),
+        lambda: bin_matrix.solve(np.eye(3, dtype=int), np.ones(3, dtype=int)),
+    ]
+    for call in calls:
+        with pytest.raises(_native.NativeLibraryError):
+            call()
 
 
 def test_product_never_imports_oracle():

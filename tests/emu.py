@@ -203,3 +203,26 @@ def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=
     assert rc == 0
     return dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
                 miss_x=int(tally[4]), miss_z=int(tally[5]))
+
+
+def mc_gapq(side_x, side_z, p, shots, seed=0, first_shot=0, named_id=-1):
+    """Host replay of the CTA-wide two-phase gap sampler (small_common.cuh::run_small_gapq); shots must be a
+    multiple of 128.  Returns the tally dict."""
+    from oracle import philox as _ophilox
+    assert shots % 128 == 0 and _ophilox.uses_gap_sampler(p)
+    L = lib()
+    io = DecodeIO()
+    io.words = shots // 32
+    io.tail_mask = 0xFFFFFFFF
+    io.sides = 3
+    io.seed, io.first_word, io.thr, io.use_gap = seed, first_shot // 32, _ophilox.threshold(p), 1
+    cdf, inv = _ophilox.gap_table(p)
+    for k in range(32):
+        io.gap_cdf[k] = int(cdf[k])
+    io.gap_inv = inv
+    tally = np.zeros(6, dtype=np.uint64)
+    rc = L.emu_mc_gapq(ctypes.byref(side_x.c), ctypes.byref(side_z.c), ctypes.byref(io), named_id,
+                       tally.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    assert rc == 0
+    return dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
+                miss_x=int(tally[4]), miss_z=int(tally[5]))

@@ -62,6 +62,72 @@ void run_ec(const PX& px, const PZ& pz, const EcParams& ec, const GenericSide* g
     }
 }
 
+// The CTA-wide two-phase gap sampler (small_common.cuh::run_small_gapq) replayed sequentially: the same phases
+// over the same primitives (Philox::block, sample_site_word_gap, rowbit / lbit, finish_side), with a CTA's
+// threads visited one after the other where the kernel has block barriers.  words must be a multiple of W.
+template <class PX, class PZ, int W>
+void run_gapq(const PX& px, const PZ& pz, const DecodeIO& io, const GenericSide* gx, const GenericSide* gz,
+              uint64_t* tally) {
+    constexpr int T = 256, MBX = PX::MB, MBZ = PZ::MB, ROWS = MBX + MBZ + 2, N = PX::NB;
+    const SideLut lut_x{gx->lut_fm, gx->lut_corr, (const uint8_t*)gx->lut_e32};
+    const SideLut lut_z{gz->lut_fm, gz->lut_corr, (const uint8_t*)gz->lut_e32};
+    static uint32_t acc[ROWS * W * T];
+    static uint16_t queue[T * W * N];
+    memset(acc, 0, sizeof(acc));
+    Philox ph;
+    ph.k0 = (uint32_t)io.seed;
+    ph.k1 = (uint32_t)(io.seed >> 32);
+    const uint32_t cdf31 = io.gap.cdf[31];
+    const int n = px.n();
+    const int64_t units = io.words / W;
+    for (int64_t ubase = 0; ubase < units; ubase += T) {
+        int count = 0;
+        for (int tid = 0; tid < T && ubase + tid < units; ++tid)                       // phase 1
+            for (int w = 0; w < W; ++w) {
+                const uint64_t g = io.first_word + (uint64_t)((ubase + tid) * W + w);
+                for (int j = 0; j < n; ++j) {
+                    uint32_t b[4];
+                    ph.block((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)j, 0u, b);
+                    if (b[0] < cdf31) queue[count++] = (uint16_t)((tid << 7) | (w << 5) | j);
+                }
+            }
+        for (int k = count - 1; k >= 0; --k) {                                         // phase 2, any order
+            const int item = queue[k], owner = item >> 7, w = (item >> 5) & 3, j = item & 31;
+            uint32_t x, z;
+            sample_site_word_gap(io.seed, io.first_word + (uint64_t)((ubase + owner) * W + w), (uint32_t)j, io.gap, cdf31, x, z);
+            uint32_t* mine = acc + w * T + owner;
+            for (int t = 0; t < MBX; ++t)
+                if (px.rowbit(t, j)) mine[t * W * T] ^= x;
+            if (px.lbit(j)) mine[MBX * W * T] ^= x;
+            for (int t = 0; t < MBZ; ++t)
+                if (pz.rowbit(t, j)) mine[(MBX + 1 + t) * W * T] ^= z;
+            if (pz.lbit(j)) mine[(MBX + 1 + MBZ) * W * T] ^= z;
+        }
+        for (int tid = 0; tid < T && ubase + tid < units; ++tid)                       // phase 3
+            for (int w = 0; w < W; ++w) {
+                uint32_t* mine = acc + w * T + tid;
+                uint32_t sx[MBX], sz[MBZ];
+                for (int t = 0; t < MBX; ++t) { sx[t] = mine[t * W * T]; mine[t * W * T] = 0u; }
+                const uint32_t lex = mine[MBX * W * T];
+                mine[MBX * W * T] = 0u;
+                for (int t = 0; t < MBZ; ++t) { sz[t] = mine[(MBX + 1 + t) * W * T]; mine[(MBX + 1 + t) * W * T] = 0u; }
+                const uint32_t lez = mine[(MBX + 1 + MBZ) * W * T];
+                mine[(MBX + 1 + MBZ) * W * T] = 0u;
+                const int64_t word = (ubase + tid) * W + w;
+                const WordOut ox = finish_side<true>(px, sx, lex, lut_x, nullptr, 0, nullptr, 0, nullptr, nullptr, word, 0xFFFFFFFFu);
+                const WordOut oz = finish_side<true>(pz, sz, lez, lut_z, nullptr, 0, nullptr, 0, nullptr, nullptr, word, 0xFFFFFFFFu);
+                tally[1] += popc32(ox.flip); tally[2] += popc32(oz.flip); tally[3] += popc32(ox.flip | oz.flip);
+                tally[4] += popc32(ox.miss); tally[5] += popc32(oz.miss);
+            }
+    }
+}
+
+template <int NB, int MB, int W>
+void run_gapq_generic(const GenericSide* x, const GenericSide* z, const DecodeIO& io, uint64_t* tally) {
+    GenericPolicy<NB, MB> px{x}, pz{z};
+    run_gapq<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, W>(px, pz, io, x, z, tally);
+}
+
 template <int NB, int MB>
 void run_ec_generic(const GenericSide* x, const GenericSide* z, const EcParams& ec, uint64_t* tally) {
     GenericPolicy<NB, MB> px{x}, pz{z};
@@ -73,6 +139,27 @@ void run_ec_generic(const GenericSide* x, const GenericSide* z, const EcParams& 
 extern "C" {
 
 __attribute__((visibility("default"))) int emu_sizeof_ec(void) { return (int)sizeof(EcParams); }
+
+// small_common.cuh::launch_named / launch_generic on the gap path: W as GapqShape chooses it (Steane 4, QRM-15 2,
+// Golay-23 1; generic 2 for the 5- and 8-row buckets, 1 for 16).  io->words must be a multiple of 4.
+__attribute__((visibility("default")))
+int emu_mc_gapq(const GenericSide* x, const GenericSide* z, const DecodeIO* io, int named_id, uint64_t* tally) {
+    if (named_id == 0) { run_gapq<StaticPolicy<named::Steane_X>, StaticPolicy<named::Steane_Z>, 4>({}, {}, *io, x, z, tally); return 0; }
+    if (named_id == 1) { run_gapq<StaticPolicy<named::Qrm15_X>, StaticPolicy<named::Qrm15_Z>, 2>({}, {}, *io, x, z, tally); return 0; }
+    if (named_id == 2) { run_gapq<StaticPolicy<named::Golay23_X>, StaticPolicy<named::Golay23_Z>, 1>({}, {}, *io, x, z, tally); return 0; }
+    const int m = x->m > z->m ? x->m : z->m;
+    const int mb = m <= kSlicedM ? kSlicedM : (m <= 8 ? 8 : 16);
+    if (x->n <= 16) {
+        if (mb == kSlicedM) run_gapq_generic<16, kSlicedM, 2>(x, z, *io, tally);
+        else if (mb == 8) run_gapq_generic<16, 8, 2>(x, z, *io, tally);
+        else run_gapq_generic<16, 16, 1>(x, z, *io, tally);
+    } else {
+        if (mb == kSlicedM) run_gapq_generic<32, kSlicedM, 2>(x, z, *io, tally);
+        else if (mb == 8) run_gapq_generic<32, 8, 2>(x, z, *io, tally);
+        else run_gapq_generic<32, 16, 1>(x, z, *io, tally);
+    }
+    return 0;
+}
 
 // ec_kernels.cu::launch_ec_rounds, one word after the other on the host
 __attribute__((visibility("default")))

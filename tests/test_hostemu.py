@@ -224,3 +224,18 @@ def test_fast_generic_partial_tables(n, m1, m2, p):
     assert got["fail_x"] == int(dx["flip"].sum()) and got["fail_z"] == int(dz["flip"].sum())
     assert got["fail_any"] == int((dx["flip"] | dz["flip"]).sum())
     assert got["miss_x"] == int(dx["miss"].sum()) and got["miss_z"] == int(dz["miss"].sum())
+
+
+@pytest.mark.parametrize("name", list(NAMED))
+@pytest.mark.parametrize("static", [True, False])
+@pytest.mark.parametrize("p", [1e-3, 7e-3])
+def test_two_phase_gap_sampler_replay(name, static, p):
+    """The CTA-wide two-phase gap sampler (queue of erring site-words -> shared accumulators -> decode), replayed
+    on the host over the kernels' own primitives, tallies exactly what the oracle sampler + oracle decode give:
+    static descriptors and the generic row masks (rowbit / lbit with a runtime qubit index), W = 4 / 2 / 1 words
+    per thread, several CTA iterations."""
+    code, sx, sz = build(name)
+    shots, seed, first = 128 * 300, 0xFACE, 128 * 5
+    got = emu.mc_gapq(sx, sz, p, shots, seed, first, NAMED[name] if static else -1)
+    ox, oz = ophilox.sample_bits(seed, first, shots, code.n, p)
+    assert got == omc.tally_xz(code, ox, oz)

@@ -81,7 +81,7 @@ k_ec_named(const __grid_constant__ EcNamedArgs a) {
 // measurements exactly as process_ec_word does.  Two block barriers per round.
 template <class DX, class DZ>
 struct EcqShape {
-    static constexpr int kRows = 3 * DX::MB + 2 * DZ::MB + 3;
+    static constexpr int kRows = EcDeltaRows<DX::MB, DZ::MB>::kRows;
     static constexpr size_t kSmem = (size_t)kRows * kThreads * 4 + (size_t)kThreads * 3 * DX::N * 2;
 };
 
@@ -91,10 +91,6 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
     using PX = StaticPolicy<DX>;
     using PZ = StaticPolicy<DZ>;
     constexpr int MBX = PX::MB, MBZ = PZ::MB, N = DX::N, ROWS = EcqShape<DX, DZ>::kRows;
-    // delta rows
-    constexpr int R_SX = 0, R_LX = MBX, R_SZ = MBX + 1, R_LZ = MBX + 1 + MBZ, R_AX = R_LZ + 1, R_BX = R_AX + MBX,
-                  R_BXL = R_BX + MBX, R_BZ = R_BXL + 1;
-    static_assert(R_BZ + MBZ == ROWS, "row map");
     PX px;
     PZ pz;
     const EcParams& ec = a.ec;
@@ -159,40 +155,16 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
                 sample_site_word_gap(ec.seed, ec.first_word + (uint64_t)(wbase + owner), base + 32u * k + (uint32_t)j, tab,
                                      tab.cdf[31], x, z);
                 uint32_t* const mine = acc + owner;
-                // where a draw goes (ec_rounds.cuh): data -> S_x, l_x, S_z, l_z; ancilla A -> H.a_x and (back-action)
-                // S_z, l_z; ancilla B -> H.b_x, L.b_x (applied after the X measurement) and H.b_z
-                const int rx = k == 0 ? R_SX : (k == 1 ? R_AX : R_BX);
-                const int rz = k == 2 ? R_BZ : R_SZ;
-                if (x != 0u) {
-#pragma unroll
-                    for (int t = 0; t < MBX; ++t)
-                        if ((DX::row(t) >> j) & 1u) atomicXor(mine + (rx + t) * kThreads, x);
-                    if (k != 1 && ((DX::kL >> j) & 1u)) atomicXor(mine + (k == 0 ? R_LX : R_BXL) * kThreads, x);
-                }
-                if (z != 0u) {
-#pragma unroll
-                    for (int t = 0; t < MBZ; ++t)
-                        if ((DZ::row(t) >> j) & 1u) atomicXor(mine + (rz + t) * kThreads, z);
-                    if (k != 2 && ((DZ::kL >> j) & 1u)) atomicXor(mine + R_LZ * kThreads, z);
-                }
+                ec_fold_draw(px, pz, k, j, x, z, [mine](int row, uint32_t v) { atomicXor(mine + row * kThreads, v); });
             }
             __syncthreads();
             if (active) {
                 uint32_t* const mine = acc + tid;
-                auto take = [&](int row) { const uint32_t v = mine[row * kThreads]; mine[row * kThreads] = 0u; return v; };
-                uint32_t ax[MBX], bx[MBX], bz[MBZ];
-#pragma unroll
-                for (int t = 0; t < MBX; ++t) { sx[t] ^= take(R_SX + t); ax[t] = take(R_AX + t); bx[t] = take(R_BX + t); }
-#pragma unroll
-                for (int t = 0; t < MBZ; ++t) { sz[t] ^= take(R_SZ + t); bz[t] = take(R_BZ + t); }
-                lx ^= take(R_LX);
-                lz ^= take(R_LZ);
-                const uint32_t bxl = take(R_BXL);
-                ec_measure(px, sx, lx, ax, lut_x, w);
-#pragma unroll
-                for (int t = 0; t < MBX; ++t) sx[t] ^= bx[t];
-                lx ^= bxl;
-                ec_measure(pz, sz, lz, bz, lut_z, w);
+                ec_apply_round(px, pz, sx, lx, sz, lz, lut_x, lut_z, w, [mine](int row) {
+                    const uint32_t v = mine[row * kThreads];
+                    mine[row * kThreads] = 0u;
+                    return v;
+                });
             }
         }
         if (active) {

@@ -117,4 +117,55 @@ QCSS_HD void process_ec_word(const PX& px, const PZ& pz, const EcParams& ec, con
     c.miss_z += popc32(oz.miss & valid);
 }
 
+// ---- pieces of the CTA-wide two-phase form (ec_kernels.cu::k_ec_named_q), shared with the host replay ----------
+// Per round the finished draws are folded into DELTA rows of the owning thread; where a draw goes is the model above:
+//   data (stream 0)      x -> S_x, l_x          z -> S_z, l_z
+//   ancilla A (stream 1) x -> H.a_x             z -> S_z, l_z   (back-action through CNOT data -> A)
+//   ancilla B (stream 2) x -> H.b_x, L.b_x      z -> H.b_z      (b_x reaches the data after the X measurement)
+template <int MBX, int MBZ>
+struct EcDeltaRows {
+    static constexpr int kSX = 0, kLX = MBX, kSZ = MBX + 1, kLZ = MBX + 1 + MBZ, kAX = kLZ + 1, kBX = kAX + MBX,
+                         kBXL = kBX + MBX, kBZ = kBXL + 1, kRows = kBZ + MBZ;
+};
+
+// xor_row(row, value): XOR `value` into delta row `row` of the draw's owner
+template <class PX, class PZ, class XorRow>
+QCSS_HD void ec_fold_draw(const PX& px, const PZ& pz, int stream, int j, uint32_t x, uint32_t z, XorRow xor_row) {
+    using R = EcDeltaRows<PX::MB, PZ::MB>;
+    const int rx = stream == 0 ? R::kSX : (stream == 1 ? R::kAX : R::kBX);
+    const int rz = stream == 2 ? R::kBZ : R::kSZ;
+    if (x != 0u) {
+#pragma unroll
+        for (int t = 0; t < PX::MB; ++t)
+            if (px.rowbit(t, j)) xor_row(rx + t, x);
+        if (stream != 1 && px.lbit(j)) xor_row(stream == 0 ? R::kLX : R::kBXL, x);
+    }
+    if (z != 0u) {
+#pragma unroll
+        for (int t = 0; t < PZ::MB; ++t)
+            if (pz.rowbit(t, j)) xor_row(rz + t, z);
+        if (stream != 2 && pz.lbit(j)) xor_row(R::kLZ, z);
+    }
+}
+
+// take(row): read-and-clear delta row `row` of this thread.  Applies one round to the register state.
+template <class PX, class PZ, class Take>
+QCSS_HD void ec_apply_round(const PX& px, const PZ& pz, uint32_t (&sx)[PX::MB], uint32_t& lx, uint32_t (&sz)[PZ::MB],
+                            uint32_t& lz, const SideLut& lut_x, const SideLut& lut_z, int64_t w, Take take) {
+    using R = EcDeltaRows<PX::MB, PZ::MB>;
+    uint32_t ax[PX::MB], bx[PX::MB], bz[PZ::MB];
+#pragma unroll
+    for (int t = 0; t < PX::MB; ++t) { sx[t] ^= take(R::kSX + t); ax[t] = take(R::kAX + t); bx[t] = take(R::kBX + t); }
+#pragma unroll
+    for (int t = 0; t < PZ::MB; ++t) { sz[t] ^= take(R::kSZ + t); bz[t] = take(R::kBZ + t); }
+    lx ^= take(R::kLX);
+    lz ^= take(R::kLZ);
+    const uint32_t bxl = take(R::kBXL);
+    ec_measure(px, sx, lx, ax, lut_x, w);
+#pragma unroll
+    for (int t = 0; t < PX::MB; ++t) sx[t] ^= bx[t];
+    lx ^= bxl;
+    ec_measure(pz, sz, lz, bz, lut_z, w);
+}
+
 }  // namespace qcss

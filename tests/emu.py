@@ -180,8 +180,9 @@ def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1,
     return out
 
 
-def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0, named_id=-1):
-    """Host emulation of qcss_ec_run (api.cu::launch_ec + ec_kernels.cu): returns the tally dict."""
+def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0, named_id=-1, queue_form=False):
+    """Host emulation of qcss_ec_run (api.cu::launch_ec + ec_kernels.cu): returns the tally dict.
+    ``queue_form``: replay the CTA-wide two-phase kernel (k_ec_named_q; static descriptors, both rates < 1/128)."""
     from oracle import philox as _ophilox
     L = lib()
     assert L.emu_sizeof_ec() == ctypes.sizeof(EcParams)
@@ -198,8 +199,9 @@ def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=
             tab.cdf[k] = int(cdf[k])
         tab.inv = inv
     tally = np.zeros(6, dtype=np.uint64)
-    rc = L.emu_ec(ctypes.byref(side_x.c), ctypes.byref(side_z.c), ctypes.byref(ec), named_id,
-                  tally.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    fn = L.emu_ecq if queue_form else L.emu_ec
+    rc = fn(ctypes.byref(side_x.c), ctypes.byref(side_z.c), ctypes.byref(ec), named_id,
+            tally.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
     assert rc == 0
     return dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
                 miss_x=int(tally[4]), miss_z=int(tally[5]))

@@ -128,6 +128,66 @@ void run_gapq_generic(const GenericSide* x, const GenericSide* z, const DecodeIO
     run_gapq<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, W>(px, pz, io, x, z, tally);
 }
 
+// ec_kernels.cu::k_ec_named_q replayed sequentially (one CTA of 256 words at a time): first blocks -> queue ->
+// ec_fold_draw into the owners' delta rows -> ec_apply_round, over the kernel's own helpers and row map.
+template <class PX, class PZ>
+void run_ecq(const PX& px, const PZ& pz, const EcParams& ec, const GenericSide* gx, const GenericSide* gz, uint64_t* tally) {
+    constexpr int T = 256, MBX = PX::MB, MBZ = PZ::MB, ROWS = EcDeltaRows<MBX, MBZ>::kRows, N = PX::NB;
+    const SideLut lut_x{gx->lut_fm, gx->lut_corr, (const uint8_t*)gx->lut_e32};
+    const SideLut lut_z{gz->lut_fm, gz->lut_corr, (const uint8_t*)gz->lut_e32};
+    static uint32_t acc[ROWS * T];
+    static uint16_t queue[T * 3 * N];
+    static uint32_t sx[T][MBX], sz[T][MBZ], lx[T], lz[T];
+    memset(acc, 0, sizeof(acc));
+    Philox ph;
+    ph.k0 = (uint32_t)ec.seed;
+    ph.k1 = (uint32_t)(ec.seed >> 32);
+    const int n = px.n();
+    for (int64_t wbase = 0; wbase < ec.words; wbase += T) {
+        const int live = (int)((ec.words - wbase) < T ? (ec.words - wbase) : T);
+        memset(sx, 0, sizeof(sx)); memset(sz, 0, sizeof(sz)); memset(lx, 0, sizeof(lx)); memset(lz, 0, sizeof(lz));
+        for (int r = 0; r < ec.rounds; ++r) {
+            const uint32_t base = (uint32_t)(3 * r) << 5;
+            int count = 0;
+            for (int tid = 0; tid < live; ++tid) {
+                const uint64_t g = ec.first_word + (uint64_t)(wbase + tid);
+                for (int k = 0; k < 3; ++k)
+                    for (int j = 0; j < n; ++j) {
+                        uint32_t b[4];
+                        ph.block((uint32_t)g, (uint32_t)(g >> 32), base + 32u * k + (uint32_t)j, 0u, b);
+                        if (b[0] < (k == 0 ? ec.tab_p.cdf[31] : ec.tab_q.cdf[31])) queue[count++] = (uint16_t)((tid << 7) | (k << 5) | j);
+                    }
+            }
+            for (int i = count - 1; i >= 0; --i) {
+                const int item = queue[i], owner = item >> 7, k = (item >> 5) & 3, j = item & 31;
+                const GapTable& tab = k == 0 ? ec.tab_p : ec.tab_q;
+                uint32_t x, z;
+                sample_site_word_gap(ec.seed, ec.first_word + (uint64_t)(wbase + owner), base + 32u * k + (uint32_t)j, tab,
+                                     tab.cdf[31], x, z);
+                uint32_t* mine = acc + owner;
+                ec_fold_draw(px, pz, k, j, x, z, [mine](int row, uint32_t v) { mine[row * T] ^= v; });
+            }
+            for (int tid = 0; tid < live; ++tid) {
+                uint32_t* mine = acc + tid;
+                ec_apply_round(px, pz, sx[tid], lx[tid], sz[tid], lz[tid], lut_x, lut_z, wbase + tid, [mine](int row) {
+                    const uint32_t v = mine[row * T];
+                    mine[row * T] = 0u;
+                    return v;
+                });
+            }
+        }
+        for (int tid = 0; tid < live; ++tid) {
+            const int64_t w = wbase + tid;
+            const uint32_t valid = (w == ec.words - 1) ? ec.tail_mask : 0xFFFFFFFFu;
+            const WordOut ox = finish_side<true>(px, sx[tid], lx[tid], lut_x, nullptr, 0, nullptr, 0, nullptr, nullptr, w, 0xFFFFFFFFu);
+            const WordOut oz = finish_side<true>(pz, sz[tid], lz[tid], lut_z, nullptr, 0, nullptr, 0, nullptr, nullptr, w, 0xFFFFFFFFu);
+            tally[1] += popc32(ox.flip & valid); tally[2] += popc32(oz.flip & valid);
+            tally[3] += popc32((ox.flip | oz.flip) & valid);
+            tally[4] += popc32(ox.miss & valid); tally[5] += popc32(oz.miss & valid);
+        }
+    }
+}
+
 template <int NB, int MB>
 void run_ec_generic(const GenericSide* x, const GenericSide* z, const EcParams& ec, uint64_t* tally) {
     GenericPolicy<NB, MB> px{x}, pz{z};
@@ -159,6 +219,16 @@ int emu_mc_gapq(const GenericSide* x, const GenericSide* z, const DecodeIO* io, 
         else run_gapq_generic<32, 16, 1>(x, z, *io, tally);
     }
     return 0;
+}
+
+// ec_kernels.cu::k_ec_named_q (static descriptors, both rates below 1/128)
+__attribute__((visibility("default")))
+int emu_ecq(const GenericSide* x, const GenericSide* z, const EcParams* ec, int named_id, uint64_t* tally) {
+#define EMU_ECQ_CASE(ID, DX, DZ) \
+    if (named_id == ID) { run_ecq(StaticPolicy<named::DX>{}, StaticPolicy<named::DZ>{}, *ec, x, z, tally); return 0; }
+    QCSS_FOR_EACH_NAMED(EMU_ECQ_CASE)
+#undef EMU_ECQ_CASE
+    return -1;
 }
 
 // ec_kernels.cu::launch_ec_rounds, one word after the other on the host

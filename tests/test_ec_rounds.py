@@ -49,6 +49,17 @@ def test_hostemu_matches_oracle(name, static):
         assert got == want, (p, q, rounds, shots)
 
 
+@pytest.mark.parametrize("name", list(NAMED))
+def test_hostemu_queue_form_matches_oracle(name):
+    """The CTA-wide two-phase EC kernel replayed on the host over its own helpers (ec_fold_draw / ec_apply_round and
+    the delta-row map): oracle tallies for every case with both rates below 1/128, ragged tails included."""
+    code, sx, sz = build(name)
+    for p, q, rounds, shots in [c for c in CASES if c[0] < 1 / 128 and c[1] < 1 / 128] + [(3e-3, 3e-3, 2, 128 * 9 + 5)]:
+        got = emu.ec_run(sx, sz, p, q, rounds, shots, seed=0xABCDEF12345, first_shot=256, named_id=NAMED[name], queue_form=True)
+        want = oec.ec_rounds(code, p, q, rounds, shots, seed=0xABCDEF12345, first_shot=256)
+        assert got == want, (p, q, rounds, shots)
+
+
 def test_hostemu_generic_shor9():
     """A code that only has the generic kernels (n = 9, m = 2 and 6)."""
     code = ocss.build_css(*[np.array(h) for h in codes.shor9()])

@@ -82,6 +82,17 @@ QCSS_API int qcss_device_count(int* count);
 QCSS_API int qcss_set_device(int device);
 QCSS_API int qcss_host_alloc(void** ptr, size_t bytes);          /* pinned host memory for the e2e path */
 QCSS_API int qcss_host_free(void* ptr);
+/* Kernel SELECTION options (process-wide).  Each one chooses between implementations whose results are
+ * bit-identical -- the parity tests run both sides -- and none is ever read from the environment:
+ *   "gapq"       1 (default) CTA-wide two-phase gap sampler below p = 1/128, 0 the in-place form
+ *   "dense"      -1 (default) large check matrices go to the tensor-core kernel by size and density,
+ *                0 never, 1 always; taken at qcss_code_create
+ *   "named"      1 (default) use a built-in static descriptor when the code matches one, 0 generic kernels;
+ *                taken at qcss_code_create
+ *   "gf2_kernel" 0 (default) batched RREF kernel by shape, 1 column-by-column, 2 m4r, 3 m4r2 (rows <= 1024)
+ * QCSS_ERR_INVALID for an unknown name or a value out of range. */
+QCSS_API int qcss_set_option(const char* name, int value);
+QCSS_API int qcss_get_option(const char* name, int* value);
 
 /* ---- code object ----------------------------------------------------------------------- */
 /* Uploads what CSSCode.__init__ computed (css_code.py:32-75): the NORMALISED parity checks

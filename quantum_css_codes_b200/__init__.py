@@ -8,8 +8,8 @@ loudly (``NativeLibraryError``) when ``libqcss.so`` has not been built.  No CPU 
 """
 
 from . import bin_matrix, codes, css_code, errors, planes            # noqa: F401
-from .css_code import CSSCode, SyndromeCode                           # noqa: F401
+from .css_code import AttachedCode, CSSCode, SyndromeCode, attach     # noqa: F401
 from .errors import InvalidCodeError, NativeLibraryError, UnsupportedGateError  # noqa: F401
 
-__all__ = ["bin_matrix", "css_code", "codes", "errors", "planes", "CSSCode", "SyndromeCode",
+__all__ = ["bin_matrix", "css_code", "codes", "errors", "planes", "CSSCode", "SyndromeCode", "AttachedCode", "attach",
            "InvalidCodeError", "UnsupportedGateError", "NativeLibraryError"]

@@ -6,6 +6,7 @@ The library is built in-tree (``python -m quantum_css_codes_b200.build`` or
 fallback: if the library is missing or a CUDA call fails, ``NativeLibraryError`` is raised.
 """
 
+import contextlib
 import ctypes
 import os
 import threading
@@ -57,6 +58,8 @@ PROTOTYPES = {
     "qcss_set_device": (ctypes.c_int, [ctypes.c_int]),
     "qcss_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
     "qcss_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcss_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "qcss_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]),
     "qcss_code_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_u8p, ctypes.c_int, _c_u8p,
                                         _c_u8p, _c_u8p,
                                         ctypes.c_int64, _c_i64p, _c_u8p,
@@ -172,6 +175,26 @@ def check(rc):
     raise NativeLibraryError(f"libqcss error {rc}: {msg}")
 
 
+def set_option(name, value):
+    """qcss_set_option: choose between bit-identical kernel implementations (include/qcss.h lists them).
+    Returns the previous value.  The library reads nothing from the environment."""
+    lib = load()
+    old = ctypes.c_int()
+    check(lib.qcss_get_option(name.encode(), ctypes.byref(old)))
+    check(lib.qcss_set_option(name.encode(), int(value)))
+    return old.value
+
+
+@contextlib.contextmanager
+def option(name, value):
+    """``with option("gapq", 0): ...`` -- set a selection option for a block and restore it."""
+    old = set_option(name, value)
+    try:
+        yield
+    finally:
+        set_option(name, old)
+
+
 def _ptr(arr):
     return ctypes.c_void_p(arr.ctypes.data) if arr is not None else ctypes.c_void_p(0)
 
@@ -209,6 +232,19 @@ class DeviceCode:
                                    ctypes.byref(handle)))
         self._lib = lib
         self.handle = handle
+
+    @classmethod
+    def from_csscode(cls, code):
+        """Device object for ANY code object carrying the reference's attributes (css_code.py:63-72, 124-161):
+        ``n``, ``parity_check_c1/2`` (normalised), ``_c1/_c2_syndromes`` (dict key -> correction) and the
+        logical rows ``x_operator_matrix()`` / ``z_operator_matrix()`` -- e.g. a ``CSSCode`` built by the
+        unmodified reference.  Nothing is recomputed: the tables and matrices are uploaded as they stand."""
+        lx = np.asarray(code.x_operator_matrix())
+        lz = np.asarray(code.z_operator_matrix())
+        if lx.shape[0] != 1 or lz.shape[0] != 1:
+            raise ValueError("the fused logical check covers one logical qubit (k = 1)")
+        return cls(int(code.n), np.asarray(code.parity_check_c1), np.asarray(code.parity_check_c2),
+                   lx[0], lz[0], code._c1_syndromes, code._c2_syndromes)
 
     def __del__(self):
         handle, self.handle = getattr(self, "handle", None), None

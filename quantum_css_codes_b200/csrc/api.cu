@@ -14,8 +14,16 @@
 
 #include "../../include/qcss.h"
 #include "launch.h"
+#include "options.h"
 
 using namespace qcss;
+
+namespace qcss {
+Options& options() {
+    static Options o;
+    return o;
+}
+}  // namespace qcss
 
 namespace {
 
@@ -57,6 +65,9 @@ struct DevBuf {
 };
 
 constexpr int kSlots = 3;
+// Largest Monte-Carlo launch: a one-wave grid has >= 148 * 8 warps on a B200, so a warp sees at most
+// 2^38 / 1184 = 2.3e8 shots (events) per launch -- a factor 18 below the 32-bit reduce in block_tally.
+constexpr int64_t kMaxShotsPerLaunch = (int64_t)1 << 38;
 
 }  // namespace
 
@@ -101,6 +112,15 @@ int check_planes(const void* p, int64_t stride, int64_t shots, const char* what)
     if (p == nullptr) return fail(QCSS_ERR_INVALID, "%s is NULL", what);
     if (((uintptr_t)p & 15u) != 0) return fail(QCSS_ERR_INVALID, "%s must be 16-byte aligned", what);
     if (stride < 2 || (stride & 1) || stride * 64 < ((shots + 127) / 128) * 128)
+        return fail(QCSS_ERR_INVALID, "%s: stride (%lld words) must be even and cover %lld shots",
+                    what, (long long)stride, (long long)shots);
+    return QCSS_OK;
+}
+
+// Host-buffer entry points validate shots and strides BEFORE sizing any allocation or copy from them.
+int check_host_stride(int64_t stride, int64_t shots, const char* what) {
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    if (stride < 2 || (stride & 1) || stride > ((int64_t)1 << 40) || stride * 64 < ((shots + 127) / 128) * 128)
         return fail(QCSS_ERR_INVALID, "%s: stride (%lld words) must be even and cover %lld shots",
                     what, (long long)stride, (long long)shots);
     return QCSS_OK;
@@ -193,10 +213,9 @@ int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, 
 }
 
 // A check matrix goes to the tensor-core kernel when it is big and dense enough for the contraction
-// to be a real GEMM (QCSS_DENSE=1 / 0 forces the choice, for the parity tests and the comparison runs).
+// to be a real GEMM (option "dense" = 1 / 0 forces the choice, for the parity tests and the comparison runs).
 bool wants_dense(int m, int n, const uint8_t* H) {
-    const char* force = getenv("QCSS_DENSE");
-    if (force != nullptr) return atoi(force) != 0;
+    if (options().dense >= 0) return options().dense != 0;
     if ((size_t)m * n < (size_t)256 * 512) return false;
     size_t nnz = 0;
     for (size_t i = 0; i < (size_t)m * n; ++i) nnz += H[i] & 1;
@@ -314,6 +333,18 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
         if (d_ez && (rc = check_planes(d_ez, e_stride, shots, "ez planes"))) return rc;
     }
     if (shots == 0) return QCSS_OK;
+    if (shots > kMaxShotsPerLaunch) {
+        // the kernels count events in 32-bit per-thread registers and reduce them per warp in 32 bits before
+        // widening: bound the shots of one launch so a warp's share stays far below 2^32 (tallies accumulate)
+        for (int64_t done = 0; done < shots; done += kMaxShotsPerLaunch) {
+            const int64_t part = shots - done < kMaxShotsPerLaunch ? shots - done : kMaxShotsPerLaunch;
+            const int64_t word_off = done / 64;
+            rc = launch_mc(c, p, part, seed, first_shot + done, d_tally, d_ex ? d_ex + word_off : nullptr,
+                           d_ez ? d_ez + word_off : nullptr, e_stride, stream);
+            if (rc) return rc;
+        }
+        return QCSS_OK;
+    }
     SmallLaunch l;
     l.x = &c->side_x;
     l.z = &c->side_z;
@@ -328,11 +359,12 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
     l.io.seed = seed;
     l.io.first_word = (uint64_t)(first_shot / 32);
     l.io.thr = thr;
-    // error rates below 1/128 take the gap sampler (measured crossover on Steane: p ~ 0.008) (QCSS_SAMPLER=bits forces the bit-serial one: A/B runs)
-    l.io.use_gap = (thr < (1u << 25) && getenv("QCSS_SAMPLER_BITS") == nullptr) ? 1u : 0u;
+    // error rates below 1/128 take the gap sampler (measured crossover on Steane: p ~ 0.008)
+    l.io.use_gap = (thr < (1u << 25)) ? 1u : 0u;
     gap_table_from_p(p, &l.io.gap);
     l.named_id = c->named_id;
     l.sample = true;
+    l.gapq = options().gapq != 0;
     QCSS_CUDA(launch_small_any(c, l, stream));
     return QCSS_OK;
 }
@@ -352,6 +384,13 @@ int launch_ec(qcss_code* c, double p_data, double p_anc, int rounds, int64_t sho
     if (rc) return rc;
     if ((rc = threshold_from_p(p_anc, &l.ec.thr_q))) return rc;
     if (shots == 0) return QCSS_OK;
+    if (shots > kMaxShotsPerLaunch) {                       // 32-bit per-warp event counters: see launch_mc
+        for (int64_t done = 0; done < shots; done += kMaxShotsPerLaunch) {
+            const int64_t part = shots - done < kMaxShotsPerLaunch ? shots - done : kMaxShotsPerLaunch;
+            if ((rc = launch_ec(c, p_data, p_anc, rounds, part, seed, first_shot + done, d_tally, stream))) return rc;
+        }
+        return QCSS_OK;
+    }
     l.x = &c->side_x;
     l.z = &c->side_z;
     l.named_id = c->named_id;
@@ -361,9 +400,9 @@ int launch_ec(qcss_code* c, double p_data, double p_anc, int rounds, int64_t sho
     l.ec.rounds = rounds;
     l.ec.seed = seed;
     l.ec.first_word = (uint64_t)(first_shot / 32);
-    const bool bits_only = getenv("QCSS_SAMPLER_BITS") != nullptr;      // same sampler rule as qcss_mc_run
-    l.ec.gap_p = (l.ec.thr_p < (1u << 25) && !bits_only) ? 1u : 0u;
-    l.ec.gap_q = (l.ec.thr_q < (1u << 25) && !bits_only) ? 1u : 0u;
+    l.ec.gap_p = (l.ec.thr_p < (1u << 25)) ? 1u : 0u;                    // same sampler rule as qcss_mc_run
+    l.ec.gap_q = (l.ec.thr_q < (1u << 25)) ? 1u : 0u;
+    l.gapq = options().gapq != 0;
     gap_table_from_p(p_data, &l.ec.tab_p);
     gap_table_from_p(p_anc, &l.ec.tab_q);
     QCSS_CUDA(launch_ec_rounds(l, stream));
@@ -423,7 +462,31 @@ void tally_from(const uint64_t* h, int64_t shots, qcss_tally* t) {
 
 extern "C" {
 
-QCSS_API int qcss_version(void) { return 100; }
+QCSS_API int qcss_version(void) { return 200; }
+
+QCSS_API int qcss_set_option(const char* name, int value) {
+    if (!name) return fail(QCSS_ERR_INVALID, "option name is NULL");
+    Options& o = options();
+    const std::string key(name);
+    if (key == "gapq" && (value == 0 || value == 1)) o.gapq = value;
+    else if (key == "dense" && value >= -1 && value <= 1) o.dense = value;
+    else if (key == "named" && (value == 0 || value == 1)) o.named = value;
+    else if (key == "gf2_kernel" && value >= 0 && value <= 3) o.gf2_kernel = value;
+    else return fail(QCSS_ERR_INVALID, "unknown option or value out of range: %s = %d", name, value);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_get_option(const char* name, int* value) {
+    if (!name || !value) return fail(QCSS_ERR_INVALID, "NULL argument");
+    const Options& o = options();
+    const std::string key(name);
+    if (key == "gapq") *value = o.gapq;
+    else if (key == "dense") *value = o.dense;
+    else if (key == "named") *value = o.named;
+    else if (key == "gf2_kernel") *value = o.gf2_kernel;
+    else return fail(QCSS_ERR_INVALID, "unknown option: %s", name);
+    return QCSS_OK;
+}
 
 QCSS_API const char* qcss_last_error(void) { return g_err; }
 
@@ -468,8 +531,7 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
         rc = build_side(c, c->side_x, c->rows_x, c->lmask_x, m2, H2, Lz, n2, keys2, corr2, c->fm_x, c->co_x, c->e32_x);
         if (!rc) rc = build_side(c, c->side_z, c->rows_z, c->lmask_z, m1, H1, Lx, n1, keys1, corr1, c->fm_z, c->co_z, c->e32_z);
         if (!rc) c->named_id = match_named(c->side_x, c->rows_x, c->lmask_x, c->side_z, c->rows_z, c->lmask_z);
-        // debugging / benchmarking knob: force the generic (runtime-H) kernels
-        if (getenv("QCSS_DISABLE_NAMED") != nullptr) c->named_id = -1;
+        if (!options().named) c->named_id = -1;         // option "named" = 0: the generic (runtime-H) kernels
     } else if ((keys1 && n1 > 0) || (keys2 && n2 > 0)) {
         // tables are accepted but unusable: decode entry points will report UNSUPPORTED
     }
@@ -566,7 +628,7 @@ static int launch_sample_tiles_checked(qcss_code* c, double p, int64_t shots, ui
     if (shots == 0) return QCSS_OK;
     GapTable gap;
     gap_table_from_p(p, &gap);
-    const uint32_t use_gap = (thr < (1u << 25) && getenv("QCSS_SAMPLER_BITS") == nullptr) ? 1u : 0u;
+    const uint32_t use_gap = (thr < (1u << 25)) ? 1u : 0u;
     cudaError_t e = launch_sample_syndrome_tiles(c->sp2, c->sp1, (uint32_t*)d_sx, (uint32_t*)d_sz, (uint32_t*)d_ex,
                                                  (uint32_t*)d_ez, (shots + 31) / 32, tail_mask_for(shots), seed,
                                                  (uint64_t)(first_shot / 32), thr, use_gap, gap, stream);
@@ -600,7 +662,7 @@ QCSS_API int qcss_sample_syndrome_tiles(qcss_code* c, double p, int64_t shots, u
     rc = launch_sample_tiles_checked(c, p, shots, seed, first_shot, sx_tiles ? (uint64_t*)c->buf_a.p : nullptr,
                                      sz_tiles ? (uint64_t*)c->buf_b.p : nullptr, ex_tiles ? (uint64_t*)c->buf_c.p : nullptr,
                                      ez_tiles ? (uint64_t*)c->buf_d.p : nullptr, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     if (sx_tiles) QCSS_CUDA(cudaMemcpyAsync(sx_tiles, c->buf_a.p, sxb, cudaMemcpyDeviceToHost, c->stream));
     if (sz_tiles) QCSS_CUDA(cudaMemcpyAsync(sz_tiles, c->buf_b.p, szb, cudaMemcpyDeviceToHost, c->stream));
     if (ex_tiles) QCSS_CUDA(cudaMemcpyAsync(ex_tiles, c->buf_c.p, eb, cudaMemcpyDeviceToHost, c->stream));
@@ -630,7 +692,7 @@ QCSS_API int qcss_syndrome_tiles(qcss_code* c, int which, const uint64_t* e_tile
     QCSS_CUDA(c->buf_b.reserve(sb));
     QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_tiles, eb, cudaMemcpyHostToDevice, c->stream));
     rc = launch_syndrome_tiles_checked(c, which, (const uint64_t*)c->buf_a.p, shots, (uint64_t*)c->buf_b.p, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     QCSS_CUDA(cudaMemcpyAsync(s_tiles, c->buf_b.p, sb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
     return QCSS_OK;
@@ -661,8 +723,10 @@ QCSS_API int qcss_syndrome(qcss_code* c, int which, const uint64_t* e_planes, in
     if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
     if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
     if (!e_planes || !s_planes) return fail(QCSS_ERR_INVALID, "NULL planes");
-    int rc = ensure_streams(c);
-    if (rc) return rc;
+    int rc;
+    if ((rc = check_host_stride(e_stride, shots, "error planes"))) return rc;
+    if ((rc = check_host_stride(s_stride, shots, "syndrome planes"))) return rc;
+    if ((rc = ensure_streams(c))) return rc;
     const int m = (which == 1) ? c->m1 : c->m2;
     const size_t eb = (size_t)c->n * e_stride * 8, sb = (size_t)m * s_stride * 8;
     QCSS_CUDA(c->buf_a.reserve(eb));
@@ -671,7 +735,7 @@ QCSS_API int qcss_syndrome(qcss_code* c, int which, const uint64_t* e_planes, in
     QCSS_CUDA(cudaMemsetAsync(c->buf_b.p, 0, sb, c->stream));
     rc = launch_syndrome(c, which, (const uint64_t*)c->buf_a.p, e_stride, shots, (uint64_t*)c->buf_b.p,
                          s_stride, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     QCSS_CUDA(cudaMemcpyAsync(s_planes, c->buf_b.p, sb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
     return QCSS_OK;
@@ -682,8 +746,9 @@ QCSS_API int qcss_decode(qcss_code* c, int which, const uint64_t* e_planes, int6
     if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
     if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
     if (!e_planes) return fail(QCSS_ERR_INVALID, "NULL planes");
-    int rc = ensure_streams(c);
-    if (rc) return rc;
+    int rc;
+    if ((rc = check_host_stride(e_stride, shots, "error planes"))) return rc;
+    if ((rc = ensure_streams(c))) return rc;
     const size_t eb = (size_t)c->n * e_stride * 8, pb = (size_t)e_stride * 8;
     QCSS_CUDA(c->buf_a.reserve(eb));
     QCSS_CUDA(c->buf_b.reserve(eb));
@@ -711,7 +776,7 @@ QCSS_API int qcss_decode(qcss_code* c, int which, const uint64_t* e_planes, int6
         io.miss_z = (uint64_t*)c->buf_d.p;
     }
     rc = launch_decode(c, &io, shots, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     uint64_t h[6] = {0, 0, 0, 0, 0, 0};
     if (corr_planes) QCSS_CUDA(cudaMemcpyAsync(corr_planes, c->buf_b.p, eb, cudaMemcpyDeviceToHost, c->stream));
     if (flip_plane) QCSS_CUDA(cudaMemcpyAsync(flip_plane, c->buf_c.p, pb, cudaMemcpyDeviceToHost, c->stream));
@@ -762,7 +827,10 @@ QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez
         io.e_stride = chunk_words;
         io.tally = (uint64_t*)c->tally.p;
         rc = launch_decode(c, &io, cshots, st);
-        if (rc) return rc;
+        if (rc) {
+            for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot_stream[i]);
+            return rc;
+        }
     }
     for (int i = 0; i < kSlots; ++i) QCSS_CUDA(cudaStreamSynchronize(c->slot_stream[i]));
     uint64_t h[6];
@@ -778,7 +846,7 @@ QCSS_API int qcss_mc_run(qcss_code* c, double p, int64_t shots, uint64_t seed, i
     QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
     rc = launch_mc(c, p, shots, seed, first_shot, (uint64_t*)c->tally.p, nullptr, nullptr, 0, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     uint64_t h[6];
     QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
@@ -800,7 +868,7 @@ QCSS_API int qcss_ec_run(qcss_code* c, double p_data, double p_ancilla, int roun
     QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
     rc = launch_ec(c, p_data, p_ancilla, rounds, shots, seed, first_shot, (uint64_t*)c->tally.p, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     uint64_t h[6];
     QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
@@ -812,8 +880,10 @@ QCSS_API int qcss_mc_sample(qcss_code* c, double p, int64_t shots, uint64_t seed
                    uint64_t* ez, int64_t e_stride) {
     if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
     if (!ex || !ez) return fail(QCSS_ERR_INVALID, "NULL planes");
-    int rc = ensure_streams(c);
-    if (rc) return rc;
+    int rc;
+    if ((rc = check_host_stride(e_stride, shots, "error planes"))) return rc;
+    if (first_shot < 0 || (first_shot & 127)) return fail(QCSS_ERR_INVALID, "first_shot must be a multiple of 128");
+    if ((rc = ensure_streams(c))) return rc;
     const size_t eb = (size_t)c->n * e_stride * 8;
     QCSS_CUDA(c->buf_a.reserve(eb));
     QCSS_CUDA(c->buf_b.reserve(eb));
@@ -821,7 +891,7 @@ QCSS_API int qcss_mc_sample(qcss_code* c, double p, int64_t shots, uint64_t seed
     QCSS_CUDA(cudaMemsetAsync(c->buf_b.p, 0, eb, c->stream));
     rc = launch_mc(c, p, shots, seed, first_shot, nullptr, (uint64_t*)c->buf_a.p, (uint64_t*)c->buf_b.p,
                    e_stride, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     QCSS_CUDA(cudaMemcpyAsync(ex, c->buf_a.p, eb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaMemcpyAsync(ez, c->buf_b.p, eb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1172,15 +1242,16 @@ QCSS_API int qcss_syndrome_hist(qcss_code* c, int which, const uint64_t* e_plane
     if (!e_planes || !hist) return fail(QCSS_ERR_INVALID, "NULL argument");
     const int m = (which == 1) ? c->m1 : c->m2;
     if (m < 1 || m > 24) return fail(QCSS_ERR_UNSUPPORTED, "syndrome histograms cover 1 <= m <= 24 (got %d)", m);
-    int rc = ensure_streams(c);
-    if (rc) return rc;
+    int rc;
+    if ((rc = check_host_stride(e_stride, shots, "error planes"))) return rc;
+    if ((rc = ensure_streams(c))) return rc;
     const size_t eb = (size_t)c->n * e_stride * 8, hb = ((size_t)1 << m) * 8;
     QCSS_CUDA(c->buf_a.reserve(eb));
     QCSS_CUDA(c->buf_c.reserve(hb));
     QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, e_planes, eb, cudaMemcpyHostToDevice, c->stream));
     QCSS_CUDA(cudaMemsetAsync(c->buf_c.p, 0, hb, c->stream));
     rc = qcss_syndrome_hist_dev(c, which, (const uint64_t*)c->buf_a.p, e_stride, shots, (uint64_t*)c->buf_c.p, c->stream);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     QCSS_CUDA(cudaMemcpyAsync(hist, c->buf_c.p, hb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
     return QCSS_OK;

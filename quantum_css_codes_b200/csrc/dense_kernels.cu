@@ -24,8 +24,6 @@
 //   epilogue  : tcgen05.ld 32 columns at a time, bit 0 of 32 accumulators -> one syndrome word.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "launch.h"
 
 namespace qcss {
@@ -75,7 +73,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, unsigned parity)
 __global__ void __launch_bounds__(kMmaThreads, 1)
 k_syndrome_mma(const uint8_t* __restrict__ hq, int m, int kchunks, int mgroups, const uint32_t* __restrict__ e,
                int n, int64_t e_stride, uint32_t* __restrict__ s, int64_t s_stride, int64_t words,
-               uint32_t tail_mask, int dbg) {
+               uint32_t tail_mask) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t free_bar[kStages];
@@ -286,9 +284,8 @@ cudaError_t launch_syndrome_mma(const uint8_t* hq, int m, int n, const uint32_t*
     if (err != cudaSuccess) return err;
     const int64_t grid = tiles * mgroups;
     if (grid <= 0 || grid > 0x7FFFFFFF) return cudaErrorInvalidValue;
-    const int dbg = getenv("QCSS_DENSE_DBG") ? atoi(getenv("QCSS_DENSE_DBG")) : 0;
     k_syndrome_mma<<<(unsigned)grid, kMmaThreads, smem, stream>>>(hq, m, kchunks, mgroups, e, n, e_stride, s, s_stride,
-                                                                  words, tail_mask, dbg);
+                                                                  words, tail_mask);
     return cudaGetLastError();
 }
 

@@ -202,7 +202,7 @@ cudaError_t launch_named(const EcLaunch& l, cudaStream_t stream) {
     a.e32_z = l.z->lut_e32;
     a.ec = l.ec;
     const size_t lut = small::lut_smem(*l.x, *l.z, !DX::kSliced, !DZ::kSliced, true);
-    const bool gapq_off = getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0;
+    const bool gapq_off = !l.gapq;
     if (l.ec.gap_p && l.ec.gap_q && !gapq_off && lut + EcqShape<DX, DZ>::kSmem <= 200 * 1024)
         return small::launch_one(k_ec_named_q<DX, DZ>, a, l.ec.words, lut + EcqShape<DX, DZ>::kSmem, stream);
     return small::launch_one(k_ec_named<DX, DZ>, a, l.ec.words, lut, stream);

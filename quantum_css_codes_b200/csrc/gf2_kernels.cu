@@ -11,12 +11,19 @@
 //   3. every other row with a 1 in column c gets the pivot row XORed in, word-parallel, starting
 //      at word c/64 (the pivot row is zero left of c).
 // This is the general-shape kernel (any number of rows); matrices with <= 1024 rows take the
-// register-resident blocked kernel in gf2_fast.cu.
+// register-resident blocked kernels in gf2_m4r2.cu / gf2_m4r.cu.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "launch.h"
+#include "options.h"
+#ifdef QCSS_EXPERIMENTS
+#include <cstdlib>
+namespace qcss {
+bool gf2_fast_supported(int m, int n);
+cudaError_t launch_gf2_fast(const uint64_t* in, int batch, int m, int n, uint64_t* out, int32_t* rank, int32_t* pivots,
+                            cudaStream_t stream);
+}
+#endif
 
 namespace qcss {
 
@@ -79,10 +86,13 @@ k_gf2_rref(const uint64_t* __restrict__ in, int batch, int m, int n, uint64_t* _
             // 3. clear column c everywhere else: one warp per row, lanes over words
             for (int row = warp; row < m; row += kWarps) {
                 if (row == lead) continue;
-                if (a[(size_t)row * W + cw] & cbit) {
+                // the predicate word is also lane 0's first XOR target: read it once per warp, before any write
+                const bool hit = __shfl_sync(0xFFFFFFFFu, (int)((a[(size_t)row * W + cw] & cbit) != 0), 0) != 0;
+                if (hit) {
                     for (int w = cw + lane; w < W; w += 32)
                         a[(size_t)row * W + w] ^= a[(size_t)lead * W + w];
                 }
+                __syncwarp();
             }
             if (threadIdx.x == 0 && piv_out != nullptr) piv_out[(size_t)b * npiv + lead] = c;
             ++lead;
@@ -105,15 +115,17 @@ k_gf2_rref(const uint64_t* __restrict__ in, int batch, int m, int n, uint64_t* _
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out, int32_t* rank,
                             int32_t* pivots, cudaStream_t stream) {
     if (batch <= 0 || m <= 0 || n <= 0) return cudaSuccess;
-    if (getenv("QCSS_GF2_SIMPLE") == nullptr) {
-        // QCSS_GF2_V1 / QCSS_GF2_V2 select the earlier generations (kept for A/B measurements and tests)
-        const bool v1 = getenv("QCSS_GF2_V1") != nullptr, v2 = getenv("QCSS_GF2_V2") != nullptr;
-        const bool v3 = getenv("QCSS_GF2_V3") != nullptr && m <= 1024;      // force the third generation
-        if ((gf2_m4r2_supported(m, n) || v3) && !v1 && !v2)
+    // option "gf2_kernel" (options.h) forces one implementation where its shape limits allow; all of them
+    // return the same canonical RREF, rank and pivots (tests/test_gpu_gf2.py runs every choice)
+#ifdef QCSS_EXPERIMENTS
+    if (getenv("QCSS_GF2_V1") != nullptr && gf2_fast_supported(m, n))       // first generation (tools/experiments)
+        return launch_gf2_fast(in, batch, m, n, out, rank, pivots, stream);
+#endif
+    const int pick = options().gf2_kernel;
+    if (pick != 1) {
+        if ((pick == 3 && m <= 1024) || (pick == 0 && gf2_m4r2_supported(m, n)))
             return launch_gf2_m4r2(in, batch, m, n, out, rank, pivots, stream);
-        if (gf2_m4r_supported(m, n) && !v1)
-            return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);
-        if (gf2_fast_supported(m, n)) return launch_gf2_fast(in, batch, m, n, out, rank, pivots, stream);
+        if (gf2_m4r_supported(m, n)) return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);
     }
     const int W = (n + 63) >> 6;
     const size_t bytes = (size_t)m * W * sizeof(uint64_t);

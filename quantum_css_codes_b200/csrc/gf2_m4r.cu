@@ -340,7 +340,7 @@ cudaError_t launch_gf2_m4r(const uint64_t* in, int batch, int m, int n, uint64_t
                            int32_t* pivots, cudaStream_t stream) {
     const size_t smem = m4r_smem_bytes(m, n);
     const int mpad = (m + 31) & ~31;
-    const bool lookahead = getenv("QCSS_GF2_NO_LOOKAHEAD") == nullptr;
+    constexpr bool lookahead = true;
     using Kern = void (*)(const uint32_t*, int, int, int, uint32_t*, int32_t*, int32_t*);
     Kern kern = mpad == 1024 ? (lookahead ? k_gf2_m4r<32, true> : k_gf2_m4r<32, false>)
                              : (lookahead ? k_gf2_m4r<0, true> : k_gf2_m4r<0, false>);

@@ -15,6 +15,7 @@ struct SmallLaunch {
     DecodeIO io;
     int named_id;              // index into named::kNamed, or -1 for the generic kernels
     bool sample;               // fused Philox sampler instead of loading error planes
+    bool gapq = true;          // sampler form below p = 1/128 (options.h): two-phase queue or in place
 };
 cudaError_t launch_small(const SmallLaunch& l, cudaStream_t stream);
 int match_named(const GenericSide& x, const uint32_t* rows_x, uint32_t lx, const GenericSide& z,
@@ -28,6 +29,7 @@ struct EcLaunch {
     const GenericSide* z;
     EcParams ec;
     int named_id;
+    bool gapq = true;
 };
 cudaError_t launch_ec_rounds(const EcLaunch& l, cudaStream_t stream);
 
@@ -44,6 +46,7 @@ cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes,
 // tile-major layout: e = [tiles][n][32 words], s = [tiles][m][32 words], tile = 1024 shots
 cudaError_t launch_syndrome_tiles(const SparseRows& h, const uint32_t* e_tiles, uint32_t* s_tiles, int64_t words,
                                   uint32_t tail_mask, cudaStream_t stream);
+bool syndrome_tiles_supported(const SparseRows& h);
 
 // fused Philox sampler + sparse syndromes, tile-major outputs (sample_tiles.cu); hx acts on X errors, hz on Z errors
 cudaError_t launch_sample_syndrome_tiles(const SparseRows& hx, const SparseRows& hz, uint32_t* sx, uint32_t* sz,
@@ -61,12 +64,7 @@ cudaError_t launch_syndrome_mma(const uint8_t* hq, int m, int n, const uint32_t*
 // ---- batched GF(2) Gauss-Jordan (gf2_kernels.cu) --------------------------------------------
 cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                             int32_t* rank, int32_t* pivots, cudaStream_t stream);
-// register-resident blocked kernel (gf2_fast.cu), rows <= 1024
-bool gf2_fast_supported(int m, int n);
-cudaError_t launch_gf2_fast(const uint64_t* in, int batch, int m, int n, uint64_t* out,
-                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
-
-// second generation (gf2_m4r.cu): one-warp bit-sliced panel, packed combination bytes; QCSS_GF2_V2=1
+// second generation (gf2_m4r.cu): one-warp bit-sliced panel, packed combination bytes
 bool gf2_m4r_supported(int m, int n);
 cudaError_t launch_gf2_m4r(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                            int32_t* rank, int32_t* pivots, cudaStream_t stream);

@@ -1,0 +1,19 @@
+// Process-wide kernel SELECTION options, set only through qcss_set_option (include/qcss.h).
+//
+// Every option chooses between implementations that produce bit-identical results (the parity
+// tests run both sides of each and compare).  Nothing here is read from the environment: an
+// inherited variable must never change what the library computes or which kernel it runs.
+#pragma once
+
+namespace qcss {
+
+struct Options {
+    int gapq = 1;         // Monte-Carlo below p = 1/128: CTA-wide two-phase gap sampler (1) or in-place form (0)
+    int dense = -1;       // large check matrices: -1 = by size and density, 0 = sparse kernels, 1 = tensor cores
+    int named = 1;        // 1 = use a built-in static descriptor when the code matches one, 0 = generic kernels
+    int gf2_kernel = 0;   // batched RREF: 0 = by shape, 1 = column-by-column, 2 = m4r (one-warp panel), 3 = m4r2
+};
+
+Options& options();
+
+}  // namespace qcss

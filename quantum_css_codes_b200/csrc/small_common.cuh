@@ -379,7 +379,7 @@ cudaError_t launch_generic(const SmallLaunch& l, cudaStream_t stream) {
     const bool lut = (MB != kSlicedM);
     const size_t smem = lut_smem(*l.x, *l.z, lut, lut, false), smem_fast = lut_smem(*l.x, *l.z, lut, lut, true);
     constexpr int SVEC = 1;                          // sampling kernels: one word per thread (see launch_named)
-    if (l.sample && l.io.use_gap && !(getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0)) {
+    if (l.sample && l.io.use_gap && l.gapq) {
         using Shape = GapqShape<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>>;
         return launch_split<Shape::kW>(k_small_generic_gapq<NB, MB>, k_small_generic<NB, MB, SVEC, true, false>, a, l,
                                        smem_fast + Shape::kSmem, smem, stream);
@@ -408,7 +408,7 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
     // thread keeps 4x fewer syndrome accumulators live and 4x fewer unrolled sampler sites (measured on
     // Golay-23 with VEC = 4: the first-error path inlined at 92 sites ran at 4.2e10 shots/s).
     constexpr int SVEC = 1;
-    if (l.sample && l.io.use_gap && !(getenv("QCSS_GAPQ") != nullptr && atoi(getenv("QCSS_GAPQ")) == 0)) {
+    if (l.sample && l.io.use_gap && l.gapq) {
         // Monte-Carlo tallies below p = 1/128: the CTA-wide two-phase gap sampler for the whole words
         using Shape = GapqShape<StaticPolicy<DX>, StaticPolicy<DZ>>;
         return launch_split<Shape::kW>(k_small_named_gapq<DX, DZ>, k_small_named<DX, DZ, SVEC, true, false>, a, l,

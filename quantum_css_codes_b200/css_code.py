@@ -206,7 +206,115 @@ def quil_classical_detect(prog, codeword, errors, outcome, scratch, parity_check
     return prog
 
 
-class CSSCode:
+class _DevicePath:
+    """The GPU hot path over the attributes every reference ``CSSCode`` carries (css_code.py:63-72,
+    124-161): ``n``, ``parity_check_c1/2``, ``_c1/_c2_syndromes``, ``x/z_operator_matrix()``.
+    ``CSSCode`` below inherits it; ``attach(obj)`` puts it next to an EXISTING reference object."""
+
+    _device_code = None
+
+    def _side(self, which):
+        if which == 2:
+            return self.parity_check_c2, self._c2_syndromes
+        if which == 1:
+            return self.parity_check_c1, self._c1_syndromes
+        raise ValueError("which must be 1 (Z errors, C_1) or 2 (X errors, C_2)")
+
+    @property
+    def device(self):
+        """The device-resident code object (created on first use)."""
+        if self._device_code is None:
+            self._device_code = _native.DeviceCode.from_csscode(self)
+        return self._device_code
+
+    def syndrome_histogram(self, errors, which):
+        """Counts of every syndrome key over a batch: ``hist[vec_to_int(H.e mod 2)]`` (uint64[2^m]),
+        computed on the device (``qcss_syndrome_hist``).  The keys are those of ``_c1/_c2_syndromes``."""
+        errors = np.asarray(errors)
+        return self.device.syndrome_hist_planes(_planes.pack_planes(errors), errors.shape[0], which)
+
+    def specialize(self):
+        """Compile and attach decode kernels specialised for this code (``specialize.py``): the static
+        family that runs Steane / QRM-15 / Golay-23 at the HBM roofline, for any code with n <= 32 and
+        m <= 16.  One nvcc run per distinct code, cached on disk.  Returns the kernel family name."""
+        from . import specialize as _spec
+        return _spec.specialize(self.device)
+
+    def syndromes(self, errors, which):
+        """Batched ``np.mod(np.matmul(parity_check, e), 2)`` (css_code.py:728) for a
+        (shots, n) 0/1 array; returns (shots, m) uint8."""
+        errors = np.asarray(errors)
+        shots = errors.shape[0]
+        h, _ = self._side(which)
+        s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
+        return _planes.unpack_planes(s_planes, shots)[:, :h.shape[0]]
+
+    def decode(self, errors, which):
+        """Lookup-decode a (shots, n) batch of one Pauli type with the semantics of
+        quil_classical_correct (css_code.py:649-685): correction = table.get(key, 0).
+        Returns dict(correction (shots, n), flip (shots,), miss (shots,), tally)."""
+        errors = np.asarray(errors)
+        shots = errors.shape[0]
+        corr, flip, miss, tally = self.device.decode_planes(_planes.pack_planes(errors), shots, which)
+        return dict(correction=_planes.unpack_planes(corr, shots),
+                    flip=_planes.unpack_plane(flip, shots),
+                    miss=_planes.unpack_plane(miss, shots), tally=tally)
+
+    def decode_xz(self, x_errors, z_errors):
+        """Tallies (shots, fail_x, fail_z, fail_any, miss_x, miss_z) for a shared batch."""
+        x_errors, z_errors = np.asarray(x_errors), np.asarray(z_errors)
+        shots = x_errors.shape[0]
+        return self.device.decode_xz_planes(_planes.pack_planes(x_errors),
+                                            _planes.pack_planes(z_errors), shots)
+
+    def monte_carlo(self, p, shots, seed=0, first_shot=0):
+        """Depolarising-noise Monte Carlo fully on the device (sampler fused into the decode
+        kernel); returns the tally dict."""
+        return self.device.mc_run(p, shots, seed, first_shot)
+
+    def error_correct_monte_carlo(self, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0):
+        """Pauli-frame Monte Carlo of ``rounds`` repetitions of the Steane error-correction gadget that
+        ``error_correct`` emits in the reference (css_code.py:436-470): each round the data block
+        suffers depolarising(p_data), a |+>_L and a |0>_L ancilla with depolarising(p_ancilla) extract
+        the X and Z syndromes through transversal CNOTs (with their back-action on the data), and the
+        Pauli frames are updated as ``quil_classical_correct`` does with ``_c2_syndromes`` /
+        ``_c1_syndromes``; the residual after the last round is decoded ideally.  Entirely on the
+        device (``qcss_ec_run``: sampler, syndromes, lookups and frames in registers); returns the tally
+        dict of ``monte_carlo``.  ``rounds=1, p_ancilla=0`` is ``monte_carlo(p_data)`` bit for bit.
+        Model and Philox stream layout: ``csrc/ec_rounds.cuh``."""
+        return self.device.ec_run(p_data, p_ancilla, rounds, shots, seed, first_shot)
+
+    def sample_errors(self, p, shots, seed=0, first_shot=0):
+        """The error batch ``monte_carlo`` would draw, as ((shots, n), (shots, n)) uint8."""
+        ex, ez = self.device.mc_sample(p, shots, seed, first_shot)
+        return _planes.unpack_planes(ex, shots), _planes.unpack_planes(ez, shots)
+
+
+class AttachedCode(_DevicePath):
+    """The device path bound to an existing code object -- typically a ``CSSCode`` built by the UNMODIFIED
+    reference (``ftqc.rewrite_program`` users keep that object for gate emission, ftqc.py:42).  Anything
+    with the reference's attributes works: ``n``, ``parity_check_c1``, ``parity_check_c2``,
+    ``_c1_syndromes``, ``_c2_syndromes``, ``x_operator_matrix()``, ``z_operator_matrix()``
+    (css_code.py:63-72, 124-161).  Other attribute reads fall through to the wrapped object, so the
+    wrapper can stand in for it."""
+
+    def __init__(self, code):
+        for name in ("n", "parity_check_c1", "parity_check_c2", "_c1_syndromes", "_c2_syndromes",
+                     "x_operator_matrix", "z_operator_matrix"):
+            if not hasattr(code, name):
+                raise TypeError(f"cannot attach: object has no attribute {name!r} (css_code.py:63-72, 124-161)")
+        self._code = code
+
+    def __getattr__(self, name):
+        return getattr(self._code, name)
+
+
+def attach(code):
+    """``attach(reference_css_code).monte_carlo(...)``: bind the CUDA hot path to an existing object."""
+    return AttachedCode(code)
+
+
+class CSSCode(_DevicePath):
     """Calderbank-Shor-Steane code built from two classical parity checks (css_code.py:19-75).
 
     The constructor performs the reference's host-side numerics (validation, standard form,
@@ -290,13 +398,18 @@ class CSSCode:
         # css_code.py:182-201.  Evaluated on first use rather than in __init__ because
         # codes_equal runs its two RREFs on the GPU; the value is the reference's.
         if self._transversal_cache is None:
-            gates = ['I', 'CNOT']
-            if codes_equal(self.parity_check_c1, self.parity_check_c2):
-                gates += ['H', 'CZ']
-                if is_doubly_even(self.parity_check_c1):
-                    gates.append('S')
-            self._transversal_cache = gates
+            self._transversal_cache = self._determine_transversal_gates(self.parity_check_c1, self.parity_check_c2)
         return self._transversal_cache
+
+    def _determine_transversal_gates(self, parity_check_c1, parity_check_c2):
+        """css_code.py:182-201: I and CNOT always; H and CZ when C_1 = C_2; S when that code is doubly even.
+        A frozenset, as in the reference."""
+        gates = ['I', 'CNOT']
+        if codes_equal(parity_check_c1, parity_check_c2):
+            gates += ['H', 'CZ']
+            if is_doubly_even(parity_check_c1):
+                gates.append('S')
+        return frozenset(gates)
 
     def is_transversal(self, gate_name: str) -> bool:
         """Whether the gate is fault tolerant when applied qubit by qubit (css_code.py:174-180)."""
@@ -329,86 +442,6 @@ class CSSCode:
     @property
     def error_correct_scratch_size(self) -> int:
         return self.encode_scratch_size                           # css_code.py:539-540
-
-    # ---- GPU hot path -----------------------------------------------------------------------
-    def _side(self, which):
-        if which == 2:
-            return self.parity_check_c2, self._c2_syndromes
-        if which == 1:
-            return self.parity_check_c1, self._c1_syndromes
-        raise ValueError("which must be 1 (Z errors, C_1) or 2 (X errors, C_2)")
-
-    @property
-    def device(self):
-        """The device-resident code object (created on first use)."""
-        if self._device_code is None:
-            self._device_code = _native.DeviceCode(
-                self.n, self.parity_check_c1, self.parity_check_c2,
-                self.x_operator_matrix()[0], self.z_operator_matrix()[0],
-                self._c1_syndromes, self._c2_syndromes)
-        return self._device_code
-
-    def syndrome_histogram(self, errors, which):
-        """Counts of every syndrome key over a batch: ``hist[vec_to_int(H.e mod 2)]`` (uint64[2^m]),
-        computed on the device (``qcss_syndrome_hist``).  The keys are those of ``_c1/_c2_syndromes``."""
-        errors = np.asarray(errors)
-        return self.device.syndrome_hist_planes(_planes.pack_planes(errors), errors.shape[0], which)
-
-    def specialize(self):
-        """Compile and attach decode kernels specialised for this code (``specialize.py``): the static
-        family that runs Steane / QRM-15 / Golay-23 at the HBM roofline, for any code with n <= 32 and
-        m <= 16.  One nvcc run per distinct code, cached on disk.  Returns the kernel family name."""
-        from . import specialize as _spec
-        return _spec.specialize(self.device)
-
-    def syndromes(self, errors, which):
-        """Batched ``np.mod(np.matmul(parity_check, e), 2)`` (css_code.py:728) for a
-        (shots, n) 0/1 array; returns (shots, m) uint8."""
-        errors = np.asarray(errors)
-        shots = errors.shape[0]
-        h, _ = self._side(which)
-        s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
-        return _planes.unpack_planes(s_planes, shots)[:, :h.shape[0]]
-
-    def decode(self, errors, which):
-        """Lookup-decode a (shots, n) batch of one Pauli type with the semantics of
-        quil_classical_correct (css_code.py:649-685): correction = table.get(key, 0).
-        Returns dict(correction (shots, n), flip (shots,), miss (shots,), tally)."""
-        errors = np.asarray(errors)
-        shots = errors.shape[0]
-        corr, flip, miss, tally = self.device.decode_planes(_planes.pack_planes(errors), shots, which)
-        return dict(correction=_planes.unpack_planes(corr, shots),
-                    flip=_planes.unpack_plane(flip, shots),
-                    miss=_planes.unpack_plane(miss, shots), tally=tally)
-
-    def decode_xz(self, x_errors, z_errors):
-        """Tallies (shots, fail_x, fail_z, fail_any, miss_x, miss_z) for a shared batch."""
-        x_errors, z_errors = np.asarray(x_errors), np.asarray(z_errors)
-        shots = x_errors.shape[0]
-        return self.device.decode_xz_planes(_planes.pack_planes(x_errors),
-                                            _planes.pack_planes(z_errors), shots)
-
-    def monte_carlo(self, p, shots, seed=0, first_shot=0):
-        """Depolarising-noise Monte Carlo fully on the device (sampler fused into the decode
-        kernel); returns the tally dict."""
-        return self.device.mc_run(p, shots, seed, first_shot)
-
-    def error_correct_monte_carlo(self, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0):
-        """Pauli-frame Monte Carlo of ``rounds`` repetitions of the Steane error-correction gadget that
-        ``error_correct`` emits in the reference (css_code.py:436-470): each round the data block
-        suffers depolarising(p_data), a |+>_L and a |0>_L ancilla with depolarising(p_ancilla) extract
-        the X and Z syndromes through transversal CNOTs (with their back-action on the data), and the
-        Pauli frames are updated as ``quil_classical_correct`` does with ``_c2_syndromes`` /
-        ``_c1_syndromes``; the residual after the last round is decoded ideally.  Entirely on the
-        device (``qcss_ec_run``: sampler, syndromes, lookups and frames in registers); returns the tally
-        dict of ``monte_carlo``.  ``rounds=1, p_ancilla=0`` is ``monte_carlo(p_data)`` bit for bit.
-        Model and Philox stream layout: ``csrc/ec_rounds.cuh``."""
-        return self.device.ec_run(p_data, p_ancilla, rounds, shots, seed, first_shot)
-
-    def sample_errors(self, p, shots, seed=0, first_shot=0):
-        """The error batch ``monte_carlo`` would draw, as ((shots, n), (shots, n)) uint8."""
-        ex, ez = self.device.mc_sample(p, shots, seed, first_shot)
-        return _planes.unpack_planes(ex, shots), _planes.unpack_planes(ez, shots)
 
 
 class SyndromeCode:

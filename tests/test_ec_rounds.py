@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 
 import emu
 from oracle import css as ocss, ec_rounds as oec, montecarlo as omc, philox as ophilox
-from quantum_css_codes_b200 import codes, distributed as qdist
+from quantum_css_codes_b200 import codes, distributed as qdist, _native
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMED = {"steane": 0, "qrm15": 1, "golay23": 2}
@@ -187,15 +187,14 @@ def test_gpu_sharding_invariance_and_rates():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["steane", "qrm15", "golay23"])
-def test_gpu_queue_kernel_equals_in_place_kernel(name, monkeypatch):
+def test_gpu_queue_kernel_equals_in_place_kernel(name):
     """Both error rates below 1/128: the CTA-wide two-phase kernel (k_ec_named_q) against the in-place one
-    (QCSS_GAPQ=0) on the same Philox streams, many CTA iterations, ragged tail, offset shard."""
+    (option "gapq" = 0) on the same Philox streams, many CTA iterations, ragged tail, offset shard."""
     dev = device_code(name)
     runs = [((1e-3, 1e-3, 10, 30_000_017), {}), ((5e-3, 2e-3, 3, 10_000_000), {}),
             ((1e-4, 7e-3, 7, 3_000_001), dict(first_shot=128 * 999))]
-    monkeypatch.setenv("QCSS_GAPQ", "0")
-    want = [dev.error_correct_monte_carlo(*args, seed=0xEC, **kw) for args, kw in runs]
-    monkeypatch.delenv("QCSS_GAPQ")
+    with _native.option("gapq", 0):
+        want = [dev.error_correct_monte_carlo(*args, seed=0xEC, **kw) for args, kw in runs]
     got = [dev.error_correct_monte_carlo(*args, seed=0xEC, **kw) for args, kw in runs]
     assert got == want
     assert want[0]["fail_any"] > 0

@@ -7,7 +7,7 @@ import pytest
 import bin_matrix
 import css_code
 from oracle import gf2 as ogf2
-from quantum_css_codes_b200 import codes
+from quantum_css_codes_b200 import codes, _native
 
 pytestmark = pytest.mark.gpu
 
@@ -68,12 +68,16 @@ def test_rref_structured(m, n):
     assert rank[2] <= 7 and rank[3] == 0
 
 
-@pytest.mark.parametrize("knob", ["QCSS_GF2_V1", "QCSS_GF2_V2", "QCSS_GF2_V3", "QCSS_GF2_SIMPLE"])
-def test_rref_every_kernel_generation(knob, monkeypatch):
-    """The dispatcher picks a kernel by shape; the knobs force each generation (gf2_fast, gf2_m4r,
-    gf2_m4r2, the general kernel) over small, ragged, rank-deficient and full-size shapes."""
-    monkeypatch.setenv(knob, "1")
-    rng = np.random.default_rng(len(knob))
+@pytest.mark.parametrize("knob", [1, 2, 3])
+def test_rref_every_kernel_generation(knob):
+    """The dispatcher picks a kernel by shape; option "gf2_kernel" forces each implementation (1 the general
+    column-by-column kernel, 2 gf2_m4r, 3 gf2_m4r2) over small, ragged, rank-deficient and full-size shapes."""
+    with _native.option("gf2_kernel", knob):
+        _rref_every_shape(knob)
+
+
+def _rref_every_shape(knob):
+    rng = np.random.default_rng(11 + knob)
     for m, n in [(1, 1), (7, 70), (33, 31), (64, 200), (130, 1100), (300, 100), (640, 640), (1024, 1100)]:
         mats = rng.integers(0, 2, size=(3, m, n), dtype=np.int64)
         if m > 4:

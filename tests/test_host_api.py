@@ -130,6 +130,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.qcss_version() >= 100
 
 
+def test_library_reads_no_environment_knobs(monkeypatch):
+    """Kernel selection goes through qcss_set_option only: the shipped library contains none of the round-1
+    environment-variable names (nor any other QCSS_* string), so an inherited variable cannot change which
+    kernel runs or what it computes; the superseded kernels are not in the binary either."""
+    blob = open(_native.LIB_PATH, "rb").read()
+    for name in (b"QCSS_RING_DBG", b"QCSS_TMA_DBG", b"QCSS_DENSE_DBG", b"QCSS_TILES", b"QCSS_RING", b"QCSS_GAPQ",
+                 b"QCSS_DENSE", b"QCSS_SAMPLER_BITS", b"QCSS_DISABLE_NAMED", b"QCSS_GF2_", b"QCSS_TILED_"):
+        assert name not in blob, name
+    for kernel in (b"k_syndrome_tma", b"k_syndrome_wide", b"k_syndrome_l1", b"k_gf2_fast"):
+        assert kernel not in blob, kernel
+    # setting the old variables changes nothing the library can observe: options keep their defaults
+    for name in ("QCSS_GAPQ", "QCSS_DENSE", "QCSS_RING_DBG", "QCSS_GF2_SIMPLE"):
+        monkeypatch.setenv(name, "1")
+    lib = _native.load()
+    import ctypes
+    for key, default in (("gapq", 1), ("dense", -1), ("named", 1), ("gf2_kernel", 0)):
+        val = ctypes.c_int(99)
+        assert lib.qcss_get_option(key.encode(), ctypes.byref(val)) == 0 and val.value == default
+    with _native.option("gf2_kernel", 2):
+        assert lib.qcss_get_option(b"gf2_kernel", ctypes.byref(val)) == 0 and val.value == 2
+    assert lib.qcss_get_option(b"gf2_kernel", ctypes.byref(val)) == 0 and val.value == 0
+    with pytest.raises(ValueError):
+        _native.set_option("gapq", 7)
+    with pytest.raises(ValueError):
+        _native.set_option("no_such_option", 1)
+
+
 def test_no_cpu_fallback_without_gpu():
     """Without a device every numeric entry point fails loudly instead of computing on the host."""
     from conftest import has_cuda
@@ -193,3 +220,60 @@ def test_tile_major_pack_helpers_round_trip():
     one = np.zeros((1030, 2), dtype=np.uint8)
     one[1029, 1] = 1                                           # shot 1029 = tile 1, bit 5 of word 0 of plane 1
     assert planes.pack_tiles(one)[1, 1, 0] == np.uint64(1 << 5)
+
+
+class _ReferenceShapedCode:
+    """Duck-typed stand-in for a CSSCode built by the unmodified reference: exactly the attributes the
+    reference object has on this path (css_code.py:63-72, 124-161), filled from the oracle restatement."""
+
+    def __init__(self, name):
+        from oracle import css as ocss
+        ref = ocss.build_css(*[np.array(h) for h in getattr(codes, name)()])
+        self._n, self._k, self._t = ref.n, ref.k, ref.t
+        self.r_1, self.r_2 = ref.r_1, ref.r_2
+        self.parity_check_c1, self.parity_check_c2 = ref.parity_check_c1, ref.parity_check_c2
+        self._c1_syndromes, self._c2_syndromes = ref.c1_syndromes, ref.c2_syndromes
+        self._transversal_gates = frozenset(ref.transversal_gates)
+        self._lx, self._lz = ref.lx, ref.lz
+        self.gate_emitter_marker = "stays with the reference object"
+
+    n = property(lambda self: self._n)
+    k = property(lambda self: self._k)
+    t = property(lambda self: self._t)
+
+    def x_operator_matrix(self):
+        return self._lx
+
+    def z_operator_matrix(self):
+        return self._lz
+
+
+def test_attach_binds_device_path_to_a_reference_shaped_object():
+    """``attach(obj)`` wraps an existing code object (a reference CSSCode, or anything
+    with its attributes) without recomputing tables; missing attributes are reported by name; other
+    attribute reads fall through to the wrapped object."""
+    from quantum_css_codes_b200 import AttachedCode, attach
+    obj = _ReferenceShapedCode("steane")
+    bound = attach(obj)
+    assert isinstance(bound, AttachedCode)
+    assert bound.n == 7 and bound.t == 1 and bound.gate_emitter_marker.startswith("stays")
+    assert bound.parity_check_c1 is obj.parity_check_c1 and bound._side(2)[1] is obj._c2_syndromes
+    with pytest.raises(TypeError, match="_c1_syndromes"):
+        class Partial:
+            n = 7
+            parity_check_c1 = parity_check_c2 = np.eye(3, 7, dtype=int)
+        attach(Partial())
+    from conftest import has_cuda
+    if not has_cuda():
+        with pytest.raises(_native.NativeLibraryError):        # reaches qcss_code_create: loud, no fallback
+            bound.monte_carlo(1e-3, 1000)
+
+
+def test_transversal_gates_is_a_frozenset_like_the_reference():
+    """css_code.py:72, 201: ``_transversal_gates`` is a frozenset built by ``_determine_transversal_gates``."""
+    steane = CSSCode(*[np.array(h) for h in codes.steane()])
+    assert hasattr(steane, "_determine_transversal_gates")
+    from conftest import has_cuda
+    if has_cuda():
+        assert steane._transversal_gates == frozenset(['I', 'CNOT', 'H', 'CZ', 'S'])
+        assert isinstance(steane._transversal_gates, frozenset)

@@ -124,7 +124,7 @@ def probe_dense(shots, m=1024, n=2048):
     s = torch.empty((m, stride), dtype=torch.int64, device="cuda")
     ref = None
     for force in ("1", "0"):
-        os.environ["QCSS_DENSE"] = force
+        _native.set_option("dense", int(force))
         dev = SyndromeCode(h, h[:8]).device
         n_shots = shots if force == "1" else min(shots, 1 << 18)
         med, best = timed(lambda: dev.syndrome_dev(1, e.data_ptr(), stride, n_shots, s.data_ptr(), stride, stream),
@@ -138,7 +138,7 @@ def probe_dense(shots, m=1024, n=2048):
         emit(probe="dense_syndrome", kernel=dev.kernel_name(), m=m, n=n, shots=n_shots, ms=med, ms_best=best,
              shots_per_s=n_shots / (med / 1e3), int_ops_per_s=2.0 * m * n * n_shots / (med / 1e3),
              matches_other_path=same, checksum=chk)
-    del os.environ["QCSS_DENSE"]
+    _native.set_option("dense", -1)
 
 
 def probe_gf2(batch, m=1024, n=2048):
@@ -185,7 +185,7 @@ def main():
     args = ap.parse_args()
     torch.cuda.set_device(0)
     emit(probe="env", gpu=torch.cuda.get_device_name(0), hbm_peak_gbs=HBM_PEAK,
-         disable_named=bool(os.environ.get("QCSS_DISABLE_NAMED")))
+         disable_named=bool(os.environ.get("PROBE_DISABLE_NAMED")))
     big = 1 << 28 if args.quick else 1_000_000_000
     only = set(args.only.split(",")) if args.only else None
     if only is None or "decode" in only:

@@ -2,8 +2,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["QCSS_DENSE"] = "1"
-from quantum_css_codes_b200 import SyndromeCode
+from quantum_css_codes_b200 import SyndromeCode, _native
+_native.set_option("dense", 1)
 shots = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
 m, n = 1024, 2048
 h = np.random.default_rng(5).integers(0, 2, size=(m, n))

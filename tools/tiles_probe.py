@@ -38,7 +38,7 @@ def timed(fn, reps=5):
 for which in (1, 2):
     ms = timed(lambda: dev.syndrome_tiles_dev(which, e.data_ptr(), shots, s.data_ptr(), stream))
     print(json.dumps(dict(probe="hgp_tiles", which=which, shots=shots, ms=ms, shots_per_s=shots / (ms * 1e-3),
-                          gbs=bytes_per_shot * shots / (ms * 1e-3) / 1e9, knob=os.environ.get("QCSS_TILES", ""))), flush=True)
+                          gbs=bytes_per_shot * shots / (ms * 1e-3) / 1e9)), flush=True)
 # plane-major on the same bits: e viewed as planes needs a transpose; time it on fresh random planes instead
 stride = tiles * 16
 ep = e.view(-1)[: n * stride].view(n, stride)

@@ -6,15 +6,25 @@ Workload (BASELINE.json configs[1]): Steane [[7,1,3]], depolarising p = 1e-3, 1e
 X and Z error planes bit-packed and RESIDENT in HBM (2 x 7 planes x 1.25 GB = 17.5 GB per GPU;
 far larger than the 126 MB L2, so no flush is needed between steps).  One step = one pass of the
 fused syndrome + decode + logical-check + tally kernel over all resident shots, then (N > 1) one
-NCCL allreduce of the tallies.
+NCCL allreduce of the tallies at the end of the job.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--shots S] [--impl reference]
 
-Prints ONE JSON line (rank 0).  `value` = whole-job shots/s from HBM-resident inputs; `e2e` = the
-same metric through the host-buffer C-ABI call qcss_decode_xz (pinned host planes -> H2D -> kernel
--> D2H tallies inside the timed region); `roofline` = algorithmic bytes (2n/8 per shot) over the
-kernel's event-timed duration against the measured HBM copy bandwidth; `cpu_baseline` = the numpy
-oracle (port of the reference's arithmetic) timed on this host.
+Prints ONE JSON line (rank 0):
+  value          whole-job shots/s from HBM-resident inputs (weak scaling: 1e10 shots per GPU)
+  e2e            the same metric through the host-buffer C-ABI call qcss_decode_xz (pinned host planes -> H2D ->
+                 kernel -> D2H tallies inside the timed region), same shots per GPU at every N; next to it the
+                 sparse host format (qcss_decode_xz_sparse) and the reference's own (shots, n) byte format
+                 (qcss_decode_xz_shots), when the library has them
+  roofline       algorithmic bytes (2n/8 per shot) over the kernel's event-timed duration against the measured
+                 HBM copy bandwidth
+  cpu_baseline   the numpy oracle (port of the reference's arithmetic) on one host core; cpu_reference = the
+                 UNMODIFIED reference functions (baseline/_ref/bin_matrix.py) in the per-shot loop and on C5 RREF
+  strong_scaling the fixed 1e10-shot job split over the N GPUs, one allreduce per job
+  nrank_parity   (N > 1) NCCL-reduced tallies / histograms equal to rank 0's single-GPU run of the same job;
+                 the run FAILS (exit 1) when they differ
+  other_configs  every other BASELINE config at this N (QRM-15, Golay-23, HGP-1600, fused sampler, dense H on
+                 tensor cores, C5 GF(2) RREF), each with its roofline object
 """
 
 import argparse
@@ -32,10 +42,18 @@ sys.path.insert(0, REPO)
 P_ERR = 1e-3
 SEED = 0x5EED
 CPU_SAMPLE_SHOTS = 1 << 22        # per worker per step of the CPU baseline
+JOB_SHOTS = 10_000_000_000        # the north-star job (BASELINE.json configs[1])
 # dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per shot, from the committed
 # `ncu --set full` capture of this very command (profiles/r01_steane_bench_ncu_summary.txt:
-# 17.500021 GB read + 3.6 MB written for 1e10 shots).  Algorithmic bytes are 1.75 B/shot.
+# 17.500021 GB read + 3.6 MB written for 1e10 shots).  Algorithmic bytes are 1.75 B/shot.  STATIC: not
+# re-measured per run (ncu cannot run inside a timed bench).
 NCU_TRAFFIC_BYTES_PER_SHOT = {"steane": 1.7503621}
+# INT denominators measured by tools/int_peak.cu on this pool's B200 (profiles/r01_int_peak.jsonl)
+LOP3_PEAK = 1.8471e13             # 32-bit lane-ops/s (LOP3 / IMAD / SHF / PRMT pipes)
+ISSUE_PEAK = 148 * 4 * 32 * 1.965e9   # thread-instructions/s: 4 warp schedulers per SM, one warp-instruction per clock each
+# thread-instructions per sampled (32-shot word, qubit) site, counted by ncu (static, per kernel build):
+# profiles/r01_mc_fused_steane_gapq_ncu_summary.txt (k_small_named_gapq) and r01_hgp_fused_sampler_v2 (sample_tiles)
+INSTR_PER_SITE_WORD = {"gapq": 56.0}
 
 
 def parse_args():
@@ -49,12 +67,13 @@ def parse_args():
     ap.add_argument("--code", default="steane", choices=["steane", "qrm15", "golay23"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-others", action="store_true", help="skip the informational C3/C4/C5 timings")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--others-scale", type=float, default=1.0, help="shrink the other configs (quick checks only)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's batched numpy restatement of the reference arithmetic
+# CPU baselines
 # ------------------------------------------------------------------------------------------------
 
 def _cpu_worker(task):
@@ -85,8 +104,90 @@ def cpu_baseline(code_name, cores, steps=1, shots=CPU_SAMPLE_SHOTS):
     return total / busy, total
 
 
+def _reference_bin_matrix():
+    """The UNMODIFIED reference bin_matrix.py: baseline/_ref/ (copied there by __graft_entry__.build() in the
+    build container; git-ignored, travels to the GPU box), else /root/reference, else None."""
+    import importlib.util
+    for root in (os.path.join(REPO, "baseline", "_ref"), "/root/reference"):
+        path = os.path.join(root, "bin_matrix.py")
+        if os.path.exists(path):
+            spec = importlib.util.spec_from_file_location("reference_bin_matrix", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod, path
+    return None, None
+
+
+def _literal_worker(task):
+    """per shot np.mod(np.matmul(H, e), 2) -> bin_matrix.vec_to_int -> table.get ->
+    (e + c) % 2 -> np.mod(np.matmul(L, r), 2), X and Z (css_code.py:728, bin_matrix.py:36-43, css_code.py:641-685)."""
+    code_name, seed, shots = task
+    from oracle import css as ocss, montecarlo as omc
+    from quantum_css_codes_b200 import codes
+    ref, _ = _reference_bin_matrix()
+    if ref is None:
+        from oracle import gf2 as ref                       # literal restatement ("port")
+    code = ocss.build_css(*[np.array(h) for h in getattr(codes, code_name)()])
+    rng = np.random.default_rng(seed)
+    ex, ez = omc.sample_depolarizing(rng, shots, code.n, P_ERR)
+    ex, ez = ex.astype(np.int64), ez.astype(np.int64)
+    t0 = time.perf_counter()
+    fails = 0
+    for which, errs in ((2, ex), (1, ez)):
+        h, table, lop = ocss.pauli_side(code, which)
+        for e in errs:
+            s = np.mod(np.matmul(h, e), 2)
+            c = table.get(ref.vec_to_int(s))
+            r = e if c is None else (e + c) % 2
+            fails += int(np.mod(np.matmul(lop, r), 2)[0])
+    dt = time.perf_counter() - t0
+    tally = omc.tally_xz(code, ex, ez)
+    assert fails == tally["fail_x"] + tally["fail_z"]
+    return dt
+
+
+def _rref_worker(task):
+    """bin_matrix.reduced_row_echelon_form (bin_matrix.py:8-34) on one C5 matrix."""
+    index = task
+    from oracle import gf2 as ogf2
+    from quantum_css_codes_b200 import codes
+    ref, _ = _reference_bin_matrix()
+    rref = ref.reduced_row_echelon_form if ref is not None else ogf2.rref_literal
+    mat = ogf2.unpack_rows(codes.random_matrices_c5(1, offset=index)[0], 2048).astype(np.int64)
+    t0 = time.perf_counter()
+    out = rref(mat)
+    dt = time.perf_counter() - t0
+    return dt, int(out.sum())
+
+
+def cpu_reference(code_name, cores, literal_shots=200_000, matrices=None):
+    """The reference's own functions on `cores` host cores: per-shot Monte-Carlo loop and C5 RREF."""
+    ref, path = _reference_bin_matrix()
+    kind = "reference" if ref is not None else "port"
+    matrices = matrices if matrices is not None else max(cores, 4 if cores == 1 else cores)
+    if cores == 1:
+        lit = [_literal_worker((code_name, 7, literal_shots))]
+        rr = [_rref_worker(i) for i in range(matrices)]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            lit = pool.map(_literal_worker, [(code_name, 7 + i, literal_shots) for i in range(cores)], chunksize=1)
+            rr = pool.map(_rref_worker, list(range(matrices)), chunksize=1)
+    lit_rate = literal_shots * len(lit) / (sum(lit) / cores)
+    rr_s = float(np.mean([t for t, _ in rr]))
+    return {"kind": kind, "source": path or "oracle/gf2.py literal restatement (reference checkout absent)",
+            "cores": cores, "host_cpus": os.cpu_count(),
+            "mc_literal": {"value": lit_rate, "unit": "shots/s",
+                           "sample": f"{literal_shots * len(lit)} shots, per-shot loop over the reference's primitives, X and Z"},
+            "rref_c5": {"seconds_per_matrix": rr_s, "matrices_per_s": cores / rr_s, "matrices": len(rr),
+                        "extrapolated_4096_matrices_s": 4096 * rr_s / cores,
+                        "sample": "default_rng(5) 1024 x 2048 matrices through bin_matrix.reduced_row_echelon_form"}}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU arithmetic (oracle port, numpy) on all host cores."""
+    """--impl reference: the reference's CPU arithmetic on all host cores.  `value` is the batched-numpy port
+    (oracle.montecarlo.tally_xz: the reference's arithmetic vectorised, 40-130x faster than its own per-shot
+    loop, i.e. the conservative comparison); `reference_literal` is the unmodified reference beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -99,6 +200,11 @@ def run_reference(args):
         times.append(total / rate)
     ms = 1e3 * float(np.mean(times))
     value = shots_per_step / (ms / 1e3)
+    literal = None
+    try:
+        literal = cpu_reference(args.code, cores, literal_shots=100_000, matrices=cores)
+    except Exception as exc:                                        # informational
+        literal = {"error": f"{type(exc).__name__}: {exc}"}
     line = {
         "impl": "reference", "metric": "decoded error shots/sec", "value": value, "unit": "shots/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -108,6 +214,7 @@ def run_reference(args):
                    "shots_per_step": shots_per_step, "note": "bounded sample of the 1e10-shot workload"},
         "cpu_baseline": {"value": value, "unit": "shots/s", "cores": cores, "kind": "port",
                          "sample": f"{shots_per_step} shots/step, numpy batched oracle, {cores} processes"},
+        "reference_literal": literal,
         "e2e": {"value": value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -161,6 +268,46 @@ class ClockSampler(threading.Thread):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 
+class Ctx:
+    """What every measurement needs: torch, the process group, this rank's stream and the launch counter."""
+
+    def __init__(self, torch, dist, rank, world, local_rank):
+        self.torch, self.dist, self.rank, self.world, self.local_rank = torch, dist, rank, world, local_rank
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.launches = 0
+
+    def rand_words(self, *shape):
+        """Uniform random int64 words (all 64 bits random: two int32 draws per word)."""
+        t = self.torch.randint(-2**31, 2**31, (*shape[:-1], shape[-1] * 2), dtype=self.torch.int32, device="cuda")
+        return t.view(self.torch.int64)
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, iters=3):
+        """Best of `iters` event-timed calls on this rank after one warm-up, ranks released together by a
+        barrier, then the MAX over ranks (the job is done when the slowest shard is)."""
+        torch = self.torch
+        fn()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        best = None
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            best = ms if best is None else min(best, ms)
+        return self.max_over_ranks(best)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -180,6 +327,7 @@ def run_b200(args):
     _native.check(lib.qcss_set_device(local_rank))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Ctx(torch, dist, rank, world, local_rank)
 
     code = CSSCode(*[np.array(h) for h in getattr(codes, args.code)()])
     dev = code.device
@@ -187,11 +335,10 @@ def run_b200(args):
     shots = int(args.shots)
     shots -= shots % 128
     stride = ((shots + 127) // 128) * 2                     # uint64 words per plane
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = ctx.stream
 
     ex = torch.empty((n, stride), dtype=torch.int64, device="cuda")
     ez = torch.empty((n, stride), dtype=torch.int64, device="cuda")
-    tally = torch.zeros(6, dtype=torch.int64, device="cuda")
     # synthetic resident input: the library's own Philox depolarising sampler, distinct shots per rank
     dev.mc_sample_dev(P_ERR, shots, SEED, rank * shots, ex.data_ptr(), ez.data_ptr(), stride, stream)
     torch.cuda.synchronize()
@@ -237,42 +384,53 @@ def run_b200(args):
         dist.barrier()
     sampler.stop_flag = True
     sampler.join()
+    ctx.launches += args.steps
     tally = tallies[args.steps - 1]
-    elapsed_ms = start.elapsed_time(stop)
+    elapsed_ms = ctx.max_over_ranks(start.elapsed_time(stop))
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(kstart, kstop)]))
     result = tally.cpu().numpy().astype(np.int64)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * shots / (ms_per_step / 1e3)
 
-    # ---- end-to-end through the host-buffer C ABI (pinned planes -> H2D -> kernel -> D2H) ----
+    # ---- N-rank parity: the reduced tallies must be those of ONE GPU running the whole job -----------
+    parity = None
+    if world > 1:
+        parity = nrank_parity(ctx, dev, result, shots)
+
+    # ---- strong scaling: the fixed north-star job (1e10 shots) split over the N GPUs ---------------
+    strong = strong_scaling(ctx, dev, ex, ez, stride, shots, n)
+
+    # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(torch, dist, world, dev, ex, ez, n, stride, shots, args, result)
+        e2e = measure_e2e(ctx, dev, ex, ez, n, stride, shots, args, rank * shots)
     del ex, ez
     torch.cuda.empty_cache()
 
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    others = None
+    if not args.no_others:
+        others = measure_other_configs(ctx, peak, args.others_scale)
+
+    ok = parity is None or parity["ok"]
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         bytes_per_shot = 2 * n / 8.0
         achieved = bytes_per_shot * shots / (kernel_ms / 1e3) / 1e9
-        others = None
-        if world == 1 and not args.no_others:
-            others = measure_other_configs(torch, peak)
-        cpu = None
+        cpu = cpu_ref = None
         if not args.no_cpu and world == 1:
             rate, total = cpu_baseline(args.code, 1, steps=16)      # ~11 s of single-core decode
             cpu = {"value": rate, "unit": "shots/s", "cores": 1, "kind": "port",
                    "sample": f"{total} shots (numpy batched oracle: syndrome+key+table gather+logical check, X and Z)"}
+            try:
+                cpu_ref = cpu_reference(args.code, 1, literal_shots=200_000, matrices=4)
+            except Exception as exc:
+                cpu_ref = {"error": f"{type(exc).__name__}: {exc}"}
         line = {
             "metric": "decoded error shots/sec", "value": value, "unit": "shots/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -288,184 +446,387 @@ def run_b200(args):
                          "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES_PER_SHOT[args.code] * shots
                                      if args.code in NCU_TRAFFIC_BYTES_PER_SHOT else None),
-                         "traffic_source": "profiles/r01_steane_bench_ncu_summary.txt (ncu --set full, bytes/shot x shots)",
+                         "traffic_source": "STATIC: profiles/r01_steane_bench_ncu_summary.txt (ncu --set full of this "
+                                           "command, bytes/shot x shots); not re-measured per run",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_shot": bytes_per_shot, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
+            "cpu_reference": cpu_ref,
             "clocks": sampler.summary(),
             "e2e": e2e,
-            "gpu_launches": args.steps,
+            "gpu_launches": ctx.launches,
+            "gpu_launches_timed_region": args.steps,
             "collective": (f"one nccl all_reduce of the {args.steps} x 6 int64 step tallies, inside the timed region"
                            if world > 1 else None),
             "tally": {k: int(v) for k, v in zip(_native.TALLY_FIELDS[1:], result[1:])},
+            "nrank_parity": parity,
+            "strong_scaling": strong,
             "other_configs": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("N-rank parity FAILED: the reduced tallies differ from the single-GPU run")
 
 
-def measure_other_configs(torch, peak_gbs):
-    """Informational: the other BASELINE configs (C2 fused, C3, C4, C5) timed once each with CUDA events on
-    resident synthetic inputs.  Not the bench metric; failures are reported, never raised."""
+def nrank_parity(ctx, dev, reduced_step_tally, shots):
+    """VERDICT r1 missing #2.  Three checks, each comparing an NCCL-reduced result of the N-rank run with rank 0
+    computing the WHOLE job alone (Philox streams are keyed by the global shot index, so the sums must be equal
+    bit for bit):
+      steane_step   the all-reduced tally of one bench step == qcss_mc_run over all N x shots shots
+      mc_sharded    distributed.monte_carlo_sharded(2^34 shots) == one qcss_mc_run of 2^34 shots
+      golay_hist    distributed.allreduce_histogram of per-rank qcss_syndrome_hist_dev == rank 0's histogram of
+                    every shard."""
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
+    from quantum_css_codes_b200 import CSSCode, codes, _native, distributed as qdist
+    out = {}
+    # 1. the bench step itself
+    whole = torch.zeros(6, dtype=torch.int64, device="cuda")
+    if rank == 0:
+        dev.mc_run_dev(P_ERR, world * shots, SEED, 0, whole.data_ptr(), ctx.stream)
+        ctx.launches += 1
+    torch.cuda.synchronize()
+    want = whole.cpu().numpy()[1:].tolist()
+    got = [int(v) for v in reduced_step_tally[1:]]
+    out["steane_step"] = {"ok": (got == want) if rank == 0 else True, "reduced": got, "single_gpu": want if rank == 0 else None,
+                          "shots": world * shots}
+    # 2. the library's own sharded Monte-Carlo driver
+    total = 1 << 34
+    code = CSSCode(*[np.array(h) for h in codes.steane()])
+    sharded = qdist.monte_carlo_sharded(code, P_ERR, total, seed=SEED + 1)
+    ctx.launches += 1
+    single = code.monte_carlo(P_ERR, total, seed=SEED + 1) if rank == 0 else None
+    out["mc_sharded"] = {"ok": (sharded == single) if rank == 0 else True, "reduced": sharded, "shots": total}
+    # 3. per-syndrome histograms (Golay-23, X errors: 2^11 keys)
+    golay = CSSCode(*[np.array(h) for h in codes.golay23()])
+    gdev = golay.device
+    shard = 1 << 27
+    gstride = ((shard + 127) // 128) * 2
+    gx = torch.empty((golay.n, gstride), dtype=torch.int64, device="cuda")
+    gz = torch.empty((golay.n, gstride), dtype=torch.int64, device="cuda")
+    hist = torch.zeros(1 << gdev.m2, dtype=torch.int64, device="cuda")
+    gdev.mc_sample_dev(0.02, shard, SEED + 2, rank * shard, gx.data_ptr(), gz.data_ptr(), gstride, ctx.stream)
+    gdev.syndrome_hist_dev(2, gx.data_ptr(), gstride, shard, hist.data_ptr(), ctx.stream)
+    ctx.launches += 3
+    torch.cuda.synchronize()
+    reduced = qdist.allreduce_histogram(hist.clone())
+    ok = True
+    if rank == 0:
+        alone = torch.zeros_like(hist)
+        for r in range(world):
+            gdev.mc_sample_dev(0.02, shard, SEED + 2, r * shard, gx.data_ptr(), gz.data_ptr(), gstride, ctx.stream)
+            gdev.syndrome_hist_dev(2, gx.data_ptr(), gstride, shard, alone.data_ptr(), ctx.stream)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(alone, reduced)) and int(reduced.sum().item()) == world * shard
+    out["golay_hist"] = {"ok": ok, "shots": world * shard, "keys": int(hist.numel()),
+                         "nonzero_keys": int((reduced != 0).sum().item())}
+    flag = torch.tensor([int(all(v["ok"] for v in out.values()))], dtype=torch.int64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item())
+    return out
+
+
+def strong_scaling(ctx, dev, ex, ez, stride, shots, n, jobs=20):
+    """The fixed north-star job: JOB_SHOTS shots in total, rank r owns shots [r, r + 1) x JOB_SHOTS / N resident in
+    HBM; one job = one decode kernel per rank + ONE allreduce of the six tallies.  K jobs back to back, event
+    timed, max over ranks.  The reduced tally is checked against the whole job run on one GPU."""
+    torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
+    from quantum_css_codes_b200 import distributed as qdist
+    job = min(JOB_SHOTS, shots * world)
+    first, mine = qdist.shard_range(job, rank, world)
+    if mine > shots:
+        return None
+    dev.mc_sample_dev(P_ERR, mine, SEED + 3, first, ex.data_ptr(), ez.data_ptr(), stride, ctx.stream)
+    tallies = torch.zeros((jobs + 1, 6), dtype=torch.int64, device="cuda")
+
+    def one(i):
+        dev.decode_dev(mine, ctx.stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride, tally=tallies[i].data_ptr())
+        if world > 1:
+            dist.all_reduce(tallies[i])
+
+    one(jobs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(torch.zeros(1, dtype=torch.int64, device="cuda"))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(jobs):
+        one(i)
+    b.record()
+    torch.cuda.synchronize()
+    ctx.launches += jobs + 2
+    ms = ctx.max_over_ranks(a.elapsed_time(b)) / jobs
+    whole = torch.zeros(6, dtype=torch.int64, device="cuda")
+    ok = True
+    if rank == 0:
+        dev.mc_run_dev(P_ERR, job, SEED + 3, 0, whole.data_ptr(), ctx.stream)
+        torch.cuda.synchronize()
+        ok = whole.cpu().numpy()[1:].tolist() == tallies[0].cpu().numpy()[1:].tolist()
+    return {"workload": f"fixed {job}-shot job split over {world} GPU(s), one allreduce of 6 tallies per job",
+            "job_shots": job, "ms_per_job": ms, "value": job / (ms / 1e3), "unit": "shots/s", "jobs_timed": jobs,
+            "matches_single_gpu_tally": bool(ok)}
+
+
+def measure_other_configs(ctx, peak_gbs, scale=1.0):
+    """The other BASELINE configs (C2 fused, C3, C4, C4-dense, C5) at this N: every rank runs its own shard
+    (weak: same per-GPU size; C5 strong: 4096 / N matrices per rank), event-timed best of 3, MAX over ranks;
+    `value` is the whole-job aggregate.  Failures are reported, never raised."""
+    torch, world, rank, stream = ctx.torch, ctx.world, ctx.rank, ctx.stream
     from quantum_css_codes_b200 import CSSCode, SyndromeCode, codes, _native
     lib = _native.load()
-    stream = torch.cuda.current_stream().cuda_stream
     out = {}
-
-    def timed(fn, iters=3):
-        fn()
-        torch.cuda.synchronize()
-        best = None
-        for _ in range(iters):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
-            best = ms if best is None else min(best, ms)
-        return best
 
     def guarded(name, fn):
         try:
             out[name] = fn()
-        except Exception as exc:                                   # informational section only
+        except Exception as exc:
             out[name] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+
+    def hbm(gbs_total):
+        per_gpu = gbs_total / world
+        return {"bound": "hbm", "achieved": per_gpu, "peak": peak_gbs, "unit": "GB/s", "frac": per_gpu / peak_gbs,
+                "traffic": None, "note": "per GPU; algorithmic bytes / event-timed kernel"}
 
     def c2_fused():
         code = CSSCode(*[np.array(h) for h in codes.steane()])
         tally = torch.zeros(6, dtype=torch.int64, device="cuda")
-        shots = 10_000_000_000
-        ms = timed(lambda: code.device.mc_run_dev(P_ERR, shots, SEED, 0, tally.data_ptr(), stream))
-        return {"workload": "steane 1e10 shots, fused Philox sampler + decode + tally (no HBM input)", "ms": ms,
-                "shots_per_s": shots / ms * 1e3, "bound": "int"}
+        shots = int(10_000_000_000 * scale) // 1024 * 1024
+        ms = ctx.timed(lambda: code.device.mc_run_dev(P_ERR, shots, SEED, rank * shots, tally.data_ptr(), stream))
+        ctx.launches += 4
+        rate = world * shots / ms * 1e3
+        sites = rate / 32 * code.n                                   # sampled (32-shot word, qubit) sites per second
+        instr = sites * INSTR_PER_SITE_WORD["gapq"] / world
+        return {"workload": "steane, fused Philox sampler + decode + tally (no HBM input), 1e10 shots per GPU",
+                "ms": ms, "value": rate, "unit": "shots/s", "shots_per_gpu": shots,
+                "roofline": {"bound": "int", "achieved": instr, "peak": ISSUE_PEAK, "unit": "thread-instr/s",
+                             "frac": instr / ISSUE_PEAK, "traffic": None,
+                             "model": "56 thread-instructions per sampled site-word (STATIC, ncu: "
+                                      "profiles/r01_mc_fused_steane_gapq_ncu_summary.txt) x site-words/s per GPU; "
+                                      "peak = 148 SMs x 4 schedulers x 32 lanes x 1.965 GHz"}}
 
     def c3(name):
         def run():
             code = CSSCode(*[np.array(h) for h in getattr(codes, name)()])
-            dev, n, shots = code.device, code.n, 1_000_000_000
+            dev, n, shots = code.device, code.n, int(1_000_000_000 * scale) // 1024 * 1024
             stride = ((shots + 127) // 128) * 2
             ex = torch.empty((n, stride), dtype=torch.int64, device="cuda")
             ez = torch.empty((n, stride), dtype=torch.int64, device="cuda")
             tally = torch.zeros(6, dtype=torch.int64, device="cuda")
-            dev.mc_sample_dev(P_ERR, shots, SEED, 0, ex.data_ptr(), ez.data_ptr(), stride, stream)
-            ms = timed(lambda: dev.decode_dev(shots, stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride,
-                                              tally=tally.data_ptr()))
-            gbs = 2 * n / 8 * shots / ms / 1e6
-            return {"workload": f"{name} 1e9 shots resident, syndrome + lookup decode + tally", "ms": ms,
-                    "shots_per_s": shots / ms * 1e3, "bound": "hbm", "gbs": gbs, "frac": gbs / peak_gbs,
-                    "kernel": dev.kernel_name()}
+            dev.mc_sample_dev(P_ERR, shots, SEED, rank * shots, ex.data_ptr(), ez.data_ptr(), stride, stream)
+            ms = ctx.timed(lambda: dev.decode_dev(shots, stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride,
+                                                  tally=tally.data_ptr()))
+            ctx.launches += 5
+            gbs = world * 2 * n / 8 * shots / ms / 1e6
+            return {"workload": f"{name}, 1e9 shots per GPU resident, syndrome + lookup decode + tally", "ms": ms,
+                    "value": world * shots / ms * 1e3, "unit": "shots/s", "shots_per_gpu": shots,
+                    "kernel": dev.kernel_name(), "roofline": hbm(gbs)}
         return run
 
     def c4():
         hx, hz = codes.hgp1600()
         dev = SyndromeCode(hx, hz).device
-        shots = 100_000_000
-        stride = ((shots + 127) // 128) * 2
-        e = torch.randint(-2**62, 2**62, (1600, stride), dtype=torch.int64, device="cuda")
-        s = torch.empty((768, stride), dtype=torch.int64, device="cuda")
-        ms = timed(lambda: dev.syndrome_dev(2, e.data_ptr(), stride, shots, s.data_ptr(), stride, stream))
-        gbs = (1600 + 768) / 8 * shots / ms / 1e6
-        out4 = {"workload": "hgp n=1600 m=768, 1e8 shots resident, syndromes of one Pauli type", "ms": ms,
-                "shots_per_s": shots / ms * 1e3, "bound": "hbm", "gbs": gbs, "frac": gbs / peak_gbs,
-                "kernel": dev.kernel_name(), "layout": "plane-major"}
-        del e, s
+        shots = int(100_000_000 * scale) // 1024 * 1024
         tiles = (shots + 1023) // 1024
-        e = torch.randint(-2**62, 2**62, (tiles, 1600, 16), dtype=torch.int64, device="cuda")
+        e = ctx.rand_words(tiles, 1600, 16)
         s = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
         per_type = {}
         for which in (1, 2):
-            ms_t = timed(lambda: dev.syndrome_tiles_dev(which, e.data_ptr(), shots, s.data_ptr(), stream))
-            per_type[which] = ms_t
-        ms_t = (per_type[1] + per_type[2]) / 2
-        gbs_t = (1600 + 768) / 8 * shots / ms_t / 1e6
-        out4["tile_major"] = {"workload": "same batch stored [tile of 1024 shots][plane][128 B] (qcss_syndrome_tiles_dev), "
-                                          "mean of the two Pauli types",
-                              "ms": ms_t, "ms_which1": per_type[1], "ms_which2": per_type[2],
-                              "shots_per_s": shots / ms_t * 1e3, "gbs": gbs_t, "frac": gbs_t / peak_gbs,
-                              "kernel": "tiled-ring(tile-major, cp.async.bulk)"}
-        return out4
+            per_type[which] = ctx.timed(lambda: dev.syndrome_tiles_dev(which, e.data_ptr(), shots, s.data_ptr(), stream))
+        ctx.launches += 8
+        ms_both = per_type[1] + per_type[2]
+        gbs = world * 592.0 * shots / ms_both / 1e6
+        res = {"workload": "hgp n=1600 m=768, 1e8 shots per GPU resident tile-major [tile of 1024 shots][plane][128 B], "
+                           "syndromes of BOTH Pauli types (two launches)",
+               "ms": ms_both, "ms_which1": per_type[1], "ms_which2": per_type[2],
+               "value": world * shots / ms_both * 1e3, "unit": "shots/s", "shots_per_gpu": shots,
+               "kernel": "tiled-ring(tile-major, cp.async.bulk)", "roofline": hbm(gbs)}
+        del e, s
+        torch.cuda.empty_cache()
+        stride = ((shots + 127) // 128) * 2
+        e = ctx.rand_words(1600, stride)
+        s = torch.empty((768, stride), dtype=torch.int64, device="cuda")
+        ms = ctx.timed(lambda: dev.syndrome_dev(2, e.data_ptr(), stride, shots, s.data_ptr(), stride, stream))
+        ctx.launches += 4
+        gbs = world * 296.0 * shots / ms / 1e6
+        res["plane_major"] = {"workload": "same shots stored plane-major (qcss_syndrome_dev), one Pauli type", "ms": ms,
+                              "value": world * shots / ms * 1e3, "unit": "shots/s of one Pauli type",
+                              "kernel": dev.kernel_name(), "roofline": hbm(gbs)}
+        return res
+
+    def c4_fused():
+        hx, hz = codes.hgp1600()
+        dev = SyndromeCode(hx, hz).device
+        shots = int(100_000_000 * scale) // 1024 * 1024
+        tiles = (shots + 1023) // 1024
+        sx = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
+        sz = torch.empty((tiles, 768, 16), dtype=torch.int64, device="cuda")
+        ms = ctx.timed(lambda: dev.sample_syndrome_tiles_dev(P_ERR, shots, SEED, rank * shots, sx.data_ptr(), sz.data_ptr(),
+                                                             0, 0, stream))
+        ctx.launches += 4
+        rate = world * shots / ms * 1e3
+        return {"workload": "hgp n=1600, Philox sampler fused into the sparse syndrome kernel, both Pauli types, "
+                            "1e8 shots per GPU, only the 2 x 768 syndrome bits per shot reach HBM",
+                "ms": ms, "value": rate, "unit": "shots/s", "shots_per_gpu": shots, "bound": "int",
+                "site_words_per_s_per_gpu": rate / 32 * 1600 / world}
+
+    def c4_dense():
+        m, n = 1024, 2048
+        h = _native.unpack_bits(codes.random_matrices_c5(1)[0], n)
+        with _native.option("dense", 1):
+            dev = SyndromeCode(h, h[:256]).device
+        shots = int((1 << 21) * scale) // 1024 * 1024
+        stride = ((shots + 127) // 128) * 2
+        e = ctx.rand_words(n, stride)
+        s = torch.empty((m, stride), dtype=torch.int64, device="cuda")
+        ms = ctx.timed(lambda: dev.syndrome_dev(1, e.data_ptr(), stride, shots, s.data_ptr(), stride, stream))
+        ctx.launches += 4
+        ops = 2.0 * m * n * shots / ms * 1e3                         # per GPU
+        i8_peak, src = _i8_peak()
+        return {"workload": "H = C5 matrix 0 (1024 x 2048 dense), uniform random error planes, 2^21 shots per GPU, "
+                            "tcgen05.mma.kind::i8 + mod-2 epilogue",
+                "ms": ms, "value": world * shots / ms * 1e3, "unit": "shots/s", "shots_per_gpu": shots,
+                "kernel": dev.kernel_name(),
+                "roofline": {"bound": "tensor", "achieved": ops / 1e12, "peak": i8_peak / 1e12, "unit": "Tint-op/s",
+                             "frac": ops / i8_peak, "traffic": None, "peak_source": src,
+                             "ops_per_shot": 2.0 * m * n}}
 
     def c5():
-        batch, m, n = 4096, 1024, 2048
-        mats = torch.randint(-2**62, 2**62, (batch, m, n // 64), dtype=torch.int64, device="cuda")
+        total, m, n = max(int(4096 * scale), world), 1024, 2048
+        batch = total // world
+        packed = codes.random_matrices_c5(batch, offset=rank * batch)     # SURVEY 8d: default_rng(5) matrices
+        mats = torch.from_numpy(packed.view(np.int64)).cuda()
         outm = torch.empty_like(mats)
-        rank = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        rk = torch.zeros(batch, dtype=torch.int32, device="cuda")
         piv = torch.zeros((batch, m), dtype=torch.int32, device="cuda")
-        ms = timed(lambda: _native.check(lib.qcss_gf2_rref_dev(mats.data_ptr(), batch, m, n, outm.data_ptr(),
-                                                               rank.data_ptr(), piv.data_ptr(), stream)))
-        ops = 2.52e7 * batch / ms * 1e3
-        res = {"workload": "4096 x (1024 x 2048) GF(2) RREF + rank + pivots", "ms": ms,
-               "matrices_per_s": batch / ms * 1e3, "bound": "int", "xor_word_ops_per_s": ops,
-               "frac_of_lop3_peak_1.85e13": ops / 1.85e13, "full_rank": int((rank == m).sum().item())}
+        ms = ctx.timed(lambda: _native.check(lib.qcss_gf2_rref_dev(mats.data_ptr(), batch, m, n, outm.data_ptr(),
+                                                                   rk.data_ptr(), piv.data_ptr(), stream)))
+        ctx.launches += 4
+        per_gpu_ops = 2.52e7 * batch / ms * 1e3
+        res = {"workload": f"4096 x (1024 x 2048) default_rng(5) matrices, {batch} per GPU (strong scaling): GF(2) RREF + "
+                           "rank + pivots",
+               "ms": ms, "value": world * batch / ms * 1e3, "unit": "matrices/s", "matrices_per_gpu": batch,
+               "full_rank": int((rk == m).sum().item()),
+               "roofline": {"bound": "int", "achieved": per_gpu_ops, "peak": LOP3_PEAK, "unit": "xor-word-op/s",
+                            "frac": per_gpu_ops / LOP3_PEAK, "traffic": None,
+                            "model": "SURVEY 8d FIXED count: 2.52e7 32-bit XOR word-ops per matrix (plain Gauss-Jordan), "
+                                     "whatever the algorithm executes; peak = measured LOP3 rate (profiles/r01_int_peak.jsonl)",
+                            "frac_of_m4r_minimum": None}}
         del outm, piv
         rows = n - m + 8
         basis = torch.empty((batch, rows, n // 64), dtype=torch.int64, device="cuda")
         ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
-        ms_ns = timed(lambda: _native.check(lib.qcss_gf2_nullspace_dev(mats.data_ptr(), batch, m, n, rows, basis.data_ptr(),
-                                                                       rank.data_ptr(), ovf.data_ptr(), stream)))
+        ms_ns = ctx.timed(lambda: _native.check(lib.qcss_gf2_nullspace_dev(mats.data_ptr(), batch, m, n, rows, basis.data_ptr(),
+                                                                           rk.data_ptr(), ovf.data_ptr(), stream)))
+        ctx.launches += 8
         res["with_null_space"] = {"workload": "RREF + rank + null-space basis of every matrix", "ms": ms_ns,
-                                  "matrices_per_s": batch / ms_ns * 1e3, "overflow": int(ovf.item())}
+                                  "value": world * batch / ms_ns * 1e3, "unit": "matrices/s", "overflow": int(ovf.item())}
         return res
 
     guarded("c2_fused_sampler", c2_fused)
     guarded("c3_qrm15", c3("qrm15"))
     guarded("c3_golay23", c3("golay23"))
     guarded("c4_hgp1600", c4)
+    guarded("c4_hgp1600_fused_sampler", c4_fused)
+    guarded("c4_dense", c4_dense)
     guarded("c5_gf2_rref", c5)
     return out
 
 
-def measure_e2e(torch, dist, world, dev, ex, ez, n, stride, shots, args, resident_tally):
-    """qcss_decode_xz on pinned host planes: every step copies 2*n planes host->device (chunked,
-    overlapped with the kernels) and reads the six tallies back."""
+def _i8_peak():
+    """int-ops/s of back-to-back tcgen05.mma.kind::i8 on this GPU (tools/i8_mma_peak, built by build()); falls back
+    to the value committed in profiles/ and, last, to the nominal 4.5e15."""
+    import subprocess
+    exe = os.path.join(REPO, "tools", "i8_mma_peak")
+    try:
+        if os.path.exists(exe):
+            res = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+            val = json.loads(res.stdout.strip().splitlines()[-1])
+            return float(val["int_ops_per_s_mean"]), "measured in this run: tools/i8_mma_peak (back-to-back MMAs, mean of 10)"
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(REPO, "profiles", "r02_i8_mma_peak.json")) as fh:
+            return float(json.load(fh)["int_ops_per_s_mean"]), "profiles/r02_i8_mma_peak.json"
+    except Exception:
+        return 4.5e15, "nominal dense int8 peak (no measurement available)"
+
+
+def measure_e2e(ctx, dev, ex, ez, n, stride, shots, args, first_shot):
+    """End to end through the host-buffer C ABI, the SAME shots per GPU at every N (min(shots, 2^32): bounds the
+    pinned host memory of an 8-rank run to 8 x 7.5 GB).  Every step copies its inputs host->device inside the timed
+    region and reads the six tallies back; wall clock around K calls, max over ranks."""
+    torch, dist, world = ctx.torch, ctx.dist, ctx.world
     from quantum_css_codes_b200 import _native
-    if world > 1:
-        # bound the pinned host memory of an N-rank run (N x 17.5 GB otherwise): the e2e rate is measured
-        # on the first 2^31 shots of each rank's resident batch
-        shots = min(shots, 1 << 31)
-        stride_e2e = ((shots + 127) // 128) * 2
-        ex, ez = ex[:, :stride_e2e].contiguous(), ez[:, :stride_e2e].contiguous()
-        stride = stride_e2e
-        resident_tally = None
-    nbytes = n * stride * 8
+    shots = min(shots, 1 << 32)
+    stride_e2e = ((shots + 127) // 128) * 2
+    tally_dev = torch.zeros(6, dtype=torch.int64, device="cuda")
+    dev.decode_dev(shots, ctx.stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride, tally=tally_dev.data_ptr())
+    torch.cuda.synchronize()
+    resident = tally_dev.cpu().numpy()[1:].tolist()
+    nbytes = n * stride_e2e * 8
     try:
         hx, hx_ptr = _native.host_alloc(nbytes)
         hz, hz_ptr = _native.host_alloc(nbytes)
     except Exception as exc:                                     # not enough pinnable memory
         return {"value": None, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "error": str(exc)}
-    try:
-        torch.cuda.synchronize()
-        tx = torch.from_numpy(hx.view(np.int64)).view(n, stride)
-        tz = torch.from_numpy(hz.view(np.int64)).view(n, stride)
-        tx.copy_(ex)
-        tz.copy_(ez)
-        torch.cuda.synchronize()
-        tally = dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride, shots)        # warm-up (allocates slots)
+
+    def wall(fn, steps):
+        fn()                                                      # warm-up (allocates slots)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            tally = dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride, shots)
+        for _ in range(steps):
+            res = fn()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        ok = True
-        if world == 1:
-            ok = [tally[k] for k in _native.TALLY_FIELDS[1:]] == [int(v) for v in resident_tally[1:]]
-        return {"value": world * shots * args.e2e_steps / dt, "unit": "shots/s", "shots_per_gpu_per_step": shots,
-                "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 48,
-                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-                "api": "qcss_decode_xz (host planes, chunked H2D overlapped with kernels)",
-                "matches_resident_tally": bool(ok)}
+        return dt / steps, res
+
+    try:
+        torch.cuda.synchronize()
+        tx = torch.from_numpy(hx.view(np.int64)).view(n, stride_e2e)
+        tz = torch.from_numpy(hz.view(np.int64)).view(n, stride_e2e)
+        tx.copy_(ex[:, :stride_e2e])
+        tz.copy_(ez[:, :stride_e2e])
+        torch.cuda.synchronize()
+        sec, tally = wall(lambda: dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride_e2e, shots), args.e2e_steps)
+        ctx.launches += (args.e2e_steps + 1) * max(1, -(-nbytes // (32 << 20)))
+        ok = [tally[k] for k in _native.TALLY_FIELDS[1:]] == resident
+        out = {"value": world * shots / sec, "unit": "shots/s", "shots_per_gpu_per_step": shots,
+               "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 48,
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * sec,
+               "api": "qcss_decode_xz (pinned host bit planes, chunked H2D overlapped with kernels)",
+               "matches_resident_tally": bool(ok)}
+        # raw host->device ceiling of this box at this N: the same bytes with no kernels at all
+        slot = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        src = torch.from_numpy(hx.view(np.uint8))[: 64 << 20]
+        chunks = max(1, min(32, nbytes // (64 << 20)))
+
+        def copy_only():
+            for _ in range(chunks):
+                slot.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+        sec_c, _ = wall(copy_only, 3)
+        out["h2d_ceiling_gbs_per_gpu"] = chunks * (64 << 20) / sec_c / 1e9
+        out["h2d_achieved_gbs_per_gpu"] = 2 * nbytes / sec / 1e9
+        extra = measure_e2e_formats(ctx, dev, ex, ez, n, stride, shots, args, resident, wall, hx, hx_ptr, hz, hz_ptr)
+        out.update(extra)
+        return out
     finally:
         _native.host_free(hx_ptr)
         _native.host_free(hz_ptr)
+
+
+def measure_e2e_formats(ctx, dev, ex, ez, n, stride, shots, args, resident, wall, hx, hx_ptr, hz, hz_ptr):
+    """The two other host formats of the same batch (filled in by later milestones when the entry points exist)."""
+    return {}
 
 
 def main():

@@ -1,6 +1,8 @@
 """GPU parity for K4 (batched GF(2) Gauss-Jordan) through the C ABI, against the oracle and the
 reference's captured outputs."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -110,6 +112,29 @@ def test_rref_c5_full_size():
         assert np.array_equal(out[b], want), b
         assert rank[b] == len(pv) and np.array_equal(piv[b, : rank[b]], pv)
     assert rank[0] == 1024 and rank[1] == 1023
+
+
+def test_rref_c5_sixteen_full_size_matrices_vs_reference_goldens():
+    """>= 16 full-size 1024 x 2048 matrices bit-exact against bin_matrix.reduced_row_echelon_form ITSELF --
+    tests/golden/c5_rref_golden.npz holds SHA-256 + rank of the UNMODIFIED reference's output for sixteen
+    default_rng(5) matrices (full rank, dependent rows, zero columns, zero leading columns; oracle/gen_c5_golden.py)
+    and two outputs in full.  Every kernel that takes this shape is run."""
+    import hashlib
+    from oracle.gen_c5_golden import COUNT, variant
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c5_rref_golden.npz")
+    with np.load(path, allow_pickle=False) as z:
+        sha, rank_want, full = z["sha256"], z["rank"], [z["rref_0"], z["rref_1"]]
+    packed = codes.random_matrices_c5(COUNT)
+    mats = np.stack([ogf2.pack_rows(variant(i, ogf2.unpack_rows(packed[i], 2048)).astype(np.uint8)) for i in range(COUNT)])
+    for knob in (0, 2, 3):
+        with _native.option("gf2_kernel", knob):
+            out, rank, piv = bin_matrix.rref_packed_batched(mats, 2048)
+        assert np.array_equal(out[0], full[0]) and np.array_equal(out[1], full[1]), knob
+        assert [hashlib.sha256(out[i].tobytes()).hexdigest() for i in range(COUNT)] == sha.tolist(), knob
+        assert rank.tolist() == rank_want.tolist(), knob
+        for i in range(COUNT):                                     # pivots: first set column of each non-zero RREF row
+            rows = ogf2.unpack_rows(out[i][: rank[i]], 2048)
+            assert np.array_equal(piv[i, : rank[i]], rows.argmax(axis=1)), (knob, i)
 
 
 def test_rank_nullspace_solve():

@@ -192,3 +192,23 @@ def test_rank_nullspace_solve_properties():
         b = (a @ x0) % 2
         x = gf2.solve(a, b)
         assert x is not None and np.array_equal((a @ x) % 2, b)
+
+
+def test_oracle_rref_full_size_c5_vs_reference_goldens():
+    """The oracle's packed Gauss-Jordan against the UNMODIFIED reference at BASELINE config 5's full size: SHA-256 and
+    rank of bin_matrix.reduced_row_echelon_form on sixteen 1024 x 2048 matrices (oracle/gen_c5_golden.py)."""
+    import hashlib
+    import os
+    from oracle.gen_c5_golden import COUNT, variant
+    from quantum_css_codes_b200 import codes
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c5_rref_golden.npz")
+    with np.load(path, allow_pickle=False) as z:
+        sha, rank_want, full0 = z["sha256"], z["rank"], z["rref_0"]
+    packed = codes.random_matrices_c5(COUNT)
+    for i in range(COUNT):
+        mat = gf2.pack_rows(variant(i, gf2.unpack_rows(packed[i], 2048)).astype(np.uint8))
+        out, pivots = gf2.rref_packed(mat, 2048)
+        if i == 0:
+            assert np.array_equal(out, full0)
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == sha[i], i
+        assert len(pivots) == rank_want[i]

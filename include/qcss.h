@@ -172,6 +172,41 @@ QCSS_API int qcss_decode_xz(qcss_code* code, const uint64_t* ex_planes, const ui
 /* General device-pointer form, asynchronous on `stream` (a cudaStream_t, NULL = default). */
 QCSS_API int qcss_decode_dev(qcss_code* code, const qcss_decode_io* io, int64_t shots, void* stream);
 
+/* ---- The same calls on the reference's OWN data layout (numpy arrays passed by reference): a C-contiguous
+ *      (shots, n) array of 0/1 elements, elem_bytes = 1 (uint8 / bool) or 8 (int64, the reference's dtype='int',
+ *      css_code.py:39-40; only bit 0 of an element is used, which is np.mod(x, 2) for two's-complement values).
+ *      The transposition to bit planes happens ON THE DEVICE (csrc/format_kernels.cu: coalesced loads of 1024-shot
+ *      blocks, one ballot per plane word), chunks overlap their host-to-device copies; results come back in the
+ *      reference's layout too: s_out (shots, m) bytes = np.mod(E @ H.T, 2), corr_out (shots, n) bytes, flip_out /
+ *      miss_out (shots,) bytes.  Outputs may be NULL.  qcss_pack_shots_dev / qcss_unpack_planes_dev are the
+ *      device-pointer transposers themselves (source 16-byte aligned, destination 4-byte aligned). ---------------- */
+QCSS_API int qcss_syndrome_shots(qcss_code* code, int which, const void* errors, int elem_bytes, int64_t shots, uint8_t* s_out);
+QCSS_API int qcss_decode_shots(qcss_code* code, int which, const void* errors, int elem_bytes, int64_t shots, uint8_t* corr_out,
+                      uint8_t* flip_out, uint8_t* miss_out, qcss_tally* tally);
+QCSS_API int qcss_decode_xz_shots(qcss_code* code, const void* x_errors, const void* z_errors, int elem_bytes, int64_t shots,
+                         qcss_tally* tally);
+QCSS_API int qcss_pack_shots_dev(const void* d_src, int elem_bytes, int n, int64_t shots, uint64_t* d_planes, int64_t stride,
+                        void* stream);
+QCSS_API int qcss_unpack_planes_dev(const uint64_t* d_planes, int64_t stride, int m, int64_t shots, uint8_t* d_dst, void* stream);
+
+/* ---- SPARSE batches: the errors of a batch as a list of events sorted by shot (non-decreasing),
+ *          event = shot << 18 | qubit << 2 | pauli,   pauli: 1 = X, 2 = Z, 3 = Y (bit 0 = X component, bit 1 = Z component);
+ *      repeated (shot, qubit) events compose by XOR.  At p = 1e-3 a Steane batch is 0.056 bytes per shot in this form
+ *      (1.75 as bit planes), and the decode is event driven: shots without events have the zero syndrome and take the
+ *      table entry of key 0; every other shot XORs the big-endian column keys (bin_matrix.py:36-43) of its events and
+ *      reads the table as quil_classical_correct does (css_code.py:649-685).  Tallies equal those of qcss_decode_xz on
+ *      the same batch.  QCSS_ERR_INVALID for unsorted events, qubit >= n, shot >= shots or pauli = 0 (the _dev form
+ *      reports those in *d_status: bit 0 bad field, bit 1 unsorted; d_tally = uint64[6], accumulated).
+ *      qcss_events_from_planes_dev writes the event list of a batch of bit planes (sorted by shot, then qubit; shot
+ *      numbers start at first_shot) and its length to *d_count -- also when that exceeds `capacity`, in which case
+ *      only the first `capacity` events are stored. ----------------------------------------------------------------- */
+QCSS_API int qcss_decode_xz_sparse(qcss_code* code, const uint64_t* events, int64_t n_events, int64_t shots, qcss_tally* tally);
+QCSS_API int qcss_decode_xz_sparse_dev(qcss_code* code, const uint64_t* d_events, int64_t n_events, int64_t shots,
+                              uint64_t* d_tally, int32_t* d_status, void* stream);
+QCSS_API int qcss_events_from_planes_dev(qcss_code* code, const uint64_t* d_ex, const uint64_t* d_ez, int64_t e_stride,
+                                int64_t shots, int64_t first_shot, uint64_t* d_events, int64_t capacity, uint64_t* d_count,
+                                void* stream);
+
 /* ---- K3 fused Philox sampler + K1 + K2 (no reference counterpart).
  *      Depolarising noise: each qubit of each shot gets X, Y or Z with probability p/3 each.  For
  *      p >= 1/128 the per-shot error probability is exactly floor(p * 2^32) / 2^32; below that the

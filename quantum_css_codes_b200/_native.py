@@ -95,6 +95,23 @@ PROTOTYPES = {
                                       ctypes.c_int64, ctypes.POINTER(Tally)]),
     "qcss_decode_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(DecodeIO), ctypes.c_int64,
                                        ctypes.c_void_p]),
+    "qcss_syndrome_shots": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                           ctypes.c_void_p]),
+    "qcss_decode_shots": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Tally)]),
+    "qcss_decode_xz_shots": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                            ctypes.POINTER(Tally)]),
+    "qcss_pack_shots_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_void_p]),
+    "qcss_unpack_planes_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
+    "qcss_decode_xz_sparse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.POINTER(Tally)]),
+    "qcss_decode_xz_sparse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcss_events_from_planes_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_void_p, ctypes.c_void_p]),
     "qcss_mc_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
                                    ctypes.c_int64, ctypes.POINTER(Tally)]),
     "qcss_mc_run_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64,
@@ -358,6 +375,81 @@ class DeviceCode:
         check(self._lib.qcss_decode_xz(self.handle, ctypes.c_void_p(ex_ptr), ctypes.c_void_p(ez_ptr),
                                        stride, shots, ctypes.byref(tally)))
         return tally.as_dict()
+
+    # ---- the reference's own layout: (shots, n) arrays, transposed on the device ----------------------
+    def _shot_rows(self, errors):
+        """C-contiguous (shots, n) uint8 or int64 view of ``errors`` (bool is reinterpreted, other dtypes are
+        reduced mod 2 into uint8); returns (array, elem_bytes)."""
+        errors = np.asarray(errors)
+        if errors.ndim != 2 or errors.shape[1] != self.n:
+            raise ValueError(f"expected a (shots, {self.n}) array")
+        if errors.dtype == np.bool_:
+            errors = errors.view(np.uint8)
+        elif errors.dtype not in (np.uint8, np.int64):
+            errors = np.mod(errors, 2).astype(np.uint8)
+        return np.ascontiguousarray(errors), errors.dtype.itemsize
+
+    def syndrome_shots(self, errors, which):
+        """(shots, n) errors -> (shots, m) uint8 syndromes (qcss_syndrome_shots)."""
+        rows, eb = self._shot_rows(errors)
+        out = np.zeros((rows.shape[0], self.m(which)), dtype=np.uint8)
+        check(self._lib.qcss_syndrome_shots(self.handle, which, _ptr(rows), eb, rows.shape[0], _ptr(out)))
+        return out
+
+    def decode_shots(self, errors, which, corrections=True):
+        """(shots, n) errors -> (correction (shots, n) uint8 or None, flip (shots,), miss (shots,), tally)."""
+        rows, eb = self._shot_rows(errors)
+        self.m(which)
+        shots = rows.shape[0]
+        corr = np.zeros((shots, self.n), dtype=np.uint8) if corrections else None
+        flip = np.zeros(shots, dtype=np.uint8)
+        miss = np.zeros(shots, dtype=np.uint8)
+        tally = Tally()
+        check(self._lib.qcss_decode_shots(self.handle, which, _ptr(rows), eb, shots, _ptr(corr), _ptr(flip), _ptr(miss),
+                                          ctypes.byref(tally)))
+        return corr, flip, miss, tally.as_dict()
+
+    def decode_xz_shots(self, x_errors, z_errors):
+        """Tallies of a shared (shots, n) batch of X and Z errors (qcss_decode_xz_shots)."""
+        rx, ebx = self._shot_rows(x_errors)
+        rz, ebz = self._shot_rows(z_errors)
+        if rx.shape != rz.shape:
+            raise ValueError("x and z errors must have the same shape")
+        if ebx != ebz:
+            rx, rz, ebx = (rx & 1).astype(np.uint8), (rz & 1).astype(np.uint8), 1
+        tally = Tally()
+        check(self._lib.qcss_decode_xz_shots(self.handle, _ptr(rx), _ptr(rz), ebx, rx.shape[0], ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def decode_xz_shots_host_ptr(self, x_ptr, z_ptr, elem_bytes, shots):
+        tally = Tally()
+        check(self._lib.qcss_decode_xz_shots(self.handle, ctypes.c_void_p(x_ptr), ctypes.c_void_p(z_ptr), elem_bytes,
+                                             int(shots), ctypes.byref(tally)))
+        return tally.as_dict()
+
+    # ---- sparse batches: events sorted by shot -----------------------------------------------------
+    def decode_xz_sparse(self, events, shots):
+        """Tallies of a batch given as uint64 events ``shot << 18 | qubit << 2 | pauli`` (qcss_decode_xz_sparse)."""
+        events = np.ascontiguousarray(events, dtype=np.uint64)
+        tally = Tally()
+        check(self._lib.qcss_decode_xz_sparse(self.handle, _ptr(events), events.size, int(shots), ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def decode_xz_sparse_host_ptr(self, events_ptr, n_events, shots):
+        tally = Tally()
+        check(self._lib.qcss_decode_xz_sparse(self.handle, ctypes.c_void_p(events_ptr), int(n_events), int(shots),
+                                              ctypes.byref(tally)))
+        return tally.as_dict()
+
+    def decode_xz_sparse_dev(self, events_ptr, n_events, shots, tally_ptr, status_ptr=0, stream=0):
+        check(self._lib.qcss_decode_xz_sparse_dev(self.handle, ctypes.c_void_p(events_ptr), int(n_events), int(shots),
+                                                  ctypes.c_void_p(tally_ptr), ctypes.c_void_p(status_ptr),
+                                                  ctypes.c_void_p(stream)))
+
+    def events_from_planes_dev(self, ex_ptr, ez_ptr, e_stride, shots, first_shot, events_ptr, capacity, count_ptr, stream=0):
+        check(self._lib.qcss_events_from_planes_dev(self.handle, ctypes.c_void_p(ex_ptr), ctypes.c_void_p(ez_ptr), e_stride,
+                                                    int(shots), int(first_shot), ctypes.c_void_p(events_ptr), int(capacity),
+                                                    ctypes.c_void_p(count_ptr), ctypes.c_void_p(stream)))
 
     def mc_run(self, p, shots, seed=0, first_shot=0):
         tally = Tally()

@@ -19,7 +19,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libqcss.so")
 SOURCES = ["api.cu", "small_dispatch.cu", "small_named_steane.cu", "small_named_qrm15.cu",
            "small_named_golay23.cu", "small_generic16.cu", "small_generic32.cu", "tiled_kernels.cu",
-           "gf2_kernels.cu", "gf2_m4r.cu", "gf2_m4r2.cu", "gf2_derive.cu", "gf2_normalize.cu", "ec_kernels.cu", "sample_tiles.cu", "table_kernels.cu", "hist_kernels.cu", "dense_kernels.cu"]
+           "gf2_kernels.cu", "gf2_m4r.cu", "gf2_m4r2.cu", "gf2_derive.cu", "gf2_normalize.cu", "ec_kernels.cu", "sample_tiles.cu", "table_kernels.cu", "hist_kernels.cu", "dense_kernels.cu", "format_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden"]

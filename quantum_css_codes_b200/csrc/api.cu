@@ -77,6 +77,7 @@ struct qcss_code {
     GenericSide side_x{}, side_z{};     // x: which = 2 (H2, _c2_syndromes, Lz); z: which = 1
     uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
     uint32_t lmask_x = 0, lmask_z = 0;
+    uint32_t fm0_x = 0, fm0_z = 0;      // table byte of the zero syndrome (bit0 L.correction, bit1 miss)
     int named_id = -1;
     // kernels compiled for THIS code (qcss_code_spec_source -> nvcc -> qcss_code_load_specialized)
     void* spec_dl = nullptr;
@@ -91,6 +92,7 @@ struct qcss_code {
     cudaStream_t stream = nullptr;
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     DevBuf slot_x[kSlots], slot_z[kSlots];
+    DevBuf slot_rx[kSlots], slot_rz[kSlots];          // raw (shots, n) rows / event lists of the format entry points
     DevBuf buf_a, buf_b, buf_c, buf_d, buf_e;
     DevBuf tally;
 };
@@ -162,6 +164,7 @@ int build_side(qcss_code* c, GenericSide& s, uint32_t* rows, uint32_t& lmask, in
     s.has_miss = 0;
     for (size_t k = 0; k < size; ++k)
         if (fm[k] & 2) s.has_miss = 1;
+    (&s == &c->side_x ? c->fm0_x : c->fm0_z) = fm[0];
     s.mode = (m <= kSlicedM) ? kModeSliced : kModeLut;
     if (m <= kSlicedM) {
         for (size_t k = 0; k < size; ++k) {
@@ -560,6 +563,8 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
     for (int i = 0; i < kSlots; ++i) {
         c->slot_x[i].release();
         c->slot_z[i].release();
+        c->slot_rx[i].release();
+        c->slot_rz[i].release();
         if (c->slot_stream[i]) cudaStreamDestroy(c->slot_stream[i]);
     }
     c->buf_a.release(); c->buf_b.release(); c->buf_c.release(); c->buf_d.release(); c->buf_e.release();
@@ -1254,6 +1259,299 @@ QCSS_API int qcss_syndrome_hist(qcss_code* c, int which, const uint64_t* e_plane
     if (rc) { cudaStreamSynchronize(c->stream); return rc; }   // pending copies must not outlive the call
     QCSS_CUDA(cudaMemcpyAsync(hist, c->buf_c.p, hb, cudaMemcpyDeviceToHost, c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    return QCSS_OK;
+}
+
+}  // extern "C"
+
+// ---- host data formats (the reference passes numpy arrays) ------------------------
+
+namespace {
+
+int check_elem(int elem_bytes) {
+    if (elem_bytes != 1 && elem_bytes != 8)
+        return fail(QCSS_ERR_INVALID, "elem_bytes must be 1 (uint8) or 8 (int64, numpy dtype='int'), got %d", elem_bytes);
+    return QCSS_OK;
+}
+
+// shots per chunk of the streaming entry points: ~32 MB of raw rows per Pauli type, whole 1024-shot blocks
+int64_t chunk_shots_for(int n, int elem_bytes, int64_t shots) {
+    int64_t cs = ((int64_t)(32u << 20) / ((int64_t)n * elem_bytes)) & ~(int64_t)1023;
+    if (cs < 1024) cs = 1024;
+    const int64_t all = (shots + 1023) & ~(int64_t)1023;
+    return cs < all ? cs : all;
+}
+
+__global__ void k_events_finish(unsigned long long* tally, const unsigned long long* aux, unsigned long long shots,
+                                uint32_t f0x, uint32_t f0z, int32_t* status) {
+    // shots without any event have the zero syndrome: they take the table entry of key 0 (normally "no flip, hit")
+    const unsigned long long quiet = shots - aux[0];
+    if (quiet != 0 && (f0x | f0z) != 0) {
+        tally[1] += quiet * (f0x & 1u);
+        tally[2] += quiet * (f0z & 1u);
+        tally[3] += quiet * ((f0x | f0z) & 1u);
+        tally[4] += quiet * ((f0x >> 1) & 1u);
+        tally[5] += quiet * ((f0z >> 1) & 1u);
+    }
+    if (status != nullptr) *status = (int32_t)aux[1];
+}
+
+int sparse_ready(qcss_code* c, uint32_t* f0x, uint32_t* f0z) {
+    if (!c->small) return fail(QCSS_ERR_UNSUPPORTED, "lookup decode covers n <= %d and m <= %d", kMaxN, kMaxM);
+    if (c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
+        return fail(QCSS_ERR_INVALID, "sparse decode needs both syndrome tables");
+    *f0x = c->fm0_x;
+    *f0z = c->fm0_z;
+    return QCSS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+QCSS_API int qcss_pack_shots_dev(const void* d_src, int elem_bytes, int n, int64_t shots, uint64_t* d_planes, int64_t stride,
+                        void* stream) {
+    int rc;
+    if ((rc = check_elem(elem_bytes))) return rc;
+    if (n < 1 || shots < 0) return fail(QCSS_ERR_INVALID, "bad dimensions");
+    if (!d_src || !d_planes) return fail(QCSS_ERR_INVALID, "NULL argument");
+    if (((uintptr_t)d_src & 15u) != 0) return fail(QCSS_ERR_INVALID, "source must be 16-byte aligned");
+    if ((rc = check_planes(d_planes, stride, shots, "planes"))) return rc;
+    QCSS_CUDA(launch_pack_shots(d_src, elem_bytes, n, shots, (uint32_t*)d_planes, stride * 2, (cudaStream_t)stream));
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_unpack_planes_dev(const uint64_t* d_planes, int64_t stride, int m, int64_t shots, uint8_t* d_dst, void* stream) {
+    if (m < 1 || shots < 0) return fail(QCSS_ERR_INVALID, "bad dimensions");
+    if (!d_planes || !d_dst) return fail(QCSS_ERR_INVALID, "NULL argument");
+    if (((uintptr_t)d_dst & 3u) != 0) return fail(QCSS_ERR_INVALID, "destination must be 4-byte aligned");
+    int rc;
+    if ((rc = check_planes(d_planes, stride, shots, "planes"))) return rc;
+    QCSS_CUDA(launch_unpack_planes((const uint32_t*)d_planes, stride * 2, m, shots, d_dst, (cudaStream_t)stream));
+    return QCSS_OK;
+}
+
+// Both Pauli types of the same shots in the reference's own layout; tallies only.  Chunks of whole 1024-shot blocks
+// flow host -> device on three streams; each chunk is transposed to planes on the device and decoded there.
+QCSS_API int qcss_decode_xz_shots(qcss_code* c, const void* ex, const void* ez, int elem_bytes, int64_t shots, qcss_tally* tally) {
+    if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    if (!ex || !ez) return fail(QCSS_ERR_INVALID, "NULL errors");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    int rc;
+    if ((rc = check_elem(elem_bytes))) return rc;
+    if (!c->small) return fail(QCSS_ERR_UNSUPPORTED, "lookup decode covers n <= %d and m <= %d", kMaxN, kMaxM);
+    if ((rc = ensure_streams(c))) return rc;
+    QCSS_CUDA(c->tally.reserve(8 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 8 * sizeof(uint64_t), c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t cs = chunk_shots_for(c->n, elem_bytes, shots);
+    const int64_t cwords = cs / 64;                                   // uint64 words per plane per chunk (even)
+    const size_t row_bytes = (size_t)c->n * elem_bytes;
+    for (int i = 0; i < kSlots && shots > 0; ++i) {
+        QCSS_CUDA(c->slot_rx[i].reserve((size_t)cs * row_bytes));
+        QCSS_CUDA(c->slot_rz[i].reserve((size_t)cs * row_bytes));
+        QCSS_CUDA(c->slot_x[i].reserve((size_t)c->n * cwords * 8));
+        QCSS_CUDA(c->slot_z[i].reserve((size_t)c->n * cwords * 8));
+    }
+    int slot = 0;
+    for (int64_t s0 = 0; s0 < shots; s0 += cs, slot = (slot + 1) % kSlots) {
+        const int64_t part = shots - s0 < cs ? shots - s0 : cs;
+        cudaStream_t st = c->slot_stream[slot];
+        QCSS_CUDA(cudaMemcpyAsync(c->slot_rx[slot].p, (const uint8_t*)ex + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(cudaMemcpyAsync(c->slot_rz[slot].p, (const uint8_t*)ez + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(launch_pack_shots(c->slot_rx[slot].p, elem_bytes, c->n, part, (uint32_t*)c->slot_x[slot].p, cwords * 2, st));
+        QCSS_CUDA(launch_pack_shots(c->slot_rz[slot].p, elem_bytes, c->n, part, (uint32_t*)c->slot_z[slot].p, cwords * 2, st));
+        qcss_decode_io io;
+        memset(&io, 0, sizeof(io));
+        io.ex = (const uint64_t*)c->slot_x[slot].p;
+        io.ez = (const uint64_t*)c->slot_z[slot].p;
+        io.e_stride = cwords;
+        io.tally = (uint64_t*)c->tally.p;
+        rc = launch_decode(c, &io, part, st);
+        if (rc) {
+            for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot_stream[i]);
+            return rc;
+        }
+    }
+    for (int i = 0; i < kSlots; ++i) QCSS_CUDA(cudaStreamSynchronize(c->slot_stream[i]));
+    uint64_t h[6];
+    QCSS_CUDA(cudaMemcpy(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost));
+    tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+// One Pauli type in the reference's layout: s_out / corr_out are (shots, m) / (shots, n) bytes, flip_out / miss_out
+// (shots,) bytes; any of them may be NULL.  decode = false: syndromes only (works for codes of any size).
+static int run_shots(qcss_code* c, int which, const void* e, int elem_bytes, int64_t shots, uint8_t* s_out, uint8_t* corr_out,
+                     uint8_t* flip_out, uint8_t* miss_out, qcss_tally* tally, bool decode) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (which != 1 && which != 2) return fail(QCSS_ERR_INVALID, "which must be 1 or 2");
+    if (!e) return fail(QCSS_ERR_INVALID, "NULL errors");
+    if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
+    int rc;
+    if ((rc = check_elem(elem_bytes))) return rc;
+    if ((rc = ensure_streams(c))) return rc;
+    const int m = (which == 1) ? c->m1 : c->m2;
+    if (decode && !c->small) return fail(QCSS_ERR_UNSUPPORTED, "lookup decode covers n <= %d and m <= %d", kMaxN, kMaxM);
+    QCSS_CUDA(c->tally.reserve(8 * sizeof(uint64_t)));
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 8 * sizeof(uint64_t), c->stream));
+    const int64_t cs = chunk_shots_for(c->n > m ? c->n : m, elem_bytes, shots);
+    const int64_t cwords = cs / 64;
+    const size_t row_bytes = (size_t)c->n * elem_bytes;
+    cudaStream_t st = c->stream;
+    if (shots > 0) {
+        QCSS_CUDA(c->buf_a.reserve((size_t)cs * row_bytes));                 // raw rows
+        QCSS_CUDA(c->buf_b.reserve((size_t)c->n * cwords * 8));              // error planes
+        QCSS_CUDA(c->buf_c.reserve((size_t)(m > c->n ? m : c->n) * cwords * 8));   // syndrome or correction planes
+        QCSS_CUDA(c->buf_d.reserve((size_t)2 * cwords * 8));                 // flip, miss planes
+        QCSS_CUDA(c->buf_e.reserve((size_t)cs * (size_t)(m > c->n ? m : c->n)));   // bytes going back
+    }
+    for (int64_t s0 = 0; s0 < shots; s0 += cs) {
+        const int64_t part = shots - s0 < cs ? shots - s0 : cs;
+        QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, (const uint8_t*)e + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(launch_pack_shots(c->buf_a.p, elem_bytes, c->n, part, (uint32_t*)c->buf_b.p, cwords * 2, st));
+        if (!decode) {
+            rc = launch_syndrome(c, which, (const uint64_t*)c->buf_b.p, cwords, part, (uint64_t*)c->buf_c.p, cwords, st);
+            if (rc) { cudaStreamSynchronize(st); return rc; }
+            QCSS_CUDA(launch_unpack_planes((const uint32_t*)c->buf_c.p, cwords * 2, m, part, (uint8_t*)c->buf_e.p, st));
+            QCSS_CUDA(cudaMemcpyAsync(s_out + (size_t)s0 * m, c->buf_e.p, (size_t)part * m, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
+        qcss_decode_io io;
+        memset(&io, 0, sizeof(io));
+        io.e_stride = io.c_stride = cwords;
+        io.tally = (uint64_t*)c->tally.p;
+        uint64_t* flip = (uint64_t*)c->buf_d.p;
+        uint64_t* miss = flip + cwords;
+        QCSS_CUDA(cudaMemsetAsync(c->buf_d.p, 0, (size_t)2 * cwords * 8, st));
+        if (corr_out) QCSS_CUDA(cudaMemsetAsync(c->buf_c.p, 0, (size_t)c->n * cwords * 8, st));
+        if (which == 2) { io.ex = (const uint64_t*)c->buf_b.p; io.corr_x = corr_out ? (uint64_t*)c->buf_c.p : nullptr; io.flip_x = flip; io.miss_x = miss; }
+        else            { io.ez = (const uint64_t*)c->buf_b.p; io.corr_z = corr_out ? (uint64_t*)c->buf_c.p : nullptr; io.flip_z = flip; io.miss_z = miss; }
+        rc = launch_decode(c, &io, part, st);
+        if (rc) { cudaStreamSynchronize(st); return rc; }
+        if (corr_out) {
+            QCSS_CUDA(launch_unpack_planes((const uint32_t*)c->buf_c.p, cwords * 2, c->n, part, (uint8_t*)c->buf_e.p, st));
+            QCSS_CUDA(cudaMemcpyAsync(corr_out + (size_t)s0 * c->n, c->buf_e.p, (size_t)part * c->n, cudaMemcpyDeviceToHost, st));
+        }
+        if (flip_out) {
+            QCSS_CUDA(launch_unpack_planes((const uint32_t*)flip, cwords * 2, 1, part, (uint8_t*)c->buf_e.p, st));
+            QCSS_CUDA(cudaMemcpyAsync(flip_out + s0, c->buf_e.p, (size_t)part, cudaMemcpyDeviceToHost, st));
+        }
+        if (miss_out) {
+            QCSS_CUDA(launch_unpack_planes((const uint32_t*)miss, cwords * 2, 1, part, (uint8_t*)c->buf_e.p, st));
+            QCSS_CUDA(cudaMemcpyAsync(miss_out + s0, c->buf_e.p, (size_t)part, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    uint64_t h[6] = {0, 0, 0, 0, 0, 0};
+    QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    QCSS_CUDA(cudaStreamSynchronize(st));
+    if (tally) tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_syndrome_shots(qcss_code* c, int which, const void* e, int elem_bytes, int64_t shots, uint8_t* s_out) {
+    if (!s_out) return fail(QCSS_ERR_INVALID, "NULL output");
+    return run_shots(c, which, e, elem_bytes, shots, s_out, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+QCSS_API int qcss_decode_shots(qcss_code* c, int which, const void* e, int elem_bytes, int64_t shots, uint8_t* corr_out,
+                      uint8_t* flip_out, uint8_t* miss_out, qcss_tally* tally) {
+    return run_shots(c, which, e, elem_bytes, shots, nullptr, corr_out, flip_out, miss_out, tally, true);
+}
+
+// ---- sparse batches ----------------------------------------------------------------------------------------------
+
+QCSS_API int qcss_decode_xz_sparse_dev(qcss_code* c, const uint64_t* d_events, int64_t n_events, int64_t shots, uint64_t* d_tally,
+                              int32_t* d_status, void* stream) {
+    if (!c || !d_tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    if (n_events < 0 || shots < 0) return fail(QCSS_ERR_INVALID, "negative count");
+    if (n_events > 0 && !d_events) return fail(QCSS_ERR_INVALID, "NULL events");
+    uint32_t f0x, f0z;
+    int rc = sparse_ready(c, &f0x, &f0z);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* aux = nullptr;
+    QCSS_CUDA(cudaMallocAsync((void**)&aux, 2 * sizeof(unsigned long long), st));
+    cudaError_t e = cudaMemsetAsync(aux, 0, 2 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess)
+        e = launch_decode_events(c->side_x, c->rows_x, c->lmask_x, c->side_z, c->rows_z, c->lmask_z,
+                                 (const unsigned long long*)d_events, n_events, shots, (unsigned long long*)d_tally, aux, st);
+    if (e == cudaSuccess) {
+        k_events_finish<<<1, 1, 0, st>>>((unsigned long long*)d_tally, aux, (unsigned long long)shots, f0x, f0z, d_status);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(aux, st);
+    QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_decode_xz_sparse(qcss_code* c, const uint64_t* events, int64_t n_events, int64_t shots, qcss_tally* tally) {
+    if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
+    if (n_events < 0 || shots < 0) return fail(QCSS_ERR_INVALID, "negative count");
+    if (n_events > 0 && !events) return fail(QCSS_ERR_INVALID, "NULL events");
+    uint32_t f0x, f0z;
+    int rc = sparse_ready(c, &f0x, &f0z);
+    if (rc) return rc;
+    if ((rc = ensure_streams(c))) return rc;
+    QCSS_CUDA(c->tally.reserve(8 * sizeof(uint64_t)));                   // 6 tallies, event-shot count, status bits
+    QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 8 * sizeof(uint64_t), c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t chunk = (int64_t)4 << 20;                             // events per chunk (32 MB)
+    const int64_t first = n_events < chunk ? n_events : chunk;
+    for (int i = 0; i < kSlots && n_events > 0; ++i) QCSS_CUDA(c->slot_rx[i].reserve((size_t)first * 8));
+    unsigned long long* d_tally = (unsigned long long*)c->tally.p;
+    int slot = 0;
+    for (int64_t pos = 0; pos < n_events; slot = (slot + 1) % kSlots) {
+        int64_t end = pos + chunk < n_events ? pos + chunk : n_events;
+        // a shot's events stay in one chunk: move the cut back to the start of the shot it would split
+        while (end < n_events && end > pos && (events[end] >> 18) == (events[end - 1] >> 18)) --end;
+        if (end == pos) {
+            for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot_stream[i]);
+            return fail(QCSS_ERR_INVALID, "shot %llu has more than %lld events", (unsigned long long)(events[pos] >> 18), (long long)chunk);
+        }
+        if (end < n_events && (events[end - 1] >> 18) > (events[end] >> 18)) {
+            for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot_stream[i]);
+            return fail(QCSS_ERR_INVALID, "events must be sorted by shot (event %lld)", (long long)end);
+        }
+        cudaStream_t st = c->slot_stream[slot];
+        QCSS_CUDA(cudaMemcpyAsync(c->slot_rx[slot].p, events + pos, (size_t)(end - pos) * 8, cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(launch_decode_events(c->side_x, c->rows_x, c->lmask_x, c->side_z, c->rows_z, c->lmask_z,
+                                       (const unsigned long long*)c->slot_rx[slot].p, end - pos, shots, d_tally, d_tally + 6, st));
+        pos = end;
+    }
+    for (int i = 0; i < kSlots; ++i) QCSS_CUDA(cudaStreamSynchronize(c->slot_stream[i]));
+    k_events_finish<<<1, 1, 0, c->stream>>>(d_tally, d_tally + 6, (unsigned long long)shots, f0x, f0z, nullptr);
+    QCSS_CUDA(cudaGetLastError());
+    uint64_t h[8];
+    QCSS_CUDA(cudaMemcpyAsync(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    if (h[7] & 1) return fail(QCSS_ERR_INVALID, "an event names a qubit >= n, a shot >= shots or Pauli type 0");
+    if (h[7] & 2) return fail(QCSS_ERR_INVALID, "events must be sorted by shot");
+    tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_events_from_planes_dev(qcss_code* c, const uint64_t* d_ex, const uint64_t* d_ez, int64_t e_stride, int64_t shots,
+                                int64_t first_shot, uint64_t* d_events, int64_t capacity, uint64_t* d_count, void* stream) {
+    if (!c || !d_count) return fail(QCSS_ERR_INVALID, "NULL argument");
+    if (capacity < 0 || first_shot < 0 || (capacity > 0 && !d_events)) return fail(QCSS_ERR_INVALID, "bad event buffer");
+    if (c->n > 65535 || (uint64_t)(first_shot + shots) >> 46) return fail(QCSS_ERR_UNSUPPORTED, "event fields overflow");
+    int rc;
+    if ((rc = check_planes(d_ex, e_stride, shots, "ex planes"))) return rc;
+    if ((rc = check_planes(d_ez, e_stride, shots, "ez planes"))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = 1184;
+    unsigned long long* work = nullptr;
+    QCSS_CUDA(cudaMallocAsync((void**)&work, (size_t)(ctas + 1) * sizeof(unsigned long long), st));
+    const cudaError_t e = launch_events_from_planes((const uint32_t*)d_ex, (const uint32_t*)d_ez, c->n, e_stride * 2,
+                                                    (shots + 31) / 32, tail_mask_for(shots), first_shot,
+                                                    (unsigned long long*)d_events, capacity, (unsigned long long*)d_count, work,
+                                                    ctas, st);
+    cudaFreeAsync(work, st);
+    QCSS_CUDA(e);
     return QCSS_OK;
 }
 

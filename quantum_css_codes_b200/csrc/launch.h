@@ -95,6 +95,18 @@ int64_t table_count(const TableBuild* tb);
 cudaError_t table_read(const TableBuild* tb, int64_t* keys, uint64_t* supports);
 void table_free(TableBuild* tb);
 
+// host data formats (format_kernels.cu): the reference's (shots, n) arrays <-> bit planes, sparse event lists
+cudaError_t launch_pack_shots(const void* d_src, int elem_bytes, int n, int64_t shots, uint32_t* d_planes, int64_t stride32,
+                              cudaStream_t stream);
+cudaError_t launch_unpack_planes(const uint32_t* d_planes, int64_t stride32, int m, int64_t shots, uint8_t* d_dst,
+                                 cudaStream_t stream);
+cudaError_t launch_decode_events(const GenericSide& x, const uint32_t* rows_x, uint32_t lmask_x, const GenericSide& z,
+                                 const uint32_t* rows_z, uint32_t lmask_z, const unsigned long long* d_events, int64_t count,
+                                 int64_t shots, unsigned long long* d_tally, unsigned long long* d_aux, cudaStream_t stream);
+cudaError_t launch_events_from_planes(const uint32_t* d_ex, const uint32_t* d_ez, int n, int64_t stride32, int64_t words,
+                                      uint32_t tail_mask, int64_t first_shot, unsigned long long* d_events, int64_t capacity,
+                                      unsigned long long* d_count, unsigned long long* d_work, int ctas, cudaStream_t stream);
+
 // per-syndrome histogram over syndrome planes (hist_kernels.cu)
 cudaError_t launch_syndrome_hist(const uint32_t* s, int64_t s_stride, int m, int64_t words, uint32_t tail_mask,
                                  unsigned long long* hist, cudaStream_t stream);

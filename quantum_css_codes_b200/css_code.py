@@ -243,29 +243,25 @@ class _DevicePath:
     def syndromes(self, errors, which):
         """Batched ``np.mod(np.matmul(parity_check, e), 2)`` (css_code.py:728) for a
         (shots, n) 0/1 array; returns (shots, m) uint8."""
-        errors = np.asarray(errors)
-        shots = errors.shape[0]
-        h, _ = self._side(which)
-        s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
-        return _planes.unpack_planes(s_planes, shots)[:, :h.shape[0]]
+        self._side(which)
+        return self.device.syndrome_shots(errors, which)       # transposed to bit planes on the device
 
     def decode(self, errors, which):
         """Lookup-decode a (shots, n) batch of one Pauli type with the semantics of
         quil_classical_correct (css_code.py:649-685): correction = table.get(key, 0).
         Returns dict(correction (shots, n), flip (shots,), miss (shots,), tally)."""
-        errors = np.asarray(errors)
-        shots = errors.shape[0]
-        corr, flip, miss, tally = self.device.decode_planes(_planes.pack_planes(errors), shots, which)
-        return dict(correction=_planes.unpack_planes(corr, shots),
-                    flip=_planes.unpack_plane(flip, shots),
-                    miss=_planes.unpack_plane(miss, shots), tally=tally)
+        corr, flip, miss, tally = self.device.decode_shots(errors, which)
+        return dict(correction=corr, flip=flip, miss=miss, tally=tally)
 
     def decode_xz(self, x_errors, z_errors):
         """Tallies (shots, fail_x, fail_z, fail_any, miss_x, miss_z) for a shared batch."""
-        x_errors, z_errors = np.asarray(x_errors), np.asarray(z_errors)
-        shots = x_errors.shape[0]
-        return self.device.decode_xz_planes(_planes.pack_planes(x_errors),
-                                            _planes.pack_planes(z_errors), shots)
+        return self.device.decode_xz_shots(x_errors, z_errors)
+
+    def decode_xz_sparse(self, events, shots):
+        """The same tallies for a batch given in sparse form: uint64 events ``shot << 18 | qubit << 2 | pauli``
+        sorted by shot (``planes.events_from_arrays``); 30x fewer bytes than bit planes at p = 1e-3 and
+        event-driven on the device (``qcss_decode_xz_sparse``)."""
+        return self.device.decode_xz_sparse(events, shots)
 
     def monte_carlo(self, p, shots, seed=0, first_shot=0):
         """Depolarising-noise Monte Carlo fully on the device (sampler fused into the decode
@@ -469,11 +465,7 @@ class SyndromeCode:
         return self._device_code
 
     def syndromes(self, errors, which):
-        errors = np.asarray(errors)
-        shots = errors.shape[0]
-        m = (self.parity_check_c1 if which == 1 else self.parity_check_c2).shape[0]
-        s_planes = self.device.syndrome_planes(_planes.pack_planes(errors), shots, which)
-        return _planes.unpack_planes(s_planes, shots)[:, :m]
+        return self.device.syndrome_shots(errors, which)
 
     def sample_syndromes(self, p, shots, seed=0, first_shot=0, return_errors=False):
         """Depolarising(p) errors drawn on the device and turned into syndromes in the same kernel

@@ -81,3 +81,24 @@ def planes_to_tiles(planes, shots):
     take = min(planes.shape[1], tiles * TILE_WORDS)
     padded[:, :take] = planes[:, :take]
     return np.ascontiguousarray(padded.reshape(n, tiles, TILE_WORDS).transpose(1, 0, 2))
+
+
+def events_from_arrays(x_errors, z_errors, first_shot=0):
+    """Sparse form of a batch: uint64 events ``shot << 18 | qubit << 2 | pauli`` (pauli 1 = X, 2 = Z, 3 = Y), sorted by
+    shot then qubit -- the input of ``qcss_decode_xz_sparse`` -- from two (shots, n) 0/1 arrays."""
+    pauli = (np.asarray(x_errors) & 1).astype(np.uint64) | ((np.asarray(z_errors) & 1).astype(np.uint64) << np.uint64(1))
+    shot, qubit = np.nonzero(pauli)
+    return ((shot.astype(np.uint64) + np.uint64(first_shot)) << np.uint64(18)) | (qubit.astype(np.uint64) << np.uint64(2)) \
+        | pauli[shot, qubit]
+
+
+def arrays_from_events(events, shots, n, first_shot=0):
+    """Inverse of ``events_from_arrays`` (repeated events compose by XOR): two (shots, n) uint8 arrays."""
+    events = np.asarray(events, dtype=np.uint64)
+    shot = (events >> np.uint64(18)).astype(np.int64) - first_shot
+    qubit = ((events >> np.uint64(2)) & np.uint64(0xFFFF)).astype(np.int64)
+    ex = np.zeros((shots, n), dtype=np.uint8)
+    ez = np.zeros((shots, n), dtype=np.uint8)
+    np.bitwise_xor.at(ex, (shot, qubit), (events & np.uint64(1)).astype(np.uint8))
+    np.bitwise_xor.at(ez, (shot, qubit), ((events >> np.uint64(1)) & np.uint64(1)).astype(np.uint8))
+    return ex, ez

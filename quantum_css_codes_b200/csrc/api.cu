@@ -1401,6 +1401,8 @@ static int run_shots(qcss_code* c, int which, const void* e, int elem_bytes, int
     const int64_t cwords = cs / 64;
     const size_t row_bytes = (size_t)c->n * elem_bytes;
     cudaStream_t st = c->stream;
+    const bool tiles = !c->small && !((which == 1) ? c->dense1 : c->dense2) &&
+                       syndrome_tiles_supported((which == 1) ? c->sp1 : c->sp2);
     if (shots > 0) {
         QCSS_CUDA(c->buf_a.reserve((size_t)cs * row_bytes));                 // raw rows
         QCSS_CUDA(c->buf_b.reserve((size_t)c->n * cwords * 8));              // error planes
@@ -1412,6 +1414,16 @@ static int run_shots(qcss_code* c, int which, const void* e, int elem_bytes, int
         const int64_t part = shots - s0 < cs ? shots - s0 : cs;
         QCSS_CUDA(cudaMemcpyAsync(c->buf_a.p, (const uint8_t*)e + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
                                   cudaMemcpyHostToDevice, st));
+        if (!decode && tiles) {
+            // sparse any-size codes: the rows are transposed straight into the tile-major layout the bulk-copy ring
+            // streams at 90-100 % of the HBM copy rate, and the syndromes come back out of it
+            QCSS_CUDA(launch_pack_shots(c->buf_a.p, elem_bytes, c->n, part, (uint32_t*)c->buf_b.p, 0, st));
+            rc = launch_syndrome_tiles_checked(c, which, (const uint64_t*)c->buf_b.p, part, (uint64_t*)c->buf_c.p, st);
+            if (rc) { cudaStreamSynchronize(st); return rc; }
+            QCSS_CUDA(launch_unpack_planes((const uint32_t*)c->buf_c.p, 0, m, part, (uint8_t*)c->buf_e.p, st));
+            QCSS_CUDA(cudaMemcpyAsync(s_out + (size_t)s0 * m, c->buf_e.p, (size_t)part * m, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
         QCSS_CUDA(launch_pack_shots(c->buf_a.p, elem_bytes, c->n, part, (uint32_t*)c->buf_b.p, cwords * 2, st));
         if (!decode) {
             rc = launch_syndrome(c, which, (const uint64_t*)c->buf_b.p, cwords, part, (uint64_t*)c->buf_c.p, cwords, st);

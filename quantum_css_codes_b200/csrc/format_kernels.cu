@@ -29,10 +29,13 @@ constexpr int kSegCols = 64;               // wider arrays: 64 columns per pass,
 constexpr int kSegPitch = kSegCols + 4;
 
 // ---- (shots, n) elements -> planes -------------------------------------------------------------------
-// grid-stride over (block of 1024 shots, column chunk); planes[j * stride32 + word]
+// grid-stride over (block of 1024 shots, column chunk).  Word g of column j of block b goes to
+// planes[j * pstride + b * bstride + g]: plane-major (pstride = words per plane, bstride = 32, limit = words per
+// plane) or tile-major [block][column][32 words] (pstride = 32, bstride = 32 n, limit = 32).
 template <int EB>
 __global__ void __launch_bounds__(kFmtThreads)
-k_pack_shots(const uint8_t* __restrict__ src, int n, int64_t shots, uint32_t* __restrict__ planes, int64_t stride32) {
+k_pack_shots(const uint8_t* __restrict__ src, int n, int64_t shots, uint32_t* __restrict__ planes, int64_t pstride,
+             int64_t bstride, int64_t limit) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const bool flat = n <= kFlatMaxN;
     const int jc = flat ? n : kSegCols, pitch = flat ? n : kSegPitch;
@@ -85,10 +88,10 @@ k_pack_shots(const uint8_t* __restrict__ src, int n, int64_t shots, uint32_t* __
             }
         }
         __syncthreads();
-        const int64_t w0 = s0 / 32;
+        const int64_t w0 = blk * bstride, wl = (limit == 32 && pstride == 32) ? 0 : blk * 32;
         for (int i = tid; i < cols * 32; i += kFmtThreads) {
             const int c = i >> 5, g = i & 31;
-            if (w0 + g < stride32) planes[(int64_t)(j0 + c) * stride32 + w0 + g] = outw[i];
+            if (wl + g < limit) planes[(int64_t)(j0 + c) * pstride + w0 + g] = outw[i];
         }
         __syncthreads();
     }
@@ -96,7 +99,8 @@ k_pack_shots(const uint8_t* __restrict__ src, int n, int64_t shots, uint32_t* __
 
 // ---- planes -> (shots, m) bytes ------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFmtThreads)
-k_unpack_planes(const uint32_t* __restrict__ planes, int64_t stride32, int m, int64_t shots, uint8_t* __restrict__ dst) {
+k_unpack_planes(const uint32_t* __restrict__ planes, int64_t pstride, int64_t bstride, int64_t limit, int m, int64_t shots,
+                uint8_t* __restrict__ dst) {
     extern __shared__ __align__(16) uint32_t usm[];                                 // [jc][33]
     const bool flat = m <= kFlatMaxN;
     const int jc = flat ? m : kSegCols;
@@ -107,11 +111,11 @@ k_unpack_planes(const uint32_t* __restrict__ planes, int64_t stride32, int m, in
         const int64_t blk = item / chunks;
         const int j0 = (int)(item % chunks) * kSegCols;
         const int cols = (m - j0) < jc ? (m - j0) : jc;
-        const int64_t s0 = blk * kBlockShots, w0 = s0 / 32;
+        const int64_t s0 = blk * kBlockShots, w0 = blk * bstride, wl = (limit == 32 && pstride == 32) ? 0 : blk * 32;
         const int rows = (int)((shots - s0) < kBlockShots ? (shots - s0) : kBlockShots);
         for (int i = tid; i < cols * 32; i += kFmtThreads) {
             const int c = i >> 5, g = i & 31;
-            usm[c * 33 + g] = (w0 + g < stride32) ? __ldcs(planes + (int64_t)(j0 + c) * stride32 + w0 + g) : 0u;
+            usm[c * 33 + g] = (wl + g < limit) ? __ldcs(planes + (int64_t)(j0 + c) * pstride + w0 + g) : 0u;
         }
         __syncthreads();
         if (flat) {
@@ -299,9 +303,11 @@ int fmt_grid(int64_t items) {
 
 }  // namespace
 
+// stride32 > 0: plane-major with that many 32-bit words per plane; stride32 == 0: tile-major [tile][column][32 words]
 cudaError_t launch_pack_shots(const void* d_src, int elem_bytes, int n, int64_t shots, uint32_t* d_planes, int64_t stride32,
                               cudaStream_t stream) {
     if (shots <= 0 || n <= 0) return cudaSuccess;
+    const int64_t pstride = stride32 ? stride32 : 32, bstride = stride32 ? 32 : (int64_t)32 * n, limit = stride32 ? stride32 : 32;
     const bool flat = n <= kFlatMaxN;
     const int pitch = flat ? n : kSegPitch, jc = flat ? n : kSegCols;
     const size_t smem = (((size_t)kBlockShots * pitch + 15) & ~(size_t)15) + (size_t)jc * 32 * 4;
@@ -309,10 +315,10 @@ cudaError_t launch_pack_shots(const void* d_src, int elem_bytes, int n, int64_t 
     cudaError_t err;
     if (elem_bytes == 1) {
         if ((err = cudaFuncSetAttribute(k_pack_shots<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-        k_pack_shots<1><<<fmt_grid(items), kFmtThreads, smem, stream>>>((const uint8_t*)d_src, n, shots, d_planes, stride32);
+        k_pack_shots<1><<<fmt_grid(items), kFmtThreads, smem, stream>>>((const uint8_t*)d_src, n, shots, d_planes, pstride, bstride, limit);
     } else if (elem_bytes == 8) {
         if ((err = cudaFuncSetAttribute(k_pack_shots<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-        k_pack_shots<8><<<fmt_grid(items), kFmtThreads, smem, stream>>>((const uint8_t*)d_src, n, shots, d_planes, stride32);
+        k_pack_shots<8><<<fmt_grid(items), kFmtThreads, smem, stream>>>((const uint8_t*)d_src, n, shots, d_planes, pstride, bstride, limit);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -322,10 +328,11 @@ cudaError_t launch_pack_shots(const void* d_src, int elem_bytes, int n, int64_t 
 cudaError_t launch_unpack_planes(const uint32_t* d_planes, int64_t stride32, int m, int64_t shots, uint8_t* d_dst,
                                  cudaStream_t stream) {
     if (shots <= 0 || m <= 0) return cudaSuccess;
+    const int64_t pstride = stride32 ? stride32 : 32, bstride = stride32 ? 32 : (int64_t)32 * m, limit = stride32 ? stride32 : 32;
     const bool flat = m <= kFlatMaxN;
     const size_t smem = (size_t)(flat ? m : kSegCols) * 33 * 4;
     const int64_t items = ((shots + kBlockShots - 1) / kBlockShots) * (flat ? 1 : (m + kSegCols - 1) / kSegCols);
-    k_unpack_planes<<<fmt_grid(items), kFmtThreads, smem, stream>>>(d_planes, stride32, m, shots, d_dst);
+    k_unpack_planes<<<fmt_grid(items), kFmtThreads, smem, stream>>>(d_planes, pstride, bstride, limit, m, shots, d_dst);
     return cudaGetLastError();
 }
 

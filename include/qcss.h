@@ -121,6 +121,13 @@ QCSS_API int qcss_code_kernel_name(const qcss_code* code, char* buf, int buflen)
  * the generic kernels. */
 QCSS_API int qcss_code_spec_source(const qcss_code* code, char* buf, int64_t cap, int64_t* needed);
 QCSS_API int qcss_code_load_specialized(qcss_code* code, const char* so_path, const char* tag);
+/* The same specialisation IN PROCESS, with no toolkit and no subprocess on the box: the translation unit is compiled
+ * by NVRTC (libnvrtc.so.12, opened with dlopen: `nvrtc_path`, or the loader's search path and /usr/local/cuda/lib64
+ * when NULL) against the kernel headers embedded in this library, the cubin is loaded with cudaLibraryLoadData and
+ * cached in `cache_dir` (NULL = no disk cache) under the hash of source and headers.  ~10 s per distinct code the
+ * first time.  qcss_code_kernel_name then reports "small-static(nvrtc:<tag>)".  QCSS_ERR_UNSUPPORTED when the code is
+ * not decodable or libnvrtc cannot be found. */
+QCSS_API int qcss_code_specialize(qcss_code* code, const char* nvrtc_path, const char* cache_dir);
 
 /* ---- K1 syndrome: replaces np.mod(np.matmul(parity_check, e), 2), css_code.py:728 ------- */
 QCSS_API int qcss_syndrome(qcss_code* code, int which, const uint64_t* e_planes, int64_t e_stride,

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "qcss_code_spec_source": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64,
                                              ctypes.POINTER(ctypes.c_int64)]),
     "qcss_code_load_specialized": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]),
+    "qcss_code_specialize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]),
     "qcss_syndrome": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
     "qcss_syndrome_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,

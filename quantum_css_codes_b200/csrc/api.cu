@@ -2,6 +2,7 @@
 // host-buffer entry points that stream caller memory through the GPU.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -15,6 +16,7 @@
 #include "../../include/qcss.h"
 #include "launch.h"
 #include "options.h"
+#include "small_common.cuh"      // NamedArgs, launch-shape helpers (no kernel is instantiated in this file)
 
 using namespace qcss;
 
@@ -71,6 +73,9 @@ constexpr int64_t kMaxShotsPerLaunch = (int64_t)1 << 38;
 
 }  // namespace
 
+struct SpecKernels;
+void spec_rtc_free(SpecKernels* k);
+
 struct qcss_code {
     int n = 0, m1 = 0, m2 = 0;
     bool small = false;                 // register-resident kernels apply (n <= 32, m <= 16)
@@ -80,6 +85,7 @@ struct qcss_code {
     uint32_t fm0_x = 0, fm0_z = 0;      // table byte of the zero syndrome (bit0 L.correction, bit1 miss)
     int named_id = -1;
     // kernels compiled for THIS code (qcss_code_spec_source -> nvcc -> qcss_code_load_specialized)
+    struct SpecKernels* rtc = nullptr;  // kernels compiled in-process with NVRTC (qcss_code_specialize)
     void* spec_dl = nullptr;
     int (*spec_launch)(const void* small_launch, void* stream) = nullptr;
     char spec_tag[32] = "";
@@ -99,8 +105,11 @@ struct qcss_code {
 
 namespace {
 
+cudaError_t launch_spec_rtc(const SpecKernels& k, const SmallLaunch& l, cudaStream_t stream);
+
 // static kernels of a matching descriptor, kernels compiled for this code, or the generic ones
 cudaError_t launch_small_any(const qcss_code* c, const SmallLaunch& l, cudaStream_t stream) {
+    if (c->rtc != nullptr && l.named_id < 0) return launch_spec_rtc(*c->rtc, l, stream);
     if (c->spec_launch != nullptr && l.named_id < 0) return (cudaError_t)c->spec_launch(&l, stream);
     return launch_small(l, stream);
 }
@@ -571,6 +580,7 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
     c->tally.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->spec_dl) dlclose(c->spec_dl);
+    spec_rtc_free(c->rtc);
     delete c;
     return QCSS_OK;
 }
@@ -583,6 +593,8 @@ QCSS_API int qcss_code_kernel_name(const qcss_code* c, char* buf, int buflen) {
         snprintf(buf, buflen, "tiled-sparse(n=%d)", c->n);
     else if (c->named_id >= 0)
         snprintf(buf, buflen, "small-static(%s)", named_name(c->named_id));
+    else if (c->rtc != nullptr)
+        snprintf(buf, buflen, "small-static(nvrtc:%s)", c->spec_tag);
     else if (c->spec_launch != nullptr)
         snprintf(buf, buflen, "small-static(jit:%s)", c->spec_tag);
     else
@@ -1564,6 +1576,253 @@ QCSS_API int qcss_events_from_planes_dev(qcss_code* c, const uint64_t* d_ex, con
                                                     ctas, st);
     cudaFreeAsync(work, st);
     QCSS_CUDA(e);
+    return QCSS_OK;
+}
+
+}  // extern "C"
+
+// ---- in-process specialisation with NVRTC -----------------------------------------------------
+// The static kernel family for ANY decodable code without a toolkit on the box: the descriptor translation unit is
+// compiled by libnvrtc inside this process from headers EMBEDDED in the library (csrc/build/embedded_headers.inc,
+// generated by build.py from core.cuh / decode.cuh / small_common.cuh, which compile under __CUDACC_RTC__ without any
+// system header), loaded with cudaLibraryLoadData and launched through cudaKernel_t handles with the same launch
+// shapes as small::launch_named.  The cubin is cached on disk by content hash.
+
+#include <nvrtc.h>
+
+#include "build/embedded_headers.inc"
+
+struct SpecKernels {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t fast = nullptr, full = nullptr, s_fast = nullptr, s_full = nullptr, gapq = nullptr;
+    bool x_sliced = false, z_sliced = false;
+    int gapq_w = 1;
+    size_t gapq_smem = 0;
+};
+
+void spec_rtc_free(SpecKernels* k) {
+    if (!k) return;
+    if (k->lib) cudaLibraryUnload(k->lib);
+    delete k;
+}
+
+namespace {
+
+struct Nvrtc {
+    void* dl = nullptr;
+    nvrtcResult (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*log_size)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*log)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*cubin)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*destroy)(nvrtcProgram*) = nullptr;
+};
+
+int nvrtc_open(const char* path, Nvrtc* nv) {
+    const char* tries[] = {path, "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+    for (const char* t : tries) {
+        if (t == nullptr || *t == 0) continue;
+        nv->dl = dlopen(t, RTLD_NOW | RTLD_LOCAL);
+        if (nv->dl) break;
+    }
+    if (!nv->dl) return fail(QCSS_ERR_UNSUPPORTED, "libnvrtc not found (pass its path): %s", dlerror());
+#define QCSS_NVRTC_SYM(field, name)                                                   \
+    nv->field = reinterpret_cast<decltype(nv->field)>(dlsym(nv->dl, name));            \
+    if (!nv->field) return fail(QCSS_ERR_UNSUPPORTED, "libnvrtc lacks %s", name);
+    QCSS_NVRTC_SYM(create, "nvrtcCreateProgram")
+    QCSS_NVRTC_SYM(compile, "nvrtcCompileProgram")
+    QCSS_NVRTC_SYM(log_size, "nvrtcGetProgramLogSize")
+    QCSS_NVRTC_SYM(log, "nvrtcGetProgramLog")
+    QCSS_NVRTC_SYM(cubin_size, "nvrtcGetCUBINSize")
+    QCSS_NVRTC_SYM(cubin, "nvrtcGetCUBIN")
+    QCSS_NVRTC_SYM(destroy, "nvrtcDestroyProgram")
+#undef QCSS_NVRTC_SYM
+    return QCSS_OK;
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char ch : s) { h ^= ch; h *= 1099511628211ull; }
+    return h;
+}
+
+// source -> cubin for sm_100a (QCSS_ERR_INVALID with the compiler log on failure)
+int nvrtc_compile(const Nvrtc& nv, const std::string& src, std::vector<char>* cubin) {
+    nvrtcProgram prog = nullptr;
+    if (nv.create(&prog, src.c_str(), "qcss_spec.cu", kEmbeddedHeaderCount, kEmbeddedHeaderText, kEmbeddedHeaderName) != NVRTC_SUCCESS)
+        return fail(QCSS_ERR_CUDA, "nvrtcCreateProgram failed");
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device"};
+    const nvrtcResult r = nv.compile(prog, 3, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nv.log_size(prog, &n);
+        std::vector<char> log(n + 1, 0);
+        nv.log(prog, log.data());
+        nv.destroy(&prog);
+        return fail(QCSS_ERR_INVALID, "NVRTC compilation failed: %.400s", log.data());
+    }
+    size_t n = 0;
+    nv.cubin_size(prog, &n);
+    cubin->assign(n, 0);
+    nv.cubin(prog, cubin->data());
+    nv.destroy(&prog);
+    return QCSS_OK;
+}
+
+cudaError_t launch_one_rt(cudaKernel_t kernel, const small::NamedArgs& args, int64_t units, size_t smem, cudaStream_t stream) {
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    int sms = 0;
+    cudaError_t e = small::sm_count(&sms);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, small::kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (units + small::kThreads - 1) / small::kThreads, wave = (int64_t)sms * per_sm;
+    int64_t grid = want < wave ? want : wave;
+    if (grid < 1) grid = 1;
+    void* params[1] = {const_cast<small::NamedArgs*>(&args)};
+    return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(small::kThreads), params, smem, stream);
+}
+
+// small::launch_split with runtime kernel handles: whole units through FAST, the ragged rest through FULL
+cudaError_t launch_split_rt(int vec, cudaKernel_t kfast, cudaKernel_t kfull, small::NamedArgs a, const SmallLaunch& l,
+                            size_t smem_fast, size_t smem, cudaStream_t stream) {
+    const DecodeIO io = l.io;
+    int64_t fast_units = 0;
+    if (small::fast_eligible(l)) {
+        const int64_t whole_words = (io.tail_mask == 0xFFFFFFFFu) ? io.words : io.words - 1;
+        fast_units = whole_words / vec;
+    }
+    if (fast_units > 0) {
+        a.io = io;
+        a.io.words = fast_units * vec;
+        a.io.tail_mask = 0xFFFFFFFFu;
+        const cudaError_t e = launch_one_rt(kfast, a, fast_units, smem_fast, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int64_t done = fast_units * vec;
+    if (done < io.words) {
+        a.io = io;
+        a.io.words = io.words - done;
+        a.io.first_word = io.first_word + (uint64_t)done;
+        if (a.io.ex) a.io.ex += done;
+        if (a.io.ez) a.io.ez += done;
+        if (a.io.synd_x) a.io.synd_x += done;
+        if (a.io.synd_z) a.io.synd_z += done;
+        if (a.io.corr_x) a.io.corr_x += done;
+        if (a.io.corr_z) a.io.corr_z += done;
+        if (a.io.flip_x) a.io.flip_x += done;
+        if (a.io.flip_z) a.io.flip_z += done;
+        if (a.io.miss_x) a.io.miss_x += done;
+        if (a.io.miss_z) a.io.miss_z += done;
+        if (a.io.ex_out) a.io.ex_out += done;
+        if (a.io.ez_out) a.io.ez_out += done;
+        return launch_one_rt(kfull, a, (a.io.words + vec - 1) / vec, smem, stream);
+    }
+    return cudaSuccess;
+}
+
+// small::launch_named for the in-process kernels
+cudaError_t launch_spec_rtc(const SpecKernels& k, const SmallLaunch& l, cudaStream_t stream) {
+    small::NamedArgs a;
+    a.fm_x = l.x->lut_fm;
+    a.co_x = l.x->lut_corr;
+    a.e32_x = l.x->lut_e32;
+    a.fm_z = l.z->lut_fm;
+    a.co_z = l.z->lut_corr;
+    a.e32_z = l.z->lut_e32;
+    a.io = l.io;
+    const size_t smem = small::lut_smem(*l.x, *l.z, !k.x_sliced, !k.z_sliced, false);
+    const size_t smem_fast = small::lut_smem(*l.x, *l.z, !k.x_sliced, !k.z_sliced, true);
+    if (l.sample && l.io.use_gap && l.gapq)
+        return launch_split_rt(k.gapq_w, k.gapq, k.s_full, a, l, smem_fast + k.gapq_smem, smem, stream);
+    if (l.sample) return launch_split_rt(1, k.s_fast, k.s_full, a, l, smem_fast, smem, stream);
+    return launch_split_rt(4, k.fast, k.full, a, l, smem_fast, smem, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+QCSS_API int qcss_code_specialize(qcss_code* c, const char* nvrtc_path, const char* cache_dir) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (!c->small || c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
+        return fail(QCSS_ERR_UNSUPPORTED, "specialisation needs a decodable code (n <= %d, m <= %d, both tables)", kMaxN, kMaxM);
+    std::string src = "#include \"small_common.cuh\"\nnamespace qcss {\nnamespace spec {\n";
+    emit_side(src, "Spec_X", c->side_x, c->rows_x, c->lmask_x);
+    emit_side(src, "Spec_Z", c->side_z, c->rows_z, c->lmask_z);
+    src += "}\n}\nusing namespace qcss;\n";
+    const char* decl = "extern \"C\" __global__ void __launch_bounds__(256, %d) %s(const __grid_constant__ small::NamedArgs a) { %s(a); }\n";
+    char line[512];
+    snprintf(line, sizeof(line), decl, 2, "spec_fast", "small::named_body<spec::Spec_X, spec::Spec_Z, 4, false, true>"); src += line;
+    snprintf(line, sizeof(line), decl, 1, "spec_full", "small::named_body<spec::Spec_X, spec::Spec_Z, 4, false, false>"); src += line;
+    snprintf(line, sizeof(line), decl, 3, "spec_sample_fast", "small::named_body<spec::Spec_X, spec::Spec_Z, 1, true, true>"); src += line;
+    snprintf(line, sizeof(line), decl, 1, "spec_sample_full", "small::named_body<spec::Spec_X, spec::Spec_Z, 1, true, false>"); src += line;
+    snprintf(line, sizeof(line), decl, 3, "spec_gapq", "small::named_gapq_body<spec::Spec_X, spec::Spec_Z>"); src += line;
+
+    uint64_t h = fnv1a(src);
+    for (int i = 0; i < kEmbeddedHeaderCount; ++i) h = fnv1a(kEmbeddedHeaderText[i], h);
+    char tag[32];
+    snprintf(tag, sizeof(tag), "%016llx", (unsigned long long)h);
+    std::vector<char> cubin;
+    std::string cache_file;
+    if (cache_dir != nullptr && *cache_dir) {
+        cache_file = std::string(cache_dir) + "/qcss_rtc_" + tag + ".cubin";
+        if (FILE* f = fopen(cache_file.c_str(), "rb")) {
+            fseek(f, 0, SEEK_END);
+            const long n = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            if (n > 0) {
+                cubin.resize((size_t)n);
+                if (fread(cubin.data(), 1, (size_t)n, f) != (size_t)n) cubin.clear();
+            }
+            fclose(f);
+        }
+    }
+    if (cubin.empty()) {
+        Nvrtc nv;
+        int rc = nvrtc_open(nvrtc_path, &nv);
+        if (rc) return rc;
+        rc = nvrtc_compile(nv, src, &cubin);
+        dlclose(nv.dl);
+        if (rc) return rc;
+        if (!cache_file.empty()) {
+            const std::string tmp = cache_file + ".tmp" + std::to_string((long)getpid());
+            if (FILE* f = fopen(tmp.c_str(), "wb")) {
+                const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+                fclose(f);
+                if (ok) rename(tmp.c_str(), cache_file.c_str());      // atomic: concurrent builders race benignly
+                else remove(tmp.c_str());
+            }
+        }
+    }
+    SpecKernels* k = new (std::nothrow) SpecKernels();
+    if (!k) return fail(QCSS_ERR_NOMEM, "out of host memory");
+    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->fast, k->lib, "spec_fast");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->full, k->lib, "spec_full");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->s_fast, k->lib, "spec_sample_fast");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->s_full, k->lib, "spec_sample_full");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->gapq, k->lib, "spec_gapq");
+    if (e != cudaSuccess) {
+        spec_rtc_free(k);
+        return fail(QCSS_ERR_CUDA, "loading the specialised kernels failed: %s", cudaGetErrorString(e));
+    }
+    // launch shapes of small::launch_named / GapqShape for the static policies of this code
+    const auto mb = [](const GenericSide& s) { return s.m <= kSlicedM ? s.m : (s.m <= 8 ? 8 : 16); };
+    k->x_sliced = c->side_x.m <= kSlicedM;
+    k->z_sliced = c->side_z.m <= kSlicedM;
+    const int rows = mb(c->side_x) + mb(c->side_z) + 2, T = small::kThreads;
+    k->gapq_w = (rows * 4 * T * 4 <= 36 * 1024) ? 4 : ((rows * 2 * T * 4 <= 48 * 1024) ? 2 : 1);
+    k->gapq_smem = (size_t)rows * k->gapq_w * T * 4 + (size_t)T * k->gapq_w * c->n * 2;
+    spec_rtc_free(c->rtc);
+    c->rtc = k;
+    snprintf(c->spec_tag, sizeof(c->spec_tag), "%.12s", tag);
     return QCSS_OK;
 }
 

@@ -8,7 +8,20 @@
 //   lookup decode errors ^= table.get(key, 0)           css_code.py:649-685 (miss => unchanged)
 //   logical check L.(e ^ c) mod 2                       css_code.py:124-161, 641-646
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (in-process specialisation, spec_nvrtc.cu): no system headers on the deployment box
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define QCSS_HD __host__ __device__ __forceinline__

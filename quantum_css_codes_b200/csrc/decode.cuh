@@ -1,10 +1,12 @@
 // Small-code (n <= 32) syndrome + lookup-decode + logical-check pipeline for one "unit" of
 // VEC 32-shot words.  Shared by the sm_100a kernels and the test-only host emulation.
 #pragma once
-#include <type_traits>
 #include "core.cuh"
 
 namespace qcss {
+
+struct TagTrue { static constexpr bool value = true; };
+struct TagFalse { static constexpr bool value = false; };
 
 struct Counters {
     uint32_t fail_x, fail_z, fail_any, miss_x, miss_z;
@@ -304,8 +306,8 @@ QCSS_HD void process_unit(const PX& px, const PZ& pz, const DecodeIO& io, int64_
                 }
             }
         };
-        if (io.use_gap) sample_all(std::true_type{});
-        else sample_all(std::false_type{});
+        if (io.use_gap) sample_all(TagTrue{});
+        else sample_all(TagFalse{});
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             ox[v] = finish_side<FAST>(px, sx[v], lex[v], lut_x, io.synd_x, io.s_stride, io.corr_x, io.c_stride,

@@ -12,12 +12,12 @@
 // ragged tail of a batch).  launch_split() sends the bulk of a tally-only batch through FAST and
 // the last < VEC*32 shots through FULL.
 #pragma once
+#include "decode.cuh"
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
-#include "decode.cuh"
 #include "launch.h"
+#endif
 
 namespace qcss {
 namespace small {
@@ -127,13 +127,20 @@ k_small_generic(const __grid_constant__ GenericArgs a) {
     run_small<GenericPolicy<NB, MB>, GenericPolicy<NB, MB>, VEC, SAMPLE, FAST>(px, pz, a.io, tx, tz);
 }
 
+// kernel bodies of the static family, shared by the templates below and by the extern "C" entry points of a
+// translation unit specialised for one code (nvcc: qcss_code_spec_source; NVRTC: spec_nvrtc.cu)
 template <class DX, class DZ, int VEC, bool SAMPLE, bool FAST>
-__global__ void __launch_bounds__(kThreads, FAST ? (SAMPLE ? 3 : 2) : 1)
-k_small_named(const __grid_constant__ NamedArgs a) {
+__device__ __forceinline__ void named_body(const NamedArgs& a) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;
     const SideTables tx{a.fm_x, a.co_x, a.e32_x}, tz{a.fm_z, a.co_z, a.e32_z};
     run_small<StaticPolicy<DX>, StaticPolicy<DZ>, VEC, SAMPLE, FAST>(px, pz, a.io, tx, tz);
+}
+
+template <class DX, class DZ, int VEC, bool SAMPLE, bool FAST>
+__global__ void __launch_bounds__(kThreads, FAST ? (SAMPLE ? 3 : 2) : 1)
+k_small_named(const __grid_constant__ NamedArgs a) {
+    named_body<DX, DZ, VEC, SAMPLE, FAST>(a);
 }
 
 // ---- fused gap sampler, CTA-wide two-phase form (Monte-Carlo tallies of the static kernels, p < 1/128) ----------
@@ -147,7 +154,7 @@ k_small_named(const __grid_constant__ NamedArgs a) {
 //      XOR the error word into the owning thread's syndrome / logical accumulators in shared memory
 //      (acc[row][thread]; rows of H and L are compile-time masks, the qubit index is the only runtime operand);
 //   3  every thread reads its accumulators back, clears them, decodes and tallies as before.
-// Bit-identical to the in-place kernel (tests compare both with the oracle); QCSS_GAPQ=0 selects the in-place one.
+// Bit-identical to the in-place kernel (tests compare both with the oracle); option "gapq" = 0 (qcss_set_option) selects the in-place one.
 // Words per thread per CTA iteration: as many as keep the accumulators within ~48 KB (the three block barriers of
 // an iteration are amortised over W * n site-words per thread: Steane 4, QRM-15 2, Golay-23 1).
 template <class PX, class PZ>
@@ -260,11 +267,16 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
 }
 
 template <class DX, class DZ>
-__global__ void __launch_bounds__(kThreads, 3)
-k_small_named_gapq(const __grid_constant__ NamedArgs a) {
+__device__ __forceinline__ void named_gapq_body(const NamedArgs& a) {
     StaticPolicy<DX> px;
     StaticPolicy<DZ> pz;
     run_small_gapq(px, pz, a.io, SideTables{a.fm_x, a.co_x, a.e32_x}, SideTables{a.fm_z, a.co_z, a.e32_z});
+}
+
+template <class DX, class DZ>
+__global__ void __launch_bounds__(kThreads, 3)
+k_small_named_gapq(const __grid_constant__ NamedArgs a) {
+    named_gapq_body<DX, DZ>(a);
 }
 
 template <int NB, int MB>
@@ -275,6 +287,7 @@ k_small_generic_gapq(const __grid_constant__ GenericArgs a) {
                    SideTables{a.z.lut_fm, a.z.lut_corr, a.z.lut_e32});
 }
 
+#if !defined(__CUDACC_RTC__)
 // ---- launch plumbing --------------------------------------------------------------------------
 inline cudaError_t sm_count(int* out) {
     static int cached = 0;
@@ -421,13 +434,18 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
                              a, l, smem_fast, smem, stream);
 }
 
+#endif  // !__CUDACC_RTC__
+
 }  // namespace small
 
+#if !defined(__CUDACC_RTC__)
 // one definition per translation unit (small_named_*.cu, small_generic*.cu)
 cudaError_t launch_small_steane(const SmallLaunch& l, cudaStream_t stream);
 cudaError_t launch_small_qrm15(const SmallLaunch& l, cudaStream_t stream);
 cudaError_t launch_small_golay23(const SmallLaunch& l, cudaStream_t stream);
 cudaError_t launch_small_generic16(const SmallLaunch& l, int mb, cudaStream_t stream);
 cudaError_t launch_small_generic32(const SmallLaunch& l, int mb, cudaStream_t stream);
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace qcss

@@ -233,12 +233,13 @@ class _DevicePath:
         errors = np.asarray(errors)
         return self.device.syndrome_hist_planes(_planes.pack_planes(errors), errors.shape[0], which)
 
-    def specialize(self):
+    def specialize(self, compiler="nvrtc"):
         """Compile and attach decode kernels specialised for this code (``specialize.py``): the static
         family that runs Steane / QRM-15 / Golay-23 at the HBM roofline, for any code with n <= 32 and
-        m <= 16.  One nvcc run per distinct code, cached on disk.  Returns the kernel family name."""
+        m <= 16.  In process with NVRTC by default (no toolkit, no subprocess; ``compiler="nvcc"`` runs nvcc);
+        one compilation per distinct code, cached on disk.  Returns the kernel family name."""
         from . import specialize as _spec
-        return _spec.specialize(self.device)
+        return _spec.specialize(self.device, compiler)
 
     def syndromes(self, errors, which):
         """Batched ``np.mod(np.matmul(parity_check, e), 2)`` (css_code.py:728) for a

@@ -2,12 +2,14 @@
 Per-code kernel specialisation: compile the static decode kernels (H, L and the m <= 5 truth tables as
 compile-time constants) for ONE code and attach them to its device object.
 
-    code = CSSCode(h1, h2); code.specialize()           # "small-static(jit:<hash>)"
+    code = CSSCode(h1, h2); code.specialize()           # "small-static(nvrtc:<hash>)"
 
-The library writes the translation unit (``qcss_code_spec_source``), nvcc builds it for sm_100a into
-``quantum_css_codes_b200/jit/qcss_spec_<hash>.so`` (cached by the hash of the source and of the kernel
-headers), and ``qcss_code_load_specialized`` routes the code's launches to it.  The three descriptors built
-into the library (Steane, QRM-15, Golay-23) are the same mechanism run ahead of time.
+Default (``compiler="nvrtc"``): ``qcss_code_specialize`` compiles the translation unit IN PROCESS with NVRTC
+against the kernel headers embedded in ``libqcss.so`` and loads the cubin -- no toolkit, no subprocess; the cubin
+is cached in ``quantum_css_codes_b200/jit/`` by content hash.  ``compiler="nvcc"`` is the round-1 route: the
+library writes the translation unit (``qcss_code_spec_source``), nvcc builds it for sm_100a into
+``jit/qcss_spec_<hash>.so`` and ``qcss_code_load_specialized`` routes the code's launches to it.  The three
+descriptors built into the library (Steane, QRM-15, Golay-23) are the same mechanism run ahead of time.
 """
 
 import ctypes
@@ -63,9 +65,30 @@ def build_spec(source):
     return so_path, tag
 
 
-def specialize(device_code):
+def find_nvrtc():
+    """Path of libnvrtc.so.12 for ``qcss_code_specialize``: the pip package torch depends on
+    (nvidia/cuda_nvrtc/lib), else None so the library tries the loader's search path and /usr/local/cuda/lib64."""
+    try:
+        import nvidia.cuda_nvrtc as pkg
+        base = os.path.join(os.path.dirname(pkg.__file__) if getattr(pkg, "__file__", None) else list(pkg.__path__)[0], "lib")
+        for name in sorted(os.listdir(base)):
+            if name.startswith("libnvrtc.so"):
+                return os.path.join(base, name)
+    except Exception:
+        pass
+    return None
+
+
+def specialize(device_code, compiler="nvrtc"):
     """Build (or reuse) and attach the specialised kernels; returns the kernel family name."""
     lib = _native.load()
+    if compiler == "nvrtc":
+        os.makedirs(JIT_DIR, exist_ok=True)
+        path = find_nvrtc()
+        _native.check(lib.qcss_code_specialize(device_code.handle, path.encode() if path else None, JIT_DIR.encode()))
+        return device_code.kernel_name()
+    if compiler != "nvcc":
+        raise ValueError("compiler must be 'nvrtc' or 'nvcc'")
     so_path, tag = build_spec(spec_source(device_code.handle))
     _native.check(lib.qcss_code_load_specialized(device_code.handle, so_path.encode(), tag.encode()))
     return device_code.kernel_name()

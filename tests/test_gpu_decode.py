@@ -152,10 +152,12 @@ def test_generic_kernels_partial_tables(n, m1, m2):
     assert got["miss_x"] == int(tall[2]["miss"].sum()) and got["miss_z"] == int(tall[1]["miss"].sum())
 
 
+@pytest.mark.parametrize("compiler", ["nvrtc", "nvcc"])
 @pytest.mark.parametrize("n,m1,m2", [(5, 2, 2), (12, 5, 4), (20, 3, 12), (32, 16, 9), (17, 8, 8)])
-def test_specialized_kernels_match_generic_and_oracle(n, m1, m2):
-    """qcss_code_spec_source -> nvcc -> qcss_code_load_specialized: kernels compiled for one code must give
-    the oracle's bits on every output (shared inputs) and the generic kernels' tallies on the fused
+def test_specialized_kernels_match_generic_and_oracle(n, m1, m2, compiler):
+    """Kernels compiled for ONE code -- in process by NVRTC (qcss_code_specialize: embedded headers -> cubin ->
+    cudaLibraryLoadData, no subprocess) or by an nvcc subprocess (qcss_code_spec_source -> qcss_code_load_specialized)
+    -- must give the oracle's bits on every output (shared inputs) and the generic kernels' tallies on the fused
     Philox run (which has no oracle for random tables beyond the sampler itself)."""
     from quantum_css_codes_b200 import specialize
     rng = np.random.default_rng(n * 100 + m1)
@@ -167,7 +169,7 @@ def test_specialized_kernels_match_generic_and_oracle(n, m1, m2):
         sides[which] = (h, {int(k): rng.integers(0, 2, size=n) for k in keys}, lrow[None, :])
     make = lambda: _native.DeviceCode(n, sides[1][0], sides[2][0], sides[1][2][0], sides[2][2][0], sides[1][1], sides[2][1])
     generic, dev = make(), make()
-    assert specialize.specialize(dev).startswith("small-static(jit:")
+    assert specialize.specialize(dev, compiler).startswith("small-static(nvrtc:" if compiler == "nvrtc" else "small-static(jit:")
     assert generic.kernel_name().startswith("small-generic")
     for shots in (1, 127, 5000, 128 * 300 + 5):
         ex = rng.integers(0, 2, size=(shots, n), dtype=np.uint8)
@@ -186,7 +188,7 @@ def test_specialized_kernels_match_generic_and_oracle(n, m1, m2):
         assert got["fail_x"] == int(tall[2]["flip"].sum()) and got["fail_z"] == int(tall[1]["flip"].sum())
         assert got["fail_any"] == int((tall[2]["flip"] | tall[1]["flip"]).sum())
     for p_err in (1e-3, 0.2):
-        assert dev.mc_run(p_err, 1 << 20, seed=5, first_shot=256) == generic.mc_run(p_err, 1 << 20, seed=5, first_shot=256)
+        assert dev.mc_run(p_err, (1 << 20) + 77, seed=5, first_shot=256) == generic.mc_run(p_err, (1 << 20) + 77, seed=5, first_shot=256)
         sx, sz = dev.mc_sample(p_err, 3000, seed=9)
         gx, gz = generic.mc_sample(p_err, 3000, seed=9)
         assert np.array_equal(sx, gx) and np.array_equal(sz, gz)
@@ -201,10 +203,15 @@ def test_specialize_through_csscode_and_cache():
     ref = ocss.build_css(hx, hz)
     assert code.device.kernel_name().startswith("small-generic")
     generic_low_p = code.monte_carlo(2e-3, 5_000_011, seed=6)            # generic kernels: in-place gap sampler
-    name = code.specialize()
-    assert name.startswith("small-static(jit:") and again.specialize() == name
+    name = code.specialize("nvcc")
+    assert name.startswith("small-static(jit:") and again.specialize("nvcc") == name
     so = [f for f in os.listdir(specialize.JIT_DIR) if name[len("small-static(jit:"):-1] in f]
     assert len(so) == 1
+    third = CSSCode(hx, hz)
+    rtc = third.specialize()                                             # default: NVRTC, in process
+    assert rtc.startswith("small-static(nvrtc:") and CSSCode(hx, hz).specialize() == rtc
+    assert any(f.startswith("qcss_rtc_") and f.endswith(".cubin") for f in os.listdir(specialize.JIT_DIR))
+    assert third.monte_carlo(2e-3, 5_000_011, seed=6) == generic_low_p
     rng = np.random.default_rng(9)
     ex, ez = omc.sample_depolarizing(rng, 20000, code.n, 0.1)
     assert code.decode_xz(ex, ez) == omc.tally_xz(ref, ex, ez)

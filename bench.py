@@ -53,7 +53,7 @@ LOP3_PEAK = 1.8471e13             # 32-bit lane-ops/s (LOP3 / IMAD / SHF / PRMT 
 ISSUE_PEAK = 148 * 4 * 32 * 1.965e9   # thread-instructions/s: 4 warp schedulers per SM, one warp-instruction per clock each
 # thread-instructions per sampled (32-shot word, qubit) site, counted by ncu (static, per kernel build):
 # profiles/r01_mc_fused_steane_gapq_ncu_summary.txt (k_small_named_gapq) and r01_hgp_fused_sampler_v2 (sample_tiles)
-INSTR_PER_SITE_WORD = {"gapq": 56.0}
+INSTR_PER_SITE_WORD = {"gapq": 56.0, "sample_tiles": 134.0}   # 4.1866e9 warp-inst x 32 / (2e7 / 32 x 1600 site-words)
 
 
 def parse_args():
@@ -626,6 +626,35 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
                     "kernel": dev.kernel_name(), "roofline": hbm(gbs)}
         return run
 
+    def arbitrary(label, make):
+        """A code the library has no built-in descriptor for: generic (runtime-H) kernels, then the static family
+        compiled for it IN PROCESS by NVRTC (qcss_code_specialize: no toolkit, no subprocess)."""
+        def run():
+            hx, hz = make()
+            code = CSSCode(np.array(hx), np.array(hz))
+            dev, n, shots = code.device, code.n, int(1_000_000_000 * scale) // 1024 * 1024
+            stride = ((shots + 127) // 128) * 2
+            ex = torch.empty((n, stride), dtype=torch.int64, device="cuda")
+            ez = torch.empty((n, stride), dtype=torch.int64, device="cuda")
+            tally = torch.zeros(6, dtype=torch.int64, device="cuda")
+            dev.mc_sample_dev(P_ERR, shots, SEED, rank * shots, ex.data_ptr(), ez.data_ptr(), stride, stream)
+            res = {"workload": f"{label} [[{n},1]], 1e9 shots per GPU resident, syndrome + lookup decode + tally"}
+            for phase in ("generic", "specialised"):
+                if phase == "specialised":
+                    t0 = time.perf_counter()
+                    code.specialize()
+                    res["specialise_seconds"] = time.perf_counter() - t0
+                ms = ctx.timed(lambda: dev.decode_dev(shots, stream, ex=ex.data_ptr(), ez=ez.data_ptr(), e_stride=stride,
+                                                      tally=tally.data_ptr()))
+                ctx.launches += 4
+                gbs = world * 2 * n / 8 * shots / ms / 1e6
+                res[phase] = {"ms": ms, "value": world * shots / ms * 1e3, "unit": "shots/s", "kernel": dev.kernel_name(),
+                              "roofline": hbm(gbs)}
+            res["ms"], res["value"], res["unit"] = res["specialised"]["ms"], res["specialised"]["value"], "shots/s"
+            res["roofline"] = res["specialised"]["roofline"]
+            return res
+        return run
+
     def c4():
         hx, hz = codes.hgp1600()
         dev = SyndromeCode(hx, hz).device
@@ -668,10 +697,17 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
                                                              0, 0, stream))
         ctx.launches += 4
         rate = world * shots / ms * 1e3
+        sites = rate / 32 * 1600 / world                              # sampled (32-shot word, qubit) sites per second per GPU
+        instr = sites * INSTR_PER_SITE_WORD["sample_tiles"]
         return {"workload": "hgp n=1600, Philox sampler fused into the sparse syndrome kernel, both Pauli types, "
                             "1e8 shots per GPU, only the 2 x 768 syndrome bits per shot reach HBM",
-                "ms": ms, "value": rate, "unit": "shots/s", "shots_per_gpu": shots, "bound": "int",
-                "site_words_per_s_per_gpu": rate / 32 * 1600 / world}
+                "ms": ms, "value": rate, "unit": "shots/s", "shots_per_gpu": shots,
+                "site_words_per_s_per_gpu": sites,
+                "roofline": {"bound": "int", "achieved": instr, "peak": ISSUE_PEAK, "unit": "thread-instr/s",
+                             "frac": instr / ISSUE_PEAK, "traffic": None,
+                             "model": "thread-instructions per sampled site-word incl. the CSR XOR phase (STATIC, ncu: "
+                                      "profiles/r01_hgp_fused_sampler_v2_ncu_summary.txt) x site-words/s per GPU; "
+                                      "peak = 148 SMs x 4 schedulers x 32 lanes x 1.965 GHz"}}
 
     def c4_dense():
         m, n = 1024, 2048
@@ -729,6 +765,8 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
     guarded("c2_fused_sampler", c2_fused)
     guarded("c3_qrm15", c3("qrm15"))
     guarded("c3_golay23", c3("golay23"))
+    guarded("c3_shor9_nvrtc", arbitrary("shor", codes.shor9))
+    guarded("c3_surface5_nvrtc", arbitrary("rotated surface d=5", lambda: codes.rotated_surface(5)))
     guarded("c4_hgp1600", c4)
     guarded("c4_hgp1600_fused_sampler", c4_fused)
     guarded("c4_dense", c4_dense)

@@ -106,6 +106,15 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
                      int64_t n1, const int64_t* keys1, const uint8_t* corr1,
                      int64_t n2, const int64_t* keys2, const uint8_t* corr2,
                      qcss_code** out);
+/* Opt-in extension (the reference raises "currently only supports CSS codes for a single logical
+ * qubit", css_code.py:74-75): k logical qubits.  Lx / Lz are k x n row-major 0/1 bytes (x_operator_matrix /
+ * z_operator_matrix, css_code.py:124-161, which already return k rows).  A shot counts as a logical failure when ANY
+ * logical operator flips: flip outputs are the union over the k rows, fail_x / fail_z / fail_any count it; syndromes,
+ * corrections and misses are unchanged.  k > 1 runs one decode pass per logical row plus a union kernel (no fused
+ * sampler tally, no sparse / EC / specialised paths: QCSS_ERR_UNSUPPORTED). */
+QCSS_API int qcss_code_create_multi(int n, int m1, const uint8_t* H1, int m2, const uint8_t* H2, int k, const uint8_t* Lx,
+                           const uint8_t* Lz, int64_t n1, const int64_t* keys1, const uint8_t* corr1, int64_t n2,
+                           const int64_t* keys2, const uint8_t* corr2, qcss_code** out);
 QCSS_API int qcss_code_destroy(qcss_code* code);
 /* Human-readable name of the kernel family the code dispatches to (tests). */
 QCSS_API int qcss_code_kernel_name(const qcss_code* code, char* buf, int buflen);

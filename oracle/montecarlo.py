@@ -53,7 +53,8 @@ def decode_batch(h, table, logical, errs):
     miss = ~present[keys]
     corr = corr_tab[keys]
     resid = (errs.astype(np.uint8) ^ corr)
-    flip = (resid.astype(np.int64) @ np.asarray(logical, dtype=np.int64)[0]) % 2
+    # k = 1 in the reference; with several logical rows (allow_multi_logical) a shot fails when any of them flips
+    flip = ((resid.astype(np.int64) @ np.asarray(logical, dtype=np.int64).T) % 2).any(axis=1)
     return dict(synd=synd.astype(np.uint8), keys=keys, corr=corr,
                 miss=miss.astype(np.uint8), flip=flip.astype(np.uint8))
 

@@ -65,6 +65,11 @@ PROTOTYPES = {
                                         ctypes.c_int64, _c_i64p, _c_u8p,
                                         ctypes.c_int64, _c_i64p, _c_u8p,
                                         ctypes.POINTER(ctypes.c_void_p)]),
+    "qcss_code_create_multi": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_u8p, ctypes.c_int, _c_u8p, ctypes.c_int,
+                                              _c_u8p, _c_u8p,
+                                              ctypes.c_int64, _c_i64p, _c_u8p,
+                                              ctypes.c_int64, _c_i64p, _c_u8p,
+                                              ctypes.POINTER(ctypes.c_void_p)]),
     "qcss_code_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "qcss_code_kernel_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "qcss_code_spec_source": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64,
@@ -239,15 +244,23 @@ class DeviceCode:
         lib = load()
         h1, h2 = _u8(h1), _u8(h2)
         self.n, self.m1, self.m2 = int(n), h1.shape[0], h2.shape[0]
-        lx, lz = _u8(lx), _u8(lz)
+        lx, lz = _u8(lx), _u8(lz)                       # (n,) for one logical qubit, (k, n) for several
+        self.k = 1 if lx is None or lx.ndim == 1 else lx.shape[0]
         n1, keys1, corr1 = _table_arrays(table1, n)
         n2, keys2, corr2 = _table_arrays(table2, n)
         handle = ctypes.c_void_p()
         as_u8 = lambda a: a.ctypes.data_as(_c_u8p) if a is not None else None
         as_i64 = lambda a: a.ctypes.data_as(_c_i64p) if a is not None else None
-        check(lib.qcss_code_create(self.n, self.m1, as_u8(h1), self.m2, as_u8(h2), as_u8(lx), as_u8(lz),
-                                   n1, as_i64(keys1), as_u8(corr1), n2, as_i64(keys2), as_u8(corr2),
-                                   ctypes.byref(handle)))
+        if self.k == 1:
+            lx1 = None if lx is None else np.ascontiguousarray(lx.reshape(-1))
+            lz1 = None if lz is None else np.ascontiguousarray(lz.reshape(-1))
+            check(lib.qcss_code_create(self.n, self.m1, as_u8(h1), self.m2, as_u8(h2), as_u8(lx1), as_u8(lz1),
+                                       n1, as_i64(keys1), as_u8(corr1), n2, as_i64(keys2), as_u8(corr2),
+                                       ctypes.byref(handle)))
+        else:
+            check(lib.qcss_code_create_multi(self.n, self.m1, as_u8(h1), self.m2, as_u8(h2), self.k, as_u8(lx), as_u8(lz),
+                                             n1, as_i64(keys1), as_u8(corr1), n2, as_i64(keys2), as_u8(corr2),
+                                             ctypes.byref(handle)))
         self._lib = lib
         self.handle = handle
 
@@ -259,10 +272,10 @@ class DeviceCode:
         unmodified reference.  Nothing is recomputed: the tables and matrices are uploaded as they stand."""
         lx = np.asarray(code.x_operator_matrix())
         lz = np.asarray(code.z_operator_matrix())
-        if lx.shape[0] != 1 or lz.shape[0] != 1:
-            raise ValueError("the fused logical check covers one logical qubit (k = 1)")
+        if lx.shape[0] == 1 and lz.shape[0] == 1:
+            lx, lz = lx[0], lz[0]
         return cls(int(code.n), np.asarray(code.parity_check_c1), np.asarray(code.parity_check_c2),
-                   lx[0], lz[0], code._c1_syndromes, code._c2_syndromes)
+                   lx, lz, code._c1_syndromes, code._c2_syndromes)
 
     def __del__(self):
         handle, self.handle = getattr(self, "handle", None), None

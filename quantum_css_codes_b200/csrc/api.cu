@@ -76,8 +76,19 @@ constexpr int64_t kMaxShotsPerLaunch = (int64_t)1 << 38;
 struct SpecKernels;
 void spec_rtc_free(SpecKernels* k);
 
+// Logical rows beyond the first (allow_multi_logical, k > 1): the same H and table with another L row, i.e. another
+// flip bit per table entry.
+struct LogicalExtra {
+    GenericSide side_x{}, side_z{};
+    uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
+    uint32_t lmask_x = 0, lmask_z = 0;
+    DevBuf fm_x, fm_z, co_x, co_z, e32_x, e32_z;
+};
+
 struct qcss_code {
     int n = 0, m1 = 0, m2 = 0;
+    int k = 1;                          // logical qubits; k > 1 only through qcss_code_create_multi
+    std::vector<LogicalExtra*> extra;   // logical rows 1 .. k-1
     bool small = false;                 // register-resident kernels apply (n <= 32, m <= 16)
     GenericSide side_x{}, side_z{};     // x: which = 2 (H2, _c2_syndromes, Lz); z: which = 1
     uint32_t rows_x[kMaxM] = {0}, rows_z[kMaxM] = {0};
@@ -173,7 +184,8 @@ int build_side(qcss_code* c, GenericSide& s, uint32_t* rows, uint32_t& lmask, in
     s.has_miss = 0;
     for (size_t k = 0; k < size; ++k)
         if (fm[k] & 2) s.has_miss = 1;
-    (&s == &c->side_x ? c->fm0_x : c->fm0_z) = fm[0];
+    if (&s == &c->side_x) c->fm0_x = fm[0];
+    else if (&s == &c->side_z) c->fm0_z = fm[0];
     s.mode = (m <= kSlicedM) ? kModeSliced : kModeLut;
     if (m <= kSlicedM) {
         for (size_t k = 0; k < size; ++k) {
@@ -297,6 +309,8 @@ void gap_table_from_p(double p, GapTable* t) {
     t->inv = t->cdf[0] ? (uint32_t)(4294967295u / t->cdf[0]) : 0xFFFFFFFFu;
 }
 
+int launch_decode_multi(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStream_t stream);
+
 int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStream_t stream) {
     if (shots < 0) return fail(QCSS_ERR_INVALID, "shots must be >= 0");
     if (io->ex == nullptr && io->ez == nullptr) return fail(QCSS_ERR_INVALID, "no error planes given");
@@ -320,6 +334,7 @@ int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStr
             return fail(QCSS_ERR_INVALID, "code has no _c1_syndromes table: cannot decode Z errors");
     }
     if (shots == 0) return QCSS_OK;
+    if (c->k > 1 && wants_decode) return launch_decode_multi(c, io, shots, stream);
     SmallLaunch l;
     l.x = &c->side_x;
     l.z = &c->side_z;
@@ -327,6 +342,86 @@ int launch_decode(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStr
     l.named_id = c->named_id;
     l.sample = false;
     QCSS_CUDA(launch_small_any(c, l, stream));
+    return QCSS_OK;
+}
+
+// k > 1 (allow_multi_logical; the reference raises at css_code.py:74-75): a shot fails when ANY logical operator
+// flips.  One pass of the FULL kernels per logical row writes that row's flip planes, then one kernel ORs them,
+// counts and (on request) stores the union as the flip output.  Syndromes, corrections and misses do not depend on
+// the logical row and come from the first pass.
+__global__ void k_union_flips(const uint64_t* __restrict__ fx, const uint64_t* __restrict__ fz, int k, int64_t stride,
+                              int64_t words64, uint64_t tail_mask64, uint64_t* __restrict__ out_x, uint64_t* __restrict__ out_z,
+                              unsigned long long* __restrict__ tally, const unsigned long long* __restrict__ first_pass) {
+    unsigned long long cx = 0, cz = 0, ca = 0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words64; w += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t ux = 0, uz = 0;
+        for (int i = 0; i < k; ++i) {
+            if (fx) ux |= fx[(int64_t)i * stride + w];
+            if (fz) uz |= fz[(int64_t)i * stride + w];
+        }
+        if (w == words64 - 1) { ux &= tail_mask64; uz &= tail_mask64; }
+        if (out_x) out_x[w] = ux;
+        if (out_z) out_z[w] = uz;
+        cx += __popcll(ux); cz += __popcll(uz); ca += __popcll(ux | uz);
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        cx += __shfl_xor_sync(0xFFFFFFFFu, cx, d);
+        cz += __shfl_xor_sync(0xFFFFFFFFu, cz, d);
+        ca += __shfl_xor_sync(0xFFFFFFFFu, ca, d);
+    }
+    if (tally != nullptr && (threadIdx.x & 31) == 0) {
+        if (cx) atomicAdd(tally + 1, cx);
+        if (cz) atomicAdd(tally + 2, cz);
+        if (ca) atomicAdd(tally + 3, ca);
+    }
+    if (tally != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(tally + 4, first_pass[4]);
+        atomicAdd(tally + 5, first_pass[5]);
+    }
+}
+
+int launch_decode_multi(qcss_code* c, const qcss_decode_io* io, int64_t shots, cudaStream_t stream) {
+    const int k = c->k;
+    const int64_t stride = io->e_stride, words64 = (shots + 63) / 64;
+    const size_t plane = (size_t)stride * 8;
+    uint8_t* scratch = nullptr;
+    QCSS_CUDA(cudaMallocAsync((void**)&scratch, 2 * (size_t)k * plane + 64, stream));
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)k * plane + 64, stream);
+    uint64_t* fx = reinterpret_cast<uint64_t*>(scratch);
+    uint64_t* fz = fx + (size_t)k * stride;
+    unsigned long long* first = reinterpret_cast<unsigned long long*>(scratch + 2 * (size_t)k * plane);
+    for (int i = 0; i < k && e == cudaSuccess; ++i) {
+        qcss_decode_io pass;
+        if (i == 0) {
+            pass = *io;                                   // syndromes, corrections, misses: once
+            pass.tally = io->tally ? reinterpret_cast<uint64_t*>(first) : nullptr;
+        } else {
+            memset(&pass, 0, sizeof(pass));
+            pass.ex = io->ex;
+            pass.ez = io->ez;
+            pass.e_stride = io->e_stride;
+        }
+        pass.flip_x = io->ex ? fx + (size_t)i * stride : nullptr;
+        pass.flip_z = io->ez ? fz + (size_t)i * stride : nullptr;
+        SmallLaunch l;
+        l.x = i == 0 ? &c->side_x : &c->extra[i - 1]->side_x;
+        l.z = i == 0 ? &c->side_z : &c->extra[i - 1]->side_z;
+        l.io = make_io(&pass, shots);
+        l.named_id = -1;
+        l.sample = false;
+        e = launch_small(l, stream);
+    }
+    if (e == cudaSuccess) {
+        const int r = (int)(shots & 63);
+        const uint64_t tail = r ? ((1ull << r) - 1ull) : ~0ull;
+        const int64_t blocks = (words64 + 255) / 256;
+        k_union_flips<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(
+            io->ex ? fx : nullptr, io->ez ? fz : nullptr, k, stride, words64, tail, io->flip_x, io->flip_z,
+            reinterpret_cast<unsigned long long*>(io->tally), first);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(scratch, stream);
+    QCSS_CUDA(e);
     return QCSS_OK;
 }
 
@@ -345,6 +440,29 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
         if (d_ez && (rc = check_planes(d_ez, e_stride, shots, "ez planes"))) return rc;
     }
     if (shots == 0) return QCSS_OK;
+    if (c->k > 1 && d_tally) {
+        // k > 1: no fused tally kernel; the same Philox streams are written out as planes (chunks of 2^26 shots)
+        // and decoded by launch_decode_multi
+        const int64_t chunk = (int64_t)1 << 26, cwords = chunk / 64;
+        uint64_t* planes = nullptr;
+        QCSS_CUDA(cudaMallocAsync((void**)&planes, 2 * (size_t)c->n * cwords * 8, stream));
+        for (int64_t done = 0; done < shots && rc == QCSS_OK; done += chunk) {
+            const int64_t part = shots - done < chunk ? shots - done : chunk;
+            rc = launch_mc(c, p, part, seed, first_shot + done, nullptr, planes, planes + (size_t)c->n * cwords, cwords, stream);
+            if (rc == QCSS_OK && (d_ex || d_ez)) rc = fail(QCSS_ERR_UNSUPPORTED, "k > 1: tallies and sampled planes are separate calls");
+            if (rc == QCSS_OK) {
+                qcss_decode_io io;
+                memset(&io, 0, sizeof(io));
+                io.ex = planes;
+                io.ez = planes + (size_t)c->n * cwords;
+                io.e_stride = cwords;
+                io.tally = d_tally;
+                rc = launch_decode(c, &io, part, stream);
+            }
+        }
+        cudaFreeAsync(planes, stream);
+        return rc;
+    }
     if (shots > kMaxShotsPerLaunch) {
         // the kernels count events in 32-bit per-thread registers and reduce them per warp in 32 bits before
         // widening: bound the shots of one launch so a warp's share stays far below 2^32 (tallies accumulate)
@@ -390,6 +508,7 @@ int launch_ec(qcss_code* c, double p_data, double p_anc, int rounds, int64_t sho
     if (!d_tally) return fail(QCSS_ERR_INVALID, "tally is NULL");
     if (c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
         return fail(QCSS_ERR_INVALID, "error-correction Monte Carlo needs both syndrome tables");
+    if (c->k > 1) return fail(QCSS_ERR_UNSUPPORTED, "error-correction Monte Carlo covers k = 1");
     EcLaunch l;
     memset(&l.ec, 0, sizeof(l.ec));
     int rc = threshold_from_p(p_data, &l.ec.thr_p);
@@ -563,6 +682,35 @@ QCSS_API int qcss_code_create(int n, int m1, const uint8_t* H1, int m2, const ui
     return QCSS_OK;
 }
 
+QCSS_API int qcss_code_create_multi(int n, int m1, const uint8_t* H1, int m2, const uint8_t* H2, int k, const uint8_t* Lx,
+                           const uint8_t* Lz, int64_t n1, const int64_t* keys1, const uint8_t* corr1, int64_t n2,
+                           const int64_t* keys2, const uint8_t* corr2, qcss_code** out) {
+    if (k < 1 || k > 64) return fail(QCSS_ERR_INVALID, "k must be in [1, 64]");
+    if (k > 1 && (!Lx || !Lz)) return fail(QCSS_ERR_INVALID, "k > 1 needs the logical operator rows");
+    int rc = qcss_code_create(n, m1, H1, m2, H2, Lx, Lz, n1, keys1, corr1, n2, keys2, corr2, out);
+    if (rc || k == 1) return rc;
+    qcss_code* c = *out;
+    if (!c->small || c->side_x.mode == kModeNone || c->side_z.mode == kModeNone) {
+        qcss_code_destroy(c);
+        *out = nullptr;
+        return fail(QCSS_ERR_UNSUPPORTED, "k > 1 needs a decodable code (n <= %d, m <= %d, both tables)", kMaxN, kMaxM);
+    }
+    c->k = k;
+    c->named_id = -1;                                   // runtime-L kernels
+    for (int i = 1; i < k && !rc; ++i) {
+        LogicalExtra* x = new (std::nothrow) LogicalExtra();
+        if (!x) { rc = fail(QCSS_ERR_NOMEM, "out of host memory"); break; }
+        c->extra.push_back(x);
+        rc = build_side(c, x->side_x, x->rows_x, x->lmask_x, m2, H2, Lz + (size_t)i * n, n2, keys2, corr2, x->fm_x, x->co_x, x->e32_x);
+        if (!rc) rc = build_side(c, x->side_z, x->rows_z, x->lmask_z, m1, H1, Lx + (size_t)i * n, n1, keys1, corr1, x->fm_z, x->co_z, x->e32_z);
+    }
+    if (rc) {
+        qcss_code_destroy(c);
+        *out = nullptr;
+    }
+    return rc;
+}
+
 QCSS_API int qcss_code_destroy(qcss_code* c) {
     if (!c) return QCSS_OK;
     c->fm_x.release(); c->fm_z.release(); c->co_x.release(); c->co_z.release();
@@ -581,6 +729,10 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->spec_dl) dlclose(c->spec_dl);
     spec_rtc_free(c->rtc);
+    for (LogicalExtra* x : c->extra) {
+        x->fm_x.release(); x->fm_z.release(); x->co_x.release(); x->co_z.release(); x->e32_x.release(); x->e32_z.release();
+        delete x;
+    }
     delete c;
     return QCSS_OK;
 }
@@ -1187,6 +1339,7 @@ extern "C" {
 
 QCSS_API int qcss_code_spec_source(const qcss_code* c, char* buf, int64_t cap, int64_t* needed) {
     if (!c || !needed) return fail(QCSS_ERR_INVALID, "bad arguments");
+    if (c->k > 1) return fail(QCSS_ERR_UNSUPPORTED, "specialisation covers k = 1");
     if (!c->small || c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
         return fail(QCSS_ERR_UNSUPPORTED, "specialisation needs a decodable code (n <= %d, m <= %d, both tables)", kMaxN, kMaxM);
     std::string out = "// GENERATED by qcss_code_spec_source -- kernels specialised for one code.\n"
@@ -1312,6 +1465,7 @@ int sparse_ready(qcss_code* c, uint32_t* f0x, uint32_t* f0z) {
     if (!c->small) return fail(QCSS_ERR_UNSUPPORTED, "lookup decode covers n <= %d and m <= %d", kMaxN, kMaxM);
     if (c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
         return fail(QCSS_ERR_INVALID, "sparse decode needs both syndrome tables");
+    if (c->k > 1) return fail(QCSS_ERR_UNSUPPORTED, "sparse decode covers k = 1");
     *f0x = c->fm0_x;
     *f0z = c->fm0_z;
     return QCSS_OK;
@@ -1751,6 +1905,7 @@ extern "C" {
 
 QCSS_API int qcss_code_specialize(qcss_code* c, const char* nvrtc_path, const char* cache_dir) {
     if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (c->k > 1) return fail(QCSS_ERR_UNSUPPORTED, "specialisation covers k = 1");
     if (!c->small || c->side_x.mode == kModeNone || c->side_z.mode == kModeNone)
         return fail(QCSS_ERR_UNSUPPORTED, "specialisation needs a decodable code (n <= %d, m <= %d, both tables)", kMaxN, kMaxM);
     std::string src = "#include \"small_common.cuh\"\nnamespace qcss {\nnamespace spec {\n";

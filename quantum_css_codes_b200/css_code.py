@@ -319,13 +319,17 @@ class CSSCode(_DevicePath):
     sampling -- runs in CUDA kernels on bit-plane batches through ``libqcss.so``.
     """
 
-    def __init__(self, parity_check_c1, parity_check_c2, table_builder=None, standard_form=None):
+    def __init__(self, parity_check_c1, parity_check_c2, table_builder=None, standard_form=None,
+                 allow_multi_logical=False):
         """``table_builder`` (extension, not in the reference): ``"gpu"`` builds both syndrome tables
         with the device weight-layer search (``syndrome_table_gpu``); the default is the host search
         (``syndrome_table``), which needs no GPU.  Both give identical tables.
         ``standard_form`` (extension): ``"gpu"`` runs the CSS condition and both normalisations with
         their qubit swaps on the device (``qcss_css_standard_form``); default host numpy.  Identical
-        matrices and exceptions either way."""
+        matrices and exceptions either way.
+        ``allow_multi_logical`` (extension): accept k = n - r_1 - r_2 > 1 where the reference raises
+        ``InvalidCodeError`` (css_code.py:74-75).  ``x/z_operator_matrix`` then have k rows and the device path counts
+        a shot as failed when ANY logical operator flips."""
         r_1, n_1 = parity_check_c1.shape
         r_2, n_2 = parity_check_c2.shape
         if n_1 != n_2:
@@ -371,7 +375,7 @@ class CSSCode(_DevicePath):
         self._transversal_cache = None
         self._device_code = None
 
-        if self.k != 1:
+        if self.k != 1 and not (allow_multi_logical and self.k > 1):
             raise InvalidCodeError("currently only supports CSS codes for a single logical qubit")
 
     # ---- reference surface ---------------------------------------------------------------

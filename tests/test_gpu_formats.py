@@ -168,3 +168,42 @@ def test_events_from_planes_on_device_and_sparse_dev_decode(name):
     dev.events_from_planes_dev(ex.data_ptr(), ez.data_ptr(), stride, shots, 0, events.data_ptr(), 100, count.data_ptr(), 0)
     torch.cuda.synchronize()
     assert int(count.item()) == k
+
+
+@pytest.mark.parametrize("make", ["four_two_two", "hamming_k2", "golay_k3"])
+def test_allow_multi_logical_decode_matches_oracle(make):
+    """k > 1 (opt-in extension): a shot fails when ANY of the k logical operators flips.  Corrections,
+    flips (union over the rows), misses and tallies against the oracle on shared inputs; the Monte-Carlo tally against
+    the oracle on the sampler's own error bits; unsupported paths say so."""
+    from oracle import philox as ophilox
+    if make == "four_two_two":
+        h1 = h2 = np.ones((1, 4), dtype=int)
+    elif make == "hamming_k2":
+        h1 = np.array(codes.hamming_7_4()); h2 = h1[:2]
+    else:
+        h1 = np.array(codes.golay23()[0]); h2 = h1[:9]
+    code = CSSCode(h1.copy(), h2.copy(), allow_multi_logical=True)
+    ref = ocss.build_css(h1.copy(), h2.copy(), allow_k_not_1=True)
+    assert code.k == ref.k > 1 and code.device.k == ref.k
+    rng = np.random.default_rng(code.n)
+    shots = 20_011
+    ex, ez = omc.sample_depolarizing(rng, shots, code.n, 0.06)
+    for which, errs in ((2, ex), (1, ez)):
+        h, table, lop = ocss.pauli_side(ref, which)
+        want = omc.decode_batch(h, table, lop, errs)
+        got = code.decode(errs.astype(np.int64), which)
+        assert np.array_equal(got["correction"], want["corr"])
+        assert np.array_equal(got["flip"], want["flip"]) and np.array_equal(got["miss"], want["miss"])
+        assert np.array_equal(code.syndromes(errs, which), want["synd"])
+    assert code.decode_xz(ex, ez) == omc.tally_xz(ref, ex, ez)
+    assert code.device.decode_xz_planes(planes.pack_planes(ex), planes.pack_planes(ez), shots) == omc.tally_xz(ref, ex, ez)
+    got = code.monte_carlo(0.03, 70_001, seed=21, first_shot=128 * 5)
+    sx, sz = ophilox.sample_bits(21, 128 * 5, 70_001, code.n, 0.03)
+    assert got == omc.tally_xz(ref, sx, sz)
+    single = [ocss.build_css(h1.copy(), h2.copy(), allow_k_not_1=True) for _ in range(1)][0]
+    single.lz, single.lx = ref.lz[:1], ref.lx[:1]
+    assert omc.tally_xz(single, sx, sz)["fail_any"] <= got["fail_any"]          # more logical rows, more ways to fail
+    for call in (lambda: code.specialize(), lambda: code.decode_xz_sparse(planes.events_from_arrays(ex, ez), shots),
+                 lambda: code.error_correct_monte_carlo(1e-3, 1e-3, 2, 1000)):
+        with pytest.raises(_native.NativeLibraryError):
+            call()

@@ -277,3 +277,57 @@ def test_transversal_gates_is_a_frozenset_like_the_reference():
     if has_cuda():
         assert steane._transversal_gates == frozenset(['I', 'CNOT', 'H', 'CZ', 'S'])
         assert isinstance(steane._transversal_gates, frozenset)
+
+
+def test_attach_accepts_the_unmodified_reference_object():
+    """Where the reference checkout exists (the build container), attach() takes a CSSCode built by the UNMODIFIED
+    reference (imported next to an inert pyquil stub, as oracle/gen_golden.py does): its attributes are exactly what
+    DeviceCode.from_csscode uploads, and equal our own constructor's."""
+    if not os.path.exists("/root/reference/css_code.py"):
+        pytest.skip("reference checkout not present (GPU box)")
+    import subprocess, sys, textwrap
+    script = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from oracle import gen_golden
+        ref_bm, ref_css = gen_golden.load_reference()              # the reference's modules, unmodified
+        sys.path.insert(0, %r)
+        from quantum_css_codes_b200 import attach, codes, _native
+        from quantum_css_codes_b200.css_code import CSSCode as Ours
+        for name in ("steane", "golay23"):
+            h1, h2 = [np.array(h) for h in getattr(codes, name)()]
+            theirs = ref_css.CSSCode(h1.copy(), h2.copy())
+            assert type(theirs).__module__ == "css_code" and ref_css.__file__.startswith("/root/reference")
+            bound, ours = attach(theirs), Ours(h1.copy(), h2.copy())
+            assert np.array_equal(bound.parity_check_c1, ours.parity_check_c1)
+            assert np.array_equal(bound.x_operator_matrix(), ours.x_operator_matrix())
+            assert list(bound._c2_syndromes) == list(ours._c2_syndromes)
+            assert bound.is_transversal("H") == (name in ("steane", "golay23"))       # falls through to the reference object
+            try:
+                bound.device                                       # uploads through qcss_code_create
+                uploaded = True
+            except _native.NativeLibraryError:
+                uploaded = False                                   # no GPU in the build container: loud, not silent
+            print(name, "uploaded" if uploaded else "no-device")
+        """ % (REPO, REPO))
+    res = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, cwd=REPO)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "steane" in res.stdout and "golay23" in res.stdout
+
+
+def test_allow_multi_logical_constructor_matches_oracle_and_default_still_raises():
+    """k > 1 objects only on request; the reference's exception stays the default
+    (css_code.py:74-75).  Operator matrices get k rows (css_code.py:124-161 already slice k)."""
+    from oracle import css as ocss
+    h = np.array(codes.hamming_7_4())
+    with pytest.raises(errors.InvalidCodeError, match="single logical qubit"):
+        CSSCode(h, h[:2])
+    code = CSSCode(h, h[:2], allow_multi_logical=True)
+    ref = ocss.build_css(h, h[:2], allow_k_not_1=True)
+    assert (code.n, code.k, code.r_1, code.r_2) == (7, 2, 3, 2) == (ref.n, ref.k, ref.r_1, ref.r_2)
+    assert np.array_equal(code.x_operator_matrix(), ref.lx) and code.x_operator_matrix().shape == (2, 7)
+    assert np.array_equal(code.z_operator_matrix(), ref.lz)
+    assert np.array_equal(code.parity_check_c1, ref.parity_check_c1) and list(code._c2_syndromes) == list(ref.c2_syndromes)
+    # logical Z rows commute with the X-type stabilisers (rows of H1), logical X rows with the Z-type ones (H2)
+    assert not np.any(code.z_operator_matrix() @ code.parity_check_c1.T % 2)
+    assert not np.any(code.x_operator_matrix() @ code.parity_check_c2.T % 2)

@@ -750,7 +750,10 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
                             "frac": per_gpu_ops / LOP3_PEAK, "traffic": None,
                             "model": "SURVEY 8d FIXED count: 2.52e7 32-bit XOR word-ops per matrix (plain Gauss-Jordan), "
                                      "whatever the algorithm executes; peak = measured LOP3 rate (profiles/r01_int_peak.jsonl)",
-                            "frac_of_m4r_minimum": None}}
+                            "m4r_smem_floor_ms": batch * 2.87e5 / (148 * 1.965e9) * 1e3,
+                            "frac_of_m4r_smem_floor": batch * 2.87e5 / (148 * 1.965e9) * 1e3 / ms,
+                            "m4r_model": "four-Russians k = 8: 448 block applications x (512 table-read + 128 tabulation "
+                                         "shared-memory wavefronts) per matrix at one wavefront per clock per SM"}}
         del outm, piv
         rows = n - m + 8
         basis = torch.empty((batch, rows, n // 64), dtype=torch.int64, device="cuda")

@@ -2,7 +2,7 @@
    python tools/dense_pair_probe.py [shots] [n] [m]"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from quantum_css_codes_b200 import SyndromeCode, _native
 shots = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 21
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048

@@ -602,7 +602,7 @@ QCSS_API int qcss_set_option(const char* name, int value) {
     if (key == "gapq" && (value == 0 || value == 1)) o.gapq = value;
     else if (key == "dense" && value >= -1 && value <= 1) o.dense = value;
     else if (key == "named" && (value == 0 || value == 1)) o.named = value;
-    else if (key == "gf2_kernel" && value >= 0 && value <= 3) o.gf2_kernel = value;
+    else if (key == "gf2_kernel" && value >= 0 && value <= 4) o.gf2_kernel = value;
     else return fail(QCSS_ERR_INVALID, "unknown option or value out of range: %s = %d", name, value);
     return QCSS_OK;
 }

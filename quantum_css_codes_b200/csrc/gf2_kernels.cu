@@ -123,6 +123,7 @@ cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_
 #endif
     const int pick = options().gf2_kernel;
     if (pick != 1) {
+        if (pick == 4 && gf2_m4r4_supported(m, n)) return launch_gf2_m4r4(in, batch, m, n, out, rank, pivots, stream);
         if ((pick == 3 && m <= 1024) || (pick == 0 && gf2_m4r2_supported(m, n)))
             return launch_gf2_m4r2(in, batch, m, n, out, rank, pivots, stream);
         if (gf2_m4r_supported(m, n)) return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);

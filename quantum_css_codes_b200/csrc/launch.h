@@ -69,6 +69,10 @@ bool gf2_m4r_supported(int m, int n);
 cudaError_t launch_gf2_m4r(const uint64_t* in, int batch, int m, int n, uint64_t* out,
                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
 
+// fourth generation (gf2_m4r4.cu): 1024-column slabs, conflict-free 128-byte table entries, replay bytes in shared memory
+bool gf2_m4r4_supported(int m, int n);
+cudaError_t launch_gf2_m4r4(const uint64_t* in, int batch, int m, int n, uint64_t* out,
+                            int32_t* rank, int32_t* pivots, cudaStream_t stream);
 // third generation (gf2_m4r2.cu): 512-column slabs, two matrices per SM, replay bytes through L2
 bool gf2_m4r2_supported(int m, int n);
 cudaError_t launch_gf2_m4r2(const uint64_t* in, int batch, int m, int n, uint64_t* out,

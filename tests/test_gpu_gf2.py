@@ -70,10 +70,10 @@ def test_rref_structured(m, n):
     assert rank[2] <= 7 and rank[3] == 0
 
 
-@pytest.mark.parametrize("knob", [1, 2, 3])
+@pytest.mark.parametrize("knob", [1, 2, 3, 4])
 def test_rref_every_kernel_generation(knob):
     """The dispatcher picks a kernel by shape; option "gf2_kernel" forces each implementation (1 the general
-    column-by-column kernel, 2 gf2_m4r, 3 gf2_m4r2) over small, ragged, rank-deficient and full-size shapes."""
+    column-by-column kernel, 2 gf2_m4r, 3 gf2_m4r2, 4 gf2_m4r4) over small, ragged, rank-deficient and full-size shapes."""
     with _native.option("gf2_kernel", knob):
         _rref_every_shape(knob)
 
@@ -126,7 +126,7 @@ def test_rref_c5_sixteen_full_size_matrices_vs_reference_goldens():
         sha, rank_want, full = z["sha256"], z["rank"], [z["rref_0"], z["rref_1"]]
     packed = codes.random_matrices_c5(COUNT)
     mats = np.stack([ogf2.pack_rows(variant(i, ogf2.unpack_rows(packed[i], 2048)).astype(np.uint8)) for i in range(COUNT)])
-    for knob in (0, 2, 3):
+    for knob in (0, 2, 3, 4):
         with _native.option("gf2_kernel", knob):
             out, rank, piv = bin_matrix.rref_packed_batched(mats, 2048)
         assert np.array_equal(out[0], full[0]) and np.array_equal(out[1], full[1]), knob

@@ -89,6 +89,12 @@ __device__ __forceinline__ void xor4_if(uint4& a, const uint4& b, bool c) {
     const uint32_t mk = c ? 0xFFFFFFFFu : 0u;
     a.x ^= b.x & mk; a.y ^= b.y & mk; a.z ^= b.z & mk; a.w ^= b.w & mk;
 }
+// PTX prmt: only selector nibbles whose output byte is used need to be valid
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -161,6 +167,25 @@ k_gf2_m4r2(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
                 }
             }
         };
+#ifdef QCSS_M4R2_TAB32
+        auto tabulate = [&](int k, bool skip0) {         // A/B variant (-DQCSS_M4R2_TAB32): lane = word, 32-bit pivot-row loads
+            const uint32_t* pw = P + (lane & (kSW - 1));
+            const int entries = 1 << k;
+            const int w0 = skip0 ? warp - 1 : warp, wn = skip0 ? nw - 1 : nw;
+            if (w0 < 0) return;
+            for (int E = w0 * 8; E < entries; E += wn * 8) {
+                uint32_t base = 0u;
+#pragma unroll
+                for (int u = 3; u < 8; ++u)
+                    if ((E >> u) & 1) base ^= pw[u * kSW];       // warp-uniform
+                const uint32_t p0 = pw[0], p1 = pw[kSW], p2 = pw[2 * kSW];
+                const uint32_t c1 = base ^ p0, c2 = base ^ p1, c3 = c1 ^ p1;
+                uint32_t* t = reinterpret_cast<uint32_t*>(smem + oTP) + E * 32 + lane;
+                t[0 * 32] = base; t[1 * 32] = c1; t[2 * 32] = c2; t[3 * 32] = c3;
+                t[4 * 32] = base ^ p2; t[5 * 32] = c1 ^ p2; t[6 * 32] = c2 ^ p2; t[7 * 32] = c3 ^ p2;
+            }
+        };
+#else
         // tabulate: all combinations of the k published rows (entries beyond 2^k are never read).  One
         // warp pass writes 16 entries: lane group g covers entries E + 4(g >> 1) + {0..3}, copy g & 1.
         // skip0: warp 0 sits out (discovery: it factors the next panel meanwhile) and warps 1 .. nw-1 cover the entries
@@ -191,6 +216,7 @@ k_gf2_m4r2(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
                 *reinterpret_cast<uint4*>(t + 3 * 128) = c1;
             }
         };
+#endif
         // table_reads: one 128-bit read per row; the combination bytes of my group's 8 rows are 2 words
         auto table_reads = [&](const uint8_t* ybase) {
             const uint2 yv = *reinterpret_cast<const uint2*>(ybase + row0);
@@ -295,45 +321,56 @@ k_gf2_m4r2(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
                     __syncthreads();
                     // (b) warp 0 factors the panel in byte space; the other warps apply the pending block meanwhile
                     if (warp == 0) {
-                        const uint4 q = reinterpret_cast<const uint4*>(rep)[lane];   // values 8l..8l+7
-                        const uint32_t prs0 = (__byte_perm(q.x, q.y, 0x7531u) >> 7) & 0x01010101u;
-                        const uint32_t prs1 = (__byte_perm(q.z, q.w, 0x7531u) >> 7) & 0x01010101u;
+                        // Lane l owns the byte values 8l .. 8l+7 (value 8l+e in byte e & 3 of red{e >> 2}), their reduced
+                        // value (red) and combination byte (y).  A column is branch-free: every lane keys its last
+                        // candidate (a present value whose reduced byte has the column's bit) as [reduced byte, y,
+                        // row | 0x8000] and ONE warp max-reduction (REDUX, uniform datapath; a shuffle would queue behind
+                        // the table reads in the load/store pipe) elects the pivot and broadcasts all of it; a column
+                        // without candidates reduces to 0 and multiplies its update masks by zero
+                        // (tools/experiments/panel_bench.cu: 1100 cycles alone, 1500 under 31 warps of table reads; the
+                        // round-1 ballot + shuffle form with its branches: 1450 / 2300).
+                        const uint4 q = reinterpret_cast<const uint4*>(rep)[lane];   // rows of the values 8l..8l+7 | 0x8000
+                        const uint32_t ql0 = prmt(q.x, q.y, 0x6420u), ql1 = prmt(q.z, q.w, 0x6420u);   // low bytes of the rows
+                        const uint32_t qh0 = prmt(q.x, q.y, 0x7531u), qh1 = prmt(q.z, q.w, 0x7531u);   // high bytes | 0x80
+                        const uint32_t prs0 = (qh0 >> 7) & 0x01010101u, prs1 = (qh1 >> 7) & 0x01010101u;
                         uint32_t red0 = 0x03020100u + 0x08080808u * (uint32_t)lane, red1 = red0 + 0x04040404u;
                         uint32_t y0 = 0u, y1 = 0u;
-                        uint32_t pred = 0u, py = 0u, myval = 0u, mycol = 0u;   // lane u < k: pivot u
-                        int k = 0;
+                        uint32_t myrow = 0u, mycol = 0u;       // lane u < k: pivot u
+                        uint32_t kmask = 0x01010101u;          // bit k of every byte lane
+                        uint32_t ku = 0u;
 #pragma unroll
                         for (int col = 0; col < 8; ++col) {
                             const uint32_t s0 = red0 >> col, s1 = red1 >> col;
-                            const uint32_t cand0 = s0 & prs0, cand1 = s1 & prs1;
-                            const unsigned vote = __ballot_sync(0xFFFFFFFFu, (cand0 | cand1) != 0u);
-                            if (vote != 0u) {
-                                const int srcl = __ffs(vote) - 1;
-                                // my first candidate value e (0..7), its reduced byte and y
-                                const uint32_t e = cand0 ? (uint32_t)(__ffs(cand0) - 1) >> 3
-                                                         : 4u + ((uint32_t)(__ffs(cand1) - 1) >> 3);
-                                uint32_t pack = (__byte_perm(red0, red1, e) & 0xFFu) |
-                                                ((__byte_perm(y0, y1, e) & 0xFFu) << 8) | (e << 16);
-                                pack = __shfl_sync(0xFFFFFFFFu, pack, srcl);
-                                const uint32_t v = pack & 0xFFu, yp = (pack >> 8) & 0xFFu;
-                                const uint32_t yk = yp | (1u << k);
-                                const uint32_t v4 = v * 0x01010101u, yk4 = yk * 0x01010101u;
-                                const uint32_t M0 = (s0 & 0x01010101u) * 0xFFu, M1 = (s1 & 0x01010101u) * 0xFFu;
-                                red0 ^= M0 & v4;  red1 ^= M1 & v4;
-                                y0 ^= M0 & yk4;   y1 ^= M1 & yk4;
-                                if (lane < k && ((pred >> col) & 1u)) { pred ^= v; py ^= yk; }
-                                if (lane == k) {
-                                    pred = v; py = yp;
-                                    myval = (uint32_t)srcl * 8u + (pack >> 16);
-                                    mycol = (uint32_t)col;
-                                }
-                                ++k;
+                            // candidates: bit 8i = value i, bit 8i + 4 = value 4 + i
+                            const uint32_t c = (s0 & prs0) + ((s1 & prs1) << 4);
+                            const uint32_t pbit = 31u - (uint32_t)__clz((int)c);
+                            const uint32_t sel = 0x73625140u >> (pbit & 28u);       // nibble 0: byte index i + 4h of bit 8i + 4h
+                            const uint32_t key = prmt(prmt(prmt(ql0, ql1, sel), prmt(qh0, qh1, sel), 0x0040u),
+                                                      prmt(prmt(y0, y1, sel), prmt(red0, red1, sel), 0x0040u), 0x5410u);
+                            const uint32_t pack = __reduce_max_sync(0xFFFFFFFFu, c != 0u ? key : 0u);
+                            const uint32_t found = pack != 0u ? 1u : 0u;
+                            const uint32_t v4 = prmt(pack, 0u, 0x3333u);            // reduced byte of the pivot in every byte lane
+                            const uint32_t yk4 = prmt(pack, 0u, 0x2222u) | kmask;
+                            const uint32_t fm = found * 0xFFu;
+                            const uint32_t M0 = (s0 & 0x01010101u) * fm, M1 = (s1 & 0x01010101u) * fm;
+                            red0 ^= M0 & v4;  red1 ^= M1 & v4;
+                            y0 ^= M0 & yk4;   y1 ^= M1 & yk4;
+                            if (found != 0u && lane == (int)ku) {
+                                myrow = pack & 0x3FFu;
+                                mycol = (uint32_t)col;
                             }
+                            kmask <<= found;
+                            ku += found;
                         }
+                        const int k = (int)ku;
                         reinterpret_cast<uint2*>(G)[lane] = make_uint2(y0, y1);
+                        __syncwarp();
                         uint32_t nib = 0u;
                         if (lane < k) {
-                            const int prow = rep[myval] & 0x3FF;
+                            // A pivot row must keep a single 1 in its own column: its combination byte is that of
+                            // (its strip byte ^ the unit byte of its column) = {itself} ^ G[unit], by linearity.
+                            const uint32_t py = G[1u << mycol] ^ (1u << lane);
+                            const int prow = (int)myrow;
                             pivrow[K + lane] = (int16_t)prow;
                             pivcol[K + lane] = c0 + (int)mycol;
                             rowpiv[prow] = (int16_t)(K + lane);

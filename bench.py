@@ -753,7 +753,9 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
                             "m4r_smem_floor_ms": batch * 2.87e5 / (148 * 1.965e9) * 1e3,
                             "frac_of_m4r_smem_floor": batch * 2.87e5 / (148 * 1.965e9) * 1e3 / ms,
                             "m4r_model": "four-Russians k = 8: 448 block applications x (512 table-read + 128 tabulation "
-                                         "shared-memory wavefronts) per matrix at one wavefront per clock per SM"}}
+                                         "shared-memory wavefronts) per matrix at one wavefront per clock per SM",
+                            "kernel": "k_gf2_m4r4 (1024-column slabs, one matrix per SM) by shape; k_gf2_m4r2 (two per SM) "
+                                      "for widths that leave the last 1024-column slab at most half full"}}
         del outm, piv
         rows = n - m + 8
         basis = torch.empty((batch, rows, n // 64), dtype=torch.int64, device="cuda")

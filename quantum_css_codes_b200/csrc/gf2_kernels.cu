@@ -123,7 +123,14 @@ cudaError_t launch_gf2_rref(const uint64_t* in, int batch, int m, int n, uint64_
 #endif
     const int pick = options().gf2_kernel;
     if (pick != 1) {
-        if (pick == 4 && gf2_m4r4_supported(m, n)) return launch_gf2_m4r4(in, batch, m, n, out, rank, pivots, stream);
+        // By shape (measured, tools/gf2_shapes.py): the fourth generation replays a 1024-column slab faster (2500 against
+        // 3250 cycles per block and 1024 columns) but discovers pivots slower (4400 against 3960 cycles per strip), and a
+        // half-empty last slab costs it a full replay: it wins when the matrix is wider than one slab and its width
+        // fills the 1024-column slabs to more than half (1024 x 2048: 3.59 against 3.76 ms per 1184 matrices, x 4096:
+        // 6.14 against 7.13; x 1536: 3.58 against 2.92, x 2560: 4.88 against 4.60).
+        const bool wide = n > 1024 && (((n + 511) / 512) & 1) == 0;
+        if ((pick == 4 || (pick == 0 && gf2_m4r2_supported(m, n) && wide)) && gf2_m4r4_supported(m, n))
+            return launch_gf2_m4r4(in, batch, m, n, out, rank, pivots, stream);
         if ((pick == 3 && m <= 1024) || (pick == 0 && gf2_m4r2_supported(m, n)))
             return launch_gf2_m4r2(in, batch, m, n, out, rank, pivots, stream);
         if (gf2_m4r_supported(m, n)) return launch_gf2_m4r(in, batch, m, n, out, rank, pivots, stream);

@@ -167,8 +167,15 @@ k_gf2_m4r2(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
                 }
             }
         };
-#ifdef QCSS_M4R2_TAB32
-        auto tabulate = [&](int k, bool skip0) {         // A/B variant (-DQCSS_M4R2_TAB32): lane = word, 32-bit pivot-row loads
+#ifndef QCSS_M4R2_TAB128
+        // tabulate: all combinations of the k published rows (entries beyond 2^k are never read; rows u >= k of P hold
+        // stale data that only reaches those).  lane = word of the 128-byte entry (the 16 slab words twice): the pivot
+        // rows are read with 32-bit loads (one wavefront per row per warp -- a 128-bit load costs four however many
+        // lanes share an address) and a warp pass writes eight entries, 128 contiguous bytes per store: 432 wavefronts
+        // per block instead of 640.  Same-run A/B (tools/gf2_m4r2_probe.cu, -DQCSS_M4R2_TAB128 = the round-1 form
+        // below): 2.06 / 3.76 / 7.14 ms against 2.13 / 3.90 / 7.41 ms per 1184 matrices at n = 1024 / 2048 / 4096.
+        // skip0: warp 0 sits out (discovery: it factors the next panel meanwhile) and warps 1 .. nw-1 cover the entries
+        auto tabulate = [&](int k, bool skip0) {
             const uint32_t* pw = P + (lane & (kSW - 1));
             const int entries = 1 << k;
             const int w0 = skip0 ? warp - 1 : warp, wn = skip0 ? nw - 1 : nw;

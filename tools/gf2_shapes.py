@@ -7,7 +7,7 @@ from quantum_css_codes_b200 import _native
 lib = _native.load()
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 if len(sys.argv) > 2: _native.check(lib.qcss_set_option(b"gf2_kernel", int(sys.argv[2])))
-for m, n in ((1024, 1024), (1024, 1536), (1024, 2048), (1024, 3072), (1024, 4096), (512, 1024), (768, 1600)):
+for m, n in ((1024, 1024), (1024, 1280), (1024, 1536), (1024, 2048), (1024, 2560), (1024, 3072), (1024, 4096), (512, 1024), (640, 1280), (768, 1600), (768, 2048), (896, 1792)):
     mats = torch.randint(-2**31, 2**31, (batch, m, n // 32), dtype=torch.int32, device="cuda").view(torch.int64)
     out = torch.empty_like(mats)
     rank = torch.zeros(batch, dtype=torch.int32, device="cuda")

@@ -89,7 +89,8 @@ QCSS_API int qcss_host_free(void* ptr);
  *                0 never, 1 always; taken at qcss_code_create
  *   "named"      1 (default) use a built-in static descriptor when the code matches one, 0 generic kernels;
  *                taken at qcss_code_create
- *   "gf2_kernel" 0 (default) batched RREF kernel by shape, 1 column-by-column, 2 m4r, 3 m4r2 (rows <= 1024)
+ *   "gf2_kernel" 0 (default) batched RREF kernel by shape, 1 column-by-column, 2 m4r, 3 m4r2 (rows <= 1024),
+ *                4 m4r4 (32 < rows <= 1024); a forced kernel falls back to the next one its shape limits allow
  * QCSS_ERR_INVALID for an unknown name or a value out of range. */
 QCSS_API int qcss_set_option(const char* name, int value);
 QCSS_API int qcss_get_option(const char* name, int* value);

@@ -350,7 +350,12 @@ k_gf2_m4r4(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
                         }
                         PROF(10);
                     } else if (pending) {
-                        tabulate(pend_k, warp - 1, nw - 1);
+                        // The warps that share warp 0's scheduler (warp & 3 == 0) sit the tabulation out: the panel's
+                        // instructions wait for the ALU pipe behind theirs (ncu source page: math-pipe throttle and
+                        // not-selected on every panel instruction; with the other warps idle the panel takes 1450 cycles
+                        // in this kernel, under their tabulation and table reads 2500).  The other three quarters cover
+                        // the 256 entries in at most two passes each, as 31 warps did.  -1 %.
+                        if (warp & 3) tabulate(pend_k, warp - (warp >> 2) - 1, nw - ((nw + 3) >> 2));
                         PROF(8);
                         asm volatile("bar.arrive 2, %0;" ::"r"(nthreads) : "memory");
                         asm volatile("bar.sync 1, %0;" ::"r"(nthreads - 32) : "memory");   // warps 1 .. nw-1 have tabulated

@@ -88,6 +88,22 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
+// integer multiplies as PTX so that they stay on the FMA pipe (a shift would be free to move to the ALU pipe)
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ void xor4(uint4& a, const uint4& b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
 
 // XOR of the words pw[u] selected by the bits of y
@@ -191,10 +207,22 @@ k_gf2_m4r4(const uint32_t* __restrict__ in, int batch, int m, int n, uint32_t* _
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const uint32_t w = q ? yv.y : yv.x;
+#ifdef QCSS_M4R4_ALU_ADDR
                 const uint32_t a0 = ((w << 7) & 0x7F80u) | laneoff;
                 const uint32_t a1 = ((w >> 1) & 0x7F80u) | laneoff;
                 const uint32_t a2 = ((w >> 9) & 0x7F80u) | laneoff;
                 const uint32_t a3 = ((w >> 17) & 0x7F80u) | laneoff;
+#else
+                // entry address = 128 byte + 16 j, computed on the FMA pipe (integer multiply-add, high and low halves):
+                // the ALU pipe (one warp instruction per two cycles per scheduler) keeps the 32 XORs, and the panel warp's
+                // ALU-only chain waits less behind its scheduler-mates
+                // (ptxas turns the last multiply-add into LEA.HI, ALU pipe: one ALU instruction per row instead of two; hiding
+                //  the constant from it keeps everything on the FMA pipe but measured 4 % slower)
+                const uint32_t a0 = mad_hi(mul_lo(w, 1u << 24), 1u << 15, laneoff);
+                const uint32_t a1 = mad_hi(mul_lo(mul_hi(w, 1u << 24), 1u << 24), 1u << 15, laneoff);
+                const uint32_t a2 = mad_hi(mul_lo(mul_hi(w, 1u << 16), 1u << 24), 1u << 15, laneoff);
+                const uint32_t a3 = mad_hi(mul_lo(mul_hi(w, 1u << 8), 1u << 24), 1u << 15, laneoff);
+#endif
                 xor4(r[4 * q + 0], *reinterpret_cast<const uint4*>(tp + a0));
                 xor4(r[4 * q + 1], *reinterpret_cast<const uint4*>(tp + a1));
                 xor4(r[4 * q + 2], *reinterpret_cast<const uint4*>(tp + a2));

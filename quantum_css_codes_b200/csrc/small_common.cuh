@@ -274,7 +274,7 @@ __device__ __forceinline__ void named_gapq_body(const NamedArgs& a) {
 }
 
 template <class DX, class DZ>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 k_small_named_gapq(const __grid_constant__ NamedArgs a) {
     named_gapq_body<DX, DZ>(a);
 }

@@ -1,11 +1,12 @@
 """A few launches of the fused Philox sampler + decode kernel (for ncu captures).
-    python tools/mc_probe.py [code] [shots] [p]"""
+    python tools/mc_probe.py [code] [shots] [p] [library]"""
 import os, sys
 import numpy as np
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-from quantum_css_codes_b200 import CSSCode, codes
+from quantum_css_codes_b200 import CSSCode, codes, _native
+if len(sys.argv) > 4: _native.LIB_PATH = os.path.abspath(sys.argv[4])     # A/B: another build of the library
 name = sys.argv[1] if len(sys.argv) > 1 else "steane"
 shots = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1 << 30
 p = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-3

@@ -16,9 +16,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 constexpr int KC = 64;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int chunks, int b_mn_major, uint32_t* sink, int commit_every) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int chunks, int b_mn_major, uint32_t* sink, int commit_every, int wait_mode) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar, dummy;
+    __shared__ __align__(8) uint64_t bar, dummy, ready;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     uint32_t rank;
@@ -27,6 +27,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int c
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"((unsigned)__cvta_generic_to_shared(&dummy)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&ready)));
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&ready)) : "memory");   // phase 0 complete
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -44,6 +46,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int c
         const uint32_t idesc = (2u << 4) | ((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         const uint32_t a0 = (unsigned)__cvta_generic_to_shared(smem), b0 = a0 + 128 * KC;
         for (int c = 0; c < chunks; ++c) {
+            if (wait_mode) {   // what the dense kernel's MMA lane does per chunk: wait (already complete here), then fence
+                const unsigned addr = (unsigned)__cvta_generic_to_shared(&ready);
+                if (wait_mode == 1)
+                    asm volatile("{\n.reg .pred p;\nW1:\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], 0;\n@p bra D1;\nbra W1;\nD1:\n}\n" ::"r"(addr) : "memory");
+                else
+                    asm volatile("{\n.reg .pred p;\nW2:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D2;\nbra W2;\nD2:\n}\n" ::"r"(addr) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
 #pragma unroll
             for (int acc = 0; acc < 2; ++acc) {
 #pragma unroll
@@ -88,16 +98,16 @@ int main() {
     cudaMalloc(&sink, sms * 128 * 4);
     const size_t smem = (size_t)128 * KC * 2;
     cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mn = 0; mn < 4; ++mn) {
-        const int chunks = 8192, ce = mn >> 1;
-        k_pair<<<sms, 128, smem>>>(64, mn & 1, sink, ce);
+    for (int mn = 0; mn < 8; ++mn) {
+        const int chunks = 8192, ce = 1, wm = mn >> 1;      // wait_mode 0 none, 1 acquire.cluster, 2 default (cta) scope, 3 = 2
+        k_pair<<<sms, 128, smem>>>(64, mn & 1, sink, ce, wm);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError())); return 1; }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         float best = 1e9f;
         for (int r = 0; r < 5; ++r) {
             cudaEventRecord(e0);
-            k_pair<<<sms, 128, smem>>>(chunks, mn & 1, sink, ce);
+            k_pair<<<sms, 128, smem>>>(chunks, mn & 1, sink, ce, wm);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms;
@@ -106,7 +116,8 @@ int main() {
         }
         const double ops = 2.0 * 256 * 256 * 32 * 4.0 * chunks * (sms / 2);
         printf("{\"op\": \"tcgen05.mma.kind::i8 m256n256k32 cta_group::2\", \"b_layout\": \"%s\", \"ms\": %.4f, \"int_ops_per_s\": %.4e, "
-               "\"commit_per_chunk\": %d, \"cycles_per_mma_at_1965MHz\": %.1f}\n", (mn & 1) ? "MN-major no-swizzle" : "K-major no-swizzle", best, ops / (best * 1e-3), ce,
+               "\"commit_per_chunk\": %d, \"wait_per_chunk\": \"%s\", \"cycles_per_mma_at_1965MHz\": %.1f}\n", (mn & 1) ? "MN-major no-swizzle" : "K-major no-swizzle", best, ops / (best * 1e-3), ce,
+               wm == 0 ? "none" : wm == 1 ? "try_wait.acquire.cluster + tcgen05.fence" : "try_wait (cta scope) + tcgen05.fence",
                best * 1e-3 * 1.965e9 / (4.0 * chunks));
     }
     return 0;

@@ -20,10 +20,13 @@ Gap sampler (core.cuh::sample_site_word_gap), used instead when thr < 2^25 (p < 
   * table cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32), k = 0..31, (1-p)^(k+1) by repeated multiplication
     in IEEE double (gap_table); a uniform word u gives d = #{k : cdf[k] <= u} clean lanes before the
     next error (d = 32: none left in this word).
-  * blocks q = 0, 1, ...; each block gives two draws (u, tw) = (w0, w1), (w2, w3).  With pos = next
-    lane to decide: pos + d >= 32 ends the word; otherwise the error sits at lane pos + d, its type is
-    the first two-bit field of tw (from the low end) that is not 00, read as (x, z); if all 16 fields
-    are 00 the draw is discarded (pos unchanged).
+  * a draw is a pair (u, tw).  With pos = next lane to decide: pos + d >= 32 ends the word; otherwise
+    the error sits at lane pos + d, its type is the first two-bit field of tw (from the low end) that is
+    not 00, read as (x, z); if all 16 fields are 00 the draw is discarded (pos unchanged).
+  * the first u of site j is word j & 3 of the block with counter (g_lo, g_hi, j >> 2, 0): four sites
+    share their first block.  Everything after it comes from the site's own blocks, counter
+    (g_lo, g_hi, j, q), q = 1, 2, ...: block 1 gives the first draw's tw = w0 and the second draw
+    (w2, w3) (w1 unused); blocks q >= 2 give two draws each, (w0, w1) then (w2, w3).
 """
 
 import numpy as np
@@ -87,17 +90,20 @@ def _sample_words_gap(seed, first_word, n_words, n, p, site0=0):
     g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
     ex = np.zeros((n, n_words), dtype=np.uint32)
     ez = np.zeros((n, n_words), dtype=np.uint32)
+    shared = {}
     for row in range(n):
         j = site0 + row
-        w = _blocks(seed, g, j, np.zeros(n_words, dtype=np.uint64))
-        hit = np.flatnonzero(w[:, 0].astype(np.uint64) < cdf[31])          # words with at least one error
+        if j >> 2 not in shared:
+            shared[j >> 2] = _blocks(seed, g, j >> 2, np.zeros(n_words, dtype=np.uint64))
+        first = shared[j >> 2][:, j & 3]
+        hit = np.flatnonzero(first.astype(np.uint64) < cdf[31])            # words with at least one error
         for idx in hit:
-            buf = w[idx]
-            pos, blk, x, z = 0, 1, 0, 0
+            buf = _blocks(seed, g[idx:idx + 1], j, np.array([1], dtype=np.uint64))[0]
+            draws = [(int(first[idx]), int(buf[0])), (int(buf[2]), int(buf[3]))]
+            pos, blk, x, z = 0, 2, 0, 0
             done = False
             while not done:
-                for h in (0, 1):
-                    u, tw = int(buf[2 * h]), int(buf[2 * h + 1])
+                for u, tw in draws:
                     d = int(np.count_nonzero(cdf <= u))
                     if pos + d >= 32:
                         done = True
@@ -115,6 +121,7 @@ def _sample_words_gap(seed, first_word, n_words, n, p, site0=0):
                         break
                 if not done:
                     buf = _blocks(seed, g[idx:idx + 1], j, np.array([blk], dtype=np.uint64))[0]
+                    draws = [(int(buf[0]), int(buf[1])), (int(buf[2]), int(buf[3]))]
                     blk += 1
             ex[row, idx], ez[row, idx] = x, z
     return ex, ez

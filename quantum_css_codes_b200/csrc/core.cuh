@@ -179,11 +179,17 @@ QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t th
 // before the next error by inverse CDF.  cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32) (host table, computed
 // by repeated multiplication in double precision so that C and numpy agree bit for bit); a 32-bit
 // uniform u gives d = #{k : cdf[k] <= u} clean lanes, d = 32 meaning "no further error in this word".
-// One Philox block supplies two draws (u, tw) = (w0, w1), (w2, w3): tw provides 16 two-bit attempts at
-// the Pauli type ((x, z) != (0, 0), scanned from the low end); if all 16 are (0, 0) the whole draw is
-// discarded and redrawn, which keeps gap and type exactly independent.  Expected blocks per word:
-// 1 + 32 p / 2 instead of 2.2, and the common path is one compare after the block.
-//   counter = (g_lo, g_hi, j, block index), key = seed -- as in the bit-serial sampler above.
+// A draw is a pair (u, tw): tw provides 16 two-bit attempts at the Pauli type ((x, z) != (0, 0), scanned from the
+// low end); if all 16 are (0, 0) the whole draw is discarded and redrawn, which keeps gap and type exactly
+// independent.  Where the words come from (key = seed throughout):
+//   first u of site j     word j & 3 of the block with counter (g_lo, g_hi, j >> 2, 0): FOUR sites share their first
+//                         block, because at p = 1e-3 97 % of the site-words are settled by that one compare
+//                         (u >= cdf[31]: no error among the 32 lanes) and a block per site would waste three of its
+//                         four words -- the sampler's cost is its Philox blocks;
+//   everything after it   the site's own blocks, counter (g_lo, g_hi, j, q), q = 1, 2, ...: block 1 gives the first
+//                         draw's tw = w0 and the second draw (w2, w3) (w1 is not used); blocks q >= 2 give two draws
+//                         each, (w0, w1) then (w2, w3).
+// Expected blocks per site-word: 1/4 + 32 p (bit-serial: 2.2).
 struct GapTable {
     uint32_t cdf[32];
     uint32_t inv;            // floor((2^32 - 1) / max(cdf[0], 1)): first guess d ~ u / cdf[0]
@@ -237,23 +243,29 @@ void sample_gap_rest(uint32_t k0, uint32_t k1, uint32_t g_lo, uint32_t g_hi, uin
     px.k1 = k1;
     if (!gap_draw(t, w2, w3, pos, x, z)) return;
     uint32_t buf[4];
-    for (uint32_t blk = 1u;; ++blk) {
+    for (uint32_t blk = 2u;; ++blk) {
         px.block(g_lo, g_hi, j, blk, buf);
         if (!gap_draw(t, buf[0], buf[1], pos, x, z)) return;
         if (!gap_draw(t, buf[2], buf[3], pos, x, z)) return;
     }
 }
 
-// The gap sampler after its first Philox block `buf` (block index 0 of counter (g, j)) -- split off so that a
-// caller can compute the first blocks of several site-words back to back (independent 10-round chains) before
-// looking at any of them.
-QCSS_HD void gap_finish(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t, uint32_t cdf31,
-                        const uint32_t (&buf)[4], uint32_t& x, uint32_t& z) {
+// First uniforms of the four sites 4 jq .. 4 jq + 3 of word g: one block.  A site whose word is >= cdf31 = cdf[31] has
+// no error among its 32 lanes; the others go through gap_finish.
+QCSS_HD void gap_first4(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t jq, uint32_t (&u)[4]) {
+    px.block(g_lo, g_hi, jq, 0u, u);
+}
+
+// The gap sampler of site j after its first uniform u0 (< cdf31: the caller has looked) -- split off so that a caller
+// can compute the shared first blocks of many sites back to back (independent 10-round chains) before looking at any.
+QCSS_HD void gap_finish(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t, uint32_t u0,
+                        uint32_t& x, uint32_t& z) {
     x = 0u;
     z = 0u;
-    if (buf[0] >= cdf31) return;                       // no error among the 32 lanes (cdf31 = t.cdf[31])
+    uint32_t buf[4];
+    px.block(g_lo, g_hi, j, 1u, buf);
     uint32_t pos = 0u;
-    gap_draw(t, buf[0], buf[1], pos, x, z);            // first error: inline (3 % of the words)
+    gap_draw(t, u0, buf[0], pos, x, z);                // first error: inline (3 % of the words)
     if (pos >= 32u || buf[2] >= t.cdf[31u - pos]) return;              // usually the only one
     sample_gap_rest(px.k0, px.k1, g_lo, g_hi, j, t, pos, buf[2], buf[3], x, z);
 }
@@ -264,9 +276,13 @@ QCSS_HD void sample_site_word_gap(uint64_t seed, uint64_t g, uint32_t j, const G
     px.k0 = (uint32_t)seed;
     px.k1 = (uint32_t)(seed >> 32);
     const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
-    uint32_t buf[4];
-    px.block(g_lo, g_hi, j, 0u, buf);
-    gap_finish(px, g_lo, g_hi, j, t, cdf31, buf, x, z);
+    uint32_t u[4];
+    gap_first4(px, g_lo, g_hi, j >> 2, u);
+    const uint32_t u0 = (j & 2u) ? ((j & 1u) ? u[3] : u[2]) : ((j & 1u) ? u[1] : u[0]);
+    x = 0u;
+    z = 0u;
+    if (u0 >= cdf31) return;                           // no error among the 32 lanes
+    gap_finish(px, g_lo, g_hi, j, t, u0, x, z);
 }
 
 QCSS_HD uint32_t popc32(uint32_t v) {

@@ -138,10 +138,14 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
                 for (int k = 0; k < 3; ++k) {
                     const uint32_t cdf31 = k == 0 ? cdf31_p : cdf31_q;
 #pragma unroll
-                    for (int j = 0; j < N; ++j) {
+                    for (int jq = 0; jq < (N + 3) / 4; ++jq) {   // four sites share their first block (core.cuh)
                         uint32_t b[4];
-                        ph.block(g_lo, g_hi, base + 32u * k + (uint32_t)j, 0u, b);
-                        if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (k << 5) | j);
+                        gap_first4(ph, g_lo, g_hi, ((base + 32u * k) >> 2) + (uint32_t)jq, b);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int j = 4 * jq + c;
+                            if (j < N && b[c] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (k << 5) | j);
+                        }
                     }
                 }
             }

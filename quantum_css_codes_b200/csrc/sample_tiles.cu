@@ -138,21 +138,28 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
             const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
             // (the arrays were zeroed with 16-byte stores before this phase; a clean site-word costs nothing more.
             //  One shared atomic per erring lane: a warp-aggregated push cost 17 % of all instructions.)
-            auto first_look = [&](int idx, const uint32_t (&b)[4]) {
-                if (b[0] < cdf31) queue[atomicAdd(&q_count, 1)] = (uint16_t)idx;
+            // Four qubits share their first block (core.cuh): group index gi = (qubit >> 2) * kSubWords + word.
+            auto first_look = [&](int gi, const uint32_t (&b)[4]) {
+                const int jq = gi / kSubWords;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = 4 * jq + c;
+                    if (j < n && b[c] < cdf31) queue[atomicAdd(&q_count, 1)] = (uint16_t)(j * kSubWords + w);
+                }
             };
-            int idx = threadIdx.x;
-            for (; idx + kSampleThreads < total; idx += 2 * kSampleThreads) {
+            const int groups = ((n + 3) / 4) * kSubWords;
+            int gi = threadIdx.x;
+            for (; gi + kSampleThreads < groups; gi += 2 * kSampleThreads) {
                 uint32_t b0[4], b1[4];
-                ph.block(g_lo, g_hi, (uint32_t)(idx / kSubWords), 0u, b0);
-                ph.block(g_lo, g_hi, (uint32_t)((idx + kSampleThreads) / kSubWords), 0u, b1);
-                first_look(idx, b0);
-                first_look(idx + kSampleThreads, b1);
+                gap_first4(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
+                gap_first4(ph, g_lo, g_hi, (uint32_t)((gi + kSampleThreads) / kSubWords), b1);
+                first_look(gi, b0);
+                first_look(gi + kSampleThreads, b1);
             }
-            if (idx < total) {
+            if (gi < groups) {
                 uint32_t b0[4];
-                ph.block(g_lo, g_hi, (uint32_t)(idx / kSubWords), 0u, b0);
-                first_look(idx, b0);
+                gap_first4(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
+                first_look(gi, b0);
             }
         } else {
             for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) {

@@ -148,8 +148,8 @@ k_small_named(const __grid_constant__ NamedArgs a) {
 // lane of the warp holds an error at that qubit (65 % of the warp-instructions at p = 1e-3, for one useful lane on
 // average) the whole warp walks the gap logic -- ncu: 92 instructions per site-word of which the Philox rounds are
 // 35 (profiles/r01_mc_fused_steane_gap_ncu_summary.txt).  Here a CTA iteration has three phases:
-//   1  every thread computes the first Philox block of each of its n site-words and pushes the few that hold an
-//      error (3 %) to a shared-memory queue as (thread, qubit); nothing else is kept;
+//   1  every thread computes the first Philox blocks of its site-words -- one block per FOUR qubits (core.cuh) -- and
+//      pushes the few sites that hold an error (3 %) to a shared-memory queue as (thread, qubit); nothing else is kept;
 //   2  the queue is handed out one item per lane: redo the block, finish the draw (same streams => same bits), and
 //      XOR the error word into the owning thread's syndrome / logical accumulators in shared memory
 //      (acc[row][thread]; rows of H and L are compile-time masks, the qubit index is the only runtime operand);
@@ -206,11 +206,15 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
                 const uint64_t g = io.first_word + (uint64_t)(u * W + w);
                 const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    if (j < n) {
+                for (int jq = 0; jq < (N + 3) / 4; ++jq) {       // four sites share their first block (core.cuh)
+                    if (4 * jq < n) {
                         uint32_t b[4];
-                        ph.block(g_lo, g_hi, (uint32_t)j, 0u, b);
-                        if (b[0] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
+                        gap_first4(ph, g_lo, g_hi, (uint32_t)jq, b);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = 4 * jq + k;
+                            if (j < N && j < n && b[k] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
+                        }
                     }
                 }
             }

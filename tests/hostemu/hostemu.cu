@@ -85,10 +85,13 @@ void run_gapq(const PX& px, const PZ& pz, const DecodeIO& io, const GenericSide*
         for (int tid = 0; tid < T && ubase + tid < units; ++tid)                       // phase 1
             for (int w = 0; w < W; ++w) {
                 const uint64_t g = io.first_word + (uint64_t)((ubase + tid) * W + w);
-                for (int j = 0; j < n; ++j) {
+                for (int jq = 0; 4 * jq < n; ++jq) {                                  // four sites share their first block
                     uint32_t b[4];
-                    ph.block((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)j, 0u, b);
-                    if (b[0] < cdf31) queue[count++] = (uint16_t)((tid << 7) | (w << 5) | j);
+                    gap_first4(ph, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)jq, b);
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = 4 * jq + c;
+                        if (j < n && b[c] < cdf31) queue[count++] = (uint16_t)((tid << 7) | (w << 5) | j);
+                    }
                 }
             }
         for (int k = count - 1; k >= 0; --k) {                                         // phase 2, any order
@@ -152,10 +155,14 @@ void run_ecq(const PX& px, const PZ& pz, const EcParams& ec, const GenericSide* 
             for (int tid = 0; tid < live; ++tid) {
                 const uint64_t g = ec.first_word + (uint64_t)(wbase + tid);
                 for (int k = 0; k < 3; ++k)
-                    for (int j = 0; j < n; ++j) {
+                    for (int jq = 0; 4 * jq < n; ++jq) {
                         uint32_t b[4];
-                        ph.block((uint32_t)g, (uint32_t)(g >> 32), base + 32u * k + (uint32_t)j, 0u, b);
-                        if (b[0] < (k == 0 ? ec.tab_p.cdf[31] : ec.tab_q.cdf[31])) queue[count++] = (uint16_t)((tid << 7) | (k << 5) | j);
+                        gap_first4(ph, (uint32_t)g, (uint32_t)(g >> 32), ((base + 32u * k) >> 2) + (uint32_t)jq, b);
+                        for (int c = 0; c < 4; ++c) {
+                            const int j = 4 * jq + c;
+                            if (j < n && b[c] < (k == 0 ? ec.tab_p.cdf[31] : ec.tab_q.cdf[31]))
+                                queue[count++] = (uint16_t)((tid << 7) | (k << 5) | j);
+                        }
                     }
             }
             for (int i = count - 1; i >= 0; --i) {

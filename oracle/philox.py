@@ -23,10 +23,12 @@ Gap sampler (core.cuh::sample_site_word_gap), used instead when thr < 2^25 (p < 
   * a draw is a pair (u, tw).  With pos = next lane to decide: pos + d >= 32 ends the word; otherwise
     the error sits at lane pos + d, its type is the first two-bit field of tw (from the low end) that is
     not 00, read as (x, z); if all 16 fields are 00 the draw is discarded (pos unchanged).
-  * the first u of site j is word j & 3 of the block with counter (g_lo, g_hi, j >> 2, 0): four sites
-    share their first block.  Everything after it comes from the site's own blocks, counter
-    (g_lo, g_hi, j, q), q = 1, 2, ...: block 1 gives the first draw's tw = w0 and the second draw
-    (w2, w3) (w1 unused); blocks q >= 2 give two draws each, (w0, w1) then (w2, w3).
+  * the first look at site j is 16 bits: half j & 1 (0 = low) of word (j & 7) >> 1 of the block with counter
+    (g_lo, g_hi, j >> 3, 0) -- eight sites share that block.  They are the HIGH half h of the site's first
+    uniform u0; h > cdf[31] >> 16 means no error among the 32 lanes.  Everything after it comes from the
+    site's own blocks, counter (g_lo, g_hi, j, q), q = 1, 2, ...: block 1 gives the first draw's tw = w0, the low
+    half of u0 (u0 = h << 16 | w1 & 0xffff) and the second draw (w2, w3); blocks q >= 2 give two draws each,
+    (w0, w1) then (w2, w3).
 """
 
 import numpy as np
@@ -90,16 +92,19 @@ def _sample_words_gap(seed, first_word, n_words, n, p, site0=0):
     g = np.arange(first_word, first_word + n_words, dtype=np.uint64)
     ex = np.zeros((n, n_words), dtype=np.uint32)
     ez = np.zeros((n, n_words), dtype=np.uint32)
+    look16 = (int(cdf[31]) >> 16) + 1
     shared = {}
     for row in range(n):
         j = site0 + row
-        if j >> 2 not in shared:
-            shared[j >> 2] = _blocks(seed, g, j >> 2, np.zeros(n_words, dtype=np.uint64))
-        first = shared[j >> 2][:, j & 3]
-        hit = np.flatnonzero(first.astype(np.uint64) < cdf[31])            # words with at least one error
+        if j >> 3 not in shared:
+            shared[j >> 3] = _blocks(seed, g, j >> 3, np.zeros(n_words, dtype=np.uint64))
+        word = shared[j >> 3][:, (j & 7) >> 1].astype(np.uint64)
+        first = (word >> np.uint64(16)) if (j & 1) else (word & np.uint64(0xFFFF))   # high half of the first uniform
+        hit = np.flatnonzero(first < look16)                               # words that may hold an error
         for idx in hit:
             buf = _blocks(seed, g[idx:idx + 1], j, np.array([1], dtype=np.uint64))[0]
-            draws = [(int(first[idx]), int(buf[0])), (int(buf[2]), int(buf[3]))]
+            u0 = (int(first[idx]) << 16) | (int(buf[1]) & 0xFFFF)
+            draws = [(u0, int(buf[0])), (int(buf[2]), int(buf[3]))]
             pos, blk, x, z = 0, 2, 0, 0
             done = False
             while not done:

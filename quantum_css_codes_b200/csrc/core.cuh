@@ -182,14 +182,16 @@ QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t th
 // A draw is a pair (u, tw): tw provides 16 two-bit attempts at the Pauli type ((x, z) != (0, 0), scanned from the
 // low end); if all 16 are (0, 0) the whole draw is discarded and redrawn, which keeps gap and type exactly
 // independent.  Where the words come from (key = seed throughout):
-//   first u of site j     word j & 3 of the block with counter (g_lo, g_hi, j >> 2, 0): FOUR sites share their first
-//                         block, because at p = 1e-3 97 % of the site-words are settled by that one compare
-//                         (u >= cdf[31]: no error among the 32 lanes) and a block per site would waste three of its
-//                         four words -- the sampler's cost is its Philox blocks;
+//   first look at site j  16 bits: half j & 1 (0 = low) of word (j & 7) >> 1 of the block with counter
+//                         (g_lo, g_hi, j >> 3, 0) -- EIGHT sites share that block, because at p = 1e-3 97 % of the
+//                         site-words are settled by one compare and the sampler's cost is its Philox blocks.  The 16
+//                         bits are the HIGH half h of the site's first uniform u0: h > cdf[31] >> 16 already says
+//                         u0 >= cdf[31], i.e. no error among the 32 lanes;
 //   everything after it   the site's own blocks, counter (g_lo, g_hi, j, q), q = 1, 2, ...: block 1 gives the first
-//                         draw's tw = w0 and the second draw (w2, w3) (w1 is not used); blocks q >= 2 give two draws
-//                         each, (w0, w1) then (w2, w3).
-// Expected blocks per site-word: 1/4 + 32 p (bit-serial: 2.2).
+//                         draw's tw = w0, the LOW half of u0 = low 16 bits of w1 (u0 = h << 16 | w1 & 0xffff, tested
+//                         exactly against cdf[31]) and the second draw (w2, w3); blocks q >= 2 give two draws each,
+//                         (w0, w1) then (w2, w3).
+// Expected blocks per site-word: 1/8 + 32 p (bit-serial: 2.2).
 struct GapTable {
     uint32_t cdf[32];
     uint32_t inv;            // floor((2^32 - 1) / max(cdf[0], 1)): first guess d ~ u / cdf[0]
@@ -250,20 +252,35 @@ void sample_gap_rest(uint32_t k0, uint32_t k1, uint32_t g_lo, uint32_t g_hi, uin
     }
 }
 
-// First uniforms of the four sites 4 jq .. 4 jq + 3 of word g: one block.  A site whose word is >= cdf31 = cdf[31] has
-// no error among its 32 lanes; the others go through gap_finish.
-QCSS_HD void gap_first4(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t jq, uint32_t (&u)[4]) {
-    px.block(g_lo, g_hi, jq, 0u, u);
+// First-look halves of the eight sites 8 jo .. 8 jo + 7 of word g: one block.
+QCSS_HD void gap_first8(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t jo, uint32_t (&h)[4]) {
+    px.block(g_lo, g_hi, jo, 0u, h);
 }
 
-// The gap sampler of site j after its first uniform u0 (< cdf31: the caller has looked) -- split off so that a caller
+// the 16 first-look bits of site 8 jo + c (c < 8, a compile-time constant at the unrolled call sites)
+QCSS_HD uint32_t gap_half(const uint32_t (&h)[4], int c) {
+    return (c & 1) ? (h[c >> 1] >> 16) : (h[c >> 1] & 0xFFFFu);
+}
+
+// h < gap_look16(cdf31)  <=>  the site may hold an error (its first uniform can still be below cdf31)
+QCSS_HD uint32_t gap_look16(uint32_t cdf31) { return (cdf31 >> 16) + 1u; }
+
+// the same test on the block words without extracting the half: look_hi = gap_look16(cdf31) << 16 (p < 1/128 keeps
+// cdf31 below 2^30, so the shift cannot overflow)
+QCSS_HD bool gap_look(const uint32_t (&h)[4], int c, uint32_t look_hi) {
+    return (c & 1) ? (h[c >> 1] < look_hi) : ((h[c >> 1] << 16) < look_hi);
+}
+
+// The gap sampler of site j after its first look h (< gap_look16: the caller has looked) -- split off so that a caller
 // can compute the shared first blocks of many sites back to back (independent 10-round chains) before looking at any.
-QCSS_HD void gap_finish(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t, uint32_t u0,
+QCSS_HD void gap_finish(const Philox& px, uint32_t g_lo, uint32_t g_hi, uint32_t j, const GapTable& t, uint32_t h,
                         uint32_t& x, uint32_t& z) {
     x = 0u;
     z = 0u;
     uint32_t buf[4];
     px.block(g_lo, g_hi, j, 1u, buf);
+    const uint32_t u0 = (h << 16) | (buf[1] & 0xFFFFu);
+    if (u0 >= t.cdf[31]) return;                       // no error among the 32 lanes after all (2^-16 of the looks)
     uint32_t pos = 0u;
     gap_draw(t, u0, buf[0], pos, x, z);                // first error: inline (3 % of the words)
     if (pos >= 32u || buf[2] >= t.cdf[31u - pos]) return;              // usually the only one
@@ -276,13 +293,14 @@ QCSS_HD void sample_site_word_gap(uint64_t seed, uint64_t g, uint32_t j, const G
     px.k0 = (uint32_t)seed;
     px.k1 = (uint32_t)(seed >> 32);
     const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
-    uint32_t u[4];
-    gap_first4(px, g_lo, g_hi, j >> 2, u);
-    const uint32_t u0 = (j & 2u) ? ((j & 1u) ? u[3] : u[2]) : ((j & 1u) ? u[1] : u[0]);
+    uint32_t hb[4];
+    gap_first8(px, g_lo, g_hi, j >> 3, hb);
+    const uint32_t wsel = (j & 4u) ? ((j & 2u) ? hb[3] : hb[2]) : ((j & 2u) ? hb[1] : hb[0]);
+    const uint32_t h = (j & 1u) ? (wsel >> 16) : (wsel & 0xFFFFu);
     x = 0u;
     z = 0u;
-    if (u0 >= cdf31) return;                           // no error among the 32 lanes
-    gap_finish(px, g_lo, g_hi, j, t, u0, x, z);
+    if (h >= gap_look16(cdf31)) return;                // no error among the 32 lanes
+    gap_finish(px, g_lo, g_hi, j, t, h, x, z);
 }
 
 QCSS_HD uint32_t popc32(uint32_t v) {

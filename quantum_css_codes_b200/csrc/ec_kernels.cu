@@ -74,7 +74,7 @@ k_ec_named(const __grid_constant__ EcNamedArgs a) {
 // ---- CTA-wide two-phase form (both error rates below 1/128, static descriptors) ------------------------------
 // Same idea as small_common.cuh::k_small_named_gapq: in the in-place kernel a warp walks the gap logic whenever any
 // of its lanes holds an error, three draws per qubit per round.  Here, per round: (1) every thread computes the
-// first Philox block of its 3 n site-words and queues those with an error as (thread, stream, qubit); (2) the queue
+// first-look Philox blocks of its 3 n site-words (one per eight sites) and queues those that may hold an error as (thread, stream, qubit); (2) the queue
 // is handed out one item per lane, the draw finished and its error words XORed into the owner's DELTA rows in shared
 // memory -- [dS_x | dl_x | dS_z | dl_z | H.a_x | H.b_x | L.b_x | H.b_z], the five places ec_rounds.cuh folds a
 // draw into; (3) the owner applies the deltas to its register state (S, l), clears them and performs the two
@@ -108,7 +108,7 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
     if (tid < 2) q_count[tid] = 0;
     for (int i = tid; i < ROWS * kThreads; i += kThreads) acc[i] = 0u;
     __syncthreads();
-    const uint32_t cdf31_p = s_tab[0].cdf[31], cdf31_q = s_tab[1].cdf[31];
+    const uint32_t look_p = gap_look16(s_tab[0].cdf[31]) << 16, look_q = gap_look16(s_tab[1].cdf[31]) << 16;
     Philox ph;
     ph.k0 = (uint32_t)ec.seed;
     ph.k1 = (uint32_t)(ec.seed >> 32);
@@ -134,19 +134,29 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
             const uint32_t base = (uint32_t)(3 * r) << 5;
             int* const qc = &q_count[phase];
             if (active) {
+                uint32_t hit[3];
+                int total = 0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const uint32_t cdf31 = k == 0 ? cdf31_p : cdf31_q;
+                    const uint32_t look_hi = k == 0 ? look_p : look_q;
+                    uint32_t m = 0u;
 #pragma unroll
-                    for (int jq = 0; jq < (N + 3) / 4; ++jq) {   // four sites share their first block (core.cuh)
-                        uint32_t b[4];
-                        gap_first4(ph, g_lo, g_hi, ((base + 32u * k) >> 2) + (uint32_t)jq, b);
+                    for (int jo = 0; jo < (N + 7) / 8; ++jo) {   // eight sites share their first-look block (core.cuh)
+                        uint32_t hb[4];
+                        gap_first8(ph, g_lo, g_hi, ((base + 32u * k) >> 3) + (uint32_t)jo, hb);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int j = 4 * jq + c;
-                            if (j < N && b[c] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (k << 5) | j);
-                        }
+                        for (int c = 0; c < 8; ++c)
+                            if (8 * jo + c < N && gap_look(hb, c, look_hi)) m |= 1u << (8 * jo + c);
                     }
+                    hit[k] = m;
+                    total += (int)popc32(m);
+                }
+                if (total != 0) {                                // one shared atomic per thread
+                    int at = atomicAdd(qc, total);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        for (uint32_t m = hit[k]; m != 0u; m &= m - 1u)
+                            queue[at++] = (uint16_t)((tid << 7) | (k << 5) | (int)ctz32(m));
                 }
             }
             __syncthreads();

@@ -90,7 +90,7 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
     if (a.sx != nullptr) stage_csr(a.hx, ptr_x, cols_x);
     if (a.sz != nullptr) stage_csr(a.hz, ptr_z, cols_z);
     __syncthreads();
-    const uint32_t cdf31 = s_gap.cdf[31];
+    const uint32_t cdf31 = s_gap.cdf[31], look_hi = gap_look16(cdf31) << 16;
     const int64_t tiles = (a.words + kTileWords - 1) / kTileWords;
     const int64_t subs = tiles * (kTileWords / kSubWords);
     for (int64_t st = blockIdx.x; st < subs; st += gridDim.x) {
@@ -126,7 +126,7 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
             if (!a.use_gap)
                 for (int idx = threadIdx.x; idx < total; idx += kSampleThreads) put(idx, 0u, 0u, gw);
         } else if (a.use_gap) {
-            // Phase 1: first Philox block of every site-word (two per iteration: independent 10-round chains); 97 %
+            // Phase 1: first-look Philox block of every eight site-words (two per iteration: independent 10-round chains); 97 %
             // of them (p = 1e-3) hold no error and are done after one compare.  The others are QUEUED instead of
             // being finished in place: with ~1 erring lane per warp-instruction, finishing in place makes every
             // warp pay the gap logic for one useful lane (65 % of the warps at p = 1e-3; ncu: the logic was
@@ -136,29 +136,33 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
             ph.k1 = (uint32_t)(a.seed >> 32);
             const uint64_t g = a.first_word + (uint64_t)gw;
             const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
-            // (the arrays were zeroed with 16-byte stores before this phase; a clean site-word costs nothing more.
-            //  One shared atomic per erring lane: a warp-aggregated push cost 17 % of all instructions.)
-            // Four qubits share their first block (core.cuh): group index gi = (qubit >> 2) * kSubWords + word.
-            auto first_look = [&](int gi, const uint32_t (&b)[4]) {
-                const int jq = gi / kSubWords;
+            // (the arrays were zeroed with 16-byte stores before this phase; a clean site-word costs nothing more.)
+            // Eight qubits share their first-look block (core.cuh): group index gi = (qubit >> 3) * kSubWords + word.
+            // The hits of a group collect in a mask, branch-free; one shared atomic per thread with hits.
+            auto first_look = [&](int gi, const uint32_t (&hb)[4]) {
+                const int j0 = 8 * (gi / kSubWords);
+                uint32_t m = 0u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = 4 * jq + c;
-                    if (j < n && b[c] < cdf31) queue[atomicAdd(&q_count, 1)] = (uint16_t)(j * kSubWords + w);
+                for (int c = 0; c < 8; ++c)
+                    if (gap_look(hb, c, look_hi)) m |= 1u << c;
+                if (j0 + 8 > n) m &= (1u << (n - j0)) - 1u;
+                if (m != 0u) {
+                    int at = atomicAdd(&q_count, (int)popc32(m));
+                    for (; m != 0u; m &= m - 1u) queue[at++] = (uint16_t)((j0 + (int)ctz32(m)) * kSubWords + w);
                 }
             };
-            const int groups = ((n + 3) / 4) * kSubWords;
+            const int groups = ((n + 7) / 8) * kSubWords;
             int gi = threadIdx.x;
             for (; gi + kSampleThreads < groups; gi += 2 * kSampleThreads) {
                 uint32_t b0[4], b1[4];
-                gap_first4(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
-                gap_first4(ph, g_lo, g_hi, (uint32_t)((gi + kSampleThreads) / kSubWords), b1);
+                gap_first8(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
+                gap_first8(ph, g_lo, g_hi, (uint32_t)((gi + kSampleThreads) / kSubWords), b1);
                 first_look(gi, b0);
                 first_look(gi + kSampleThreads, b1);
             }
             if (gi < groups) {
                 uint32_t b0[4];
-                gap_first4(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
+                gap_first8(ph, g_lo, g_hi, (uint32_t)(gi / kSubWords), b0);
                 first_look(gi, b0);
             }
         } else {

@@ -148,8 +148,9 @@ k_small_named(const __grid_constant__ NamedArgs a) {
 // lane of the warp holds an error at that qubit (65 % of the warp-instructions at p = 1e-3, for one useful lane on
 // average) the whole warp walks the gap logic -- ncu: 92 instructions per site-word of which the Philox rounds are
 // 35 (profiles/r01_mc_fused_steane_gap_ncu_summary.txt).  Here a CTA iteration has three phases:
-//   1  every thread computes the first Philox blocks of its site-words -- one block per FOUR qubits (core.cuh) -- and
-//      pushes the few sites that hold an error (3 %) to a shared-memory queue as (thread, qubit); nothing else is kept;
+//   1  every thread computes the first-look Philox blocks of its site-words -- one block per EIGHT qubits (core.cuh) --
+//      and pushes the few sites that may hold an error (3 %) to a shared-memory queue as (thread, qubit); nothing else
+//      is kept;
 //   2  the queue is handed out one item per lane: redo the block, finish the draw (same streams => same bits), and
 //      XOR the error word into the owning thread's syndrome / logical accumulators in shared memory
 //      (acc[row][thread]; rows of H and L are compile-time masks, the qubit index is the only runtime operand);
@@ -184,7 +185,7 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
     if (tid < 2) q_count[tid] = 0;
     for (int i = tid; i < ROWS * W * kThreads; i += kThreads) acc[i] = 0u;
     __syncthreads();
-    const uint32_t cdf31 = s_gap.cdf[31];
+    const uint32_t cdf31 = s_gap.cdf[31], look_hi = gap_look16(cdf31) << 16;
     Philox ph;
     ph.k0 = (uint32_t)io.seed;
     ph.k1 = (uint32_t)(io.seed >> 32);
@@ -199,24 +200,36 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
         const int64_t u = ubase + tid;
         const bool active = u < units;
         int* const qc = &q_count[it & 1];
-        // ---- 1: first blocks ----
+        // ---- 1: first looks (one block per EIGHT qubits, core.cuh); the hits collect in one mask per word, branch-free,
+        //         and are pushed with one shared atomic per thread ----
         if (active) {
+            uint32_t hit[W];
+            int total = 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 const uint64_t g = io.first_word + (uint64_t)(u * W + w);
                 const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+                uint32_t m = 0u;
 #pragma unroll
-                for (int jq = 0; jq < (N + 3) / 4; ++jq) {       // four sites share their first block (core.cuh)
-                    if (4 * jq < n) {
-                        uint32_t b[4];
-                        gap_first4(ph, g_lo, g_hi, (uint32_t)jq, b);
+                for (int jo = 0; jo < (N + 7) / 8; ++jo) {
+                    if (8 * jo < n) {
+                        uint32_t hb[4];
+                        gap_first8(ph, g_lo, g_hi, (uint32_t)jo, hb);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int j = 4 * jq + k;
-                            if (j < N && j < n && b[k] < cdf31) queue[atomicAdd(qc, 1)] = (uint16_t)((tid << 7) | (w << 5) | j);
-                        }
+                        for (int k = 0; k < 8; ++k)
+                            if (8 * jo + k < N && gap_look(hb, k, look_hi)) m |= 1u << (8 * jo + k);
                     }
                 }
+                if (n < N) m &= (1u << n) - 1u;
+                hit[w] = m;
+                total += (int)popc32(m);
+            }
+            if (total != 0) {
+                int at = atomicAdd(qc, total);
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    for (uint32_t m = hit[w]; m != 0u; m &= m - 1u)
+                        queue[at++] = (uint16_t)((tid << 7) | (w << 5) | (int)ctz32(m));
             }
         }
         __syncthreads();

@@ -77,7 +77,7 @@ void run_gapq(const PX& px, const PZ& pz, const DecodeIO& io, const GenericSide*
     Philox ph;
     ph.k0 = (uint32_t)io.seed;
     ph.k1 = (uint32_t)(io.seed >> 32);
-    const uint32_t cdf31 = io.gap.cdf[31];
+    const uint32_t cdf31 = io.gap.cdf[31], look_hi = gap_look16(cdf31) << 16;
     const int n = px.n();
     const int64_t units = io.words / W;
     for (int64_t ubase = 0; ubase < units; ubase += T) {
@@ -85,12 +85,12 @@ void run_gapq(const PX& px, const PZ& pz, const DecodeIO& io, const GenericSide*
         for (int tid = 0; tid < T && ubase + tid < units; ++tid)                       // phase 1
             for (int w = 0; w < W; ++w) {
                 const uint64_t g = io.first_word + (uint64_t)((ubase + tid) * W + w);
-                for (int jq = 0; 4 * jq < n; ++jq) {                                  // four sites share their first block
-                    uint32_t b[4];
-                    gap_first4(ph, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)jq, b);
-                    for (int c = 0; c < 4; ++c) {
-                        const int j = 4 * jq + c;
-                        if (j < n && b[c] < cdf31) queue[count++] = (uint16_t)((tid << 7) | (w << 5) | j);
+                for (int jo = 0; 8 * jo < n; ++jo) {                                  // eight sites share their first-look block
+                    uint32_t hb[4];
+                    gap_first8(ph, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)jo, hb);
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = 8 * jo + c;
+                        if (j < n && gap_look(hb, c, look_hi)) queue[count++] = (uint16_t)((tid << 7) | (w << 5) | j);
                     }
                 }
             }
@@ -155,12 +155,12 @@ void run_ecq(const PX& px, const PZ& pz, const EcParams& ec, const GenericSide* 
             for (int tid = 0; tid < live; ++tid) {
                 const uint64_t g = ec.first_word + (uint64_t)(wbase + tid);
                 for (int k = 0; k < 3; ++k)
-                    for (int jq = 0; 4 * jq < n; ++jq) {
-                        uint32_t b[4];
-                        gap_first4(ph, (uint32_t)g, (uint32_t)(g >> 32), ((base + 32u * k) >> 2) + (uint32_t)jq, b);
-                        for (int c = 0; c < 4; ++c) {
-                            const int j = 4 * jq + c;
-                            if (j < n && b[c] < (k == 0 ? ec.tab_p.cdf[31] : ec.tab_q.cdf[31]))
+                    for (int jo = 0; 8 * jo < n; ++jo) {
+                        uint32_t hb[4];
+                        gap_first8(ph, (uint32_t)g, (uint32_t)(g >> 32), ((base + 32u * k) >> 3) + (uint32_t)jo, hb);
+                        for (int c = 0; c < 8; ++c) {
+                            const int j = 8 * jo + c;
+                            if (j < n && gap_look(hb, c, gap_look16(k == 0 ? ec.tab_p.cdf[31] : ec.tab_q.cdf[31]) << 16))
                                 queue[count++] = (uint16_t)((tid << 7) | (k << 5) | j);
                         }
                     }

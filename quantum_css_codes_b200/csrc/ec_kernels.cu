@@ -78,7 +78,7 @@ k_ec_named(const __grid_constant__ EcNamedArgs a) {
 // is handed out one item per lane, the draw finished and its error words XORed into the owner's DELTA rows in shared
 // memory -- [dS_x | dl_x | dS_z | dl_z | H.a_x | H.b_x | L.b_x | H.b_z], the five places ec_rounds.cuh folds a
 // draw into; (3) the owner applies the deltas to its register state (S, l), clears them and performs the two
-// measurements exactly as process_ec_word does.  Two block barriers per round.
+// measurements exactly as process_ec_word does.  Two barriers per round (block or warp scope, see below).
 template <class DX, class DZ>
 struct EcqShape {
     static constexpr int kRows = EcDeltaRows<DX::MB, DZ::MB>::kRows;
@@ -99,19 +99,30 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
     const SideLut lut_x = small::stage_side<PX, true>(px, SideTables{a.fm_x, a.co_x, a.e32_x}, cursor);
     const SideLut lut_z = small::stage_side<PZ, true>(pz, SideTables{a.fm_z, a.co_z, a.e32_z}, cursor);
     uint32_t* const acc = reinterpret_cast<uint32_t*>(cursor);                  // [ROWS][kThreads]
-    uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * kThreads);  // [kThreads * 3 * N]
+    uint16_t* const queue0 = reinterpret_cast<uint16_t*>(acc + ROWS * kThreads);  // [kThreads * 3 * N]
     __shared__ GapTable s_tab[2];
-    __shared__ int q_count[2];
-    const int tid = threadIdx.x;
+    __shared__ int q_count[kThreads / 32 + 1][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 32) { s_tab[0].cdf[tid] = ec.tab_p.cdf[tid]; s_tab[1].cdf[tid] = ec.tab_q.cdf[tid]; }
     if (tid == 32) { s_tab[0].inv = ec.tab_p.inv; s_tab[1].inv = ec.tab_q.inv; }
-    if (tid < 2) q_count[tid] = 0;
+    if (tid <= kThreads / 32) q_count[tid][0] = q_count[tid][1] = 0;
     for (int i = tid; i < ROWS * kThreads; i += kThreads) acc[i] = 0u;
     __syncthreads();
     const uint32_t look_p = gap_look16(s_tab[0].cdf[31]) << 16, look_q = gap_look16(s_tab[1].cdf[31]) << 16;
     Philox ph;
     ph.k0 = (uint32_t)ec.seed;
     ph.k1 = (uint32_t)(ec.seed >> 32);
+    // queue scope as in small_common.cuh::run_small_gapq: per warp (warp barriers only) for the table-decoded codes when
+    // a warp's 96 n site-words of a round yield enough items, CTA-wide otherwise
+    const bool warpq = !(PX::kSliced && PZ::kSliced) &&
+                       __umulhi(s_tab[0].cdf[31], (uint32_t)(32 * N)) + 2u * __umulhi(s_tab[1].cdf[31], (uint32_t)(32 * N)) >= 12u;
+    uint16_t* const queue = queue0 + (warpq ? warp * (32 * 3 * N) : 0);
+    int (*const qcs)[2] = warpq ? &q_count[warp] : &q_count[kThreads / 32];
+    const int me = warpq ? lane : tid, team = warpq ? 32 : kThreads;
+    auto phase_barrier = [warpq]() {
+        if (warpq) __syncwarp();
+        else __syncthreads();
+    };
 
     Counters c = {0u, 0u, 0u, 0u, 0u};
     const int64_t step = (int64_t)gridDim.x * kThreads;
@@ -132,7 +143,7 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
 #pragma unroll 1
         for (int r = 0; r < ec.rounds; ++r, phase ^= 1) {
             const uint32_t base = (uint32_t)(3 * r) << 5;
-            int* const qc = &q_count[phase];
+            int* const qc = &(*qcs)[phase];
             if (active) {
                 uint32_t hit[3];
                 int total = 0;
@@ -159,10 +170,10 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
                             queue[at++] = (uint16_t)((tid << 7) | (k << 5) | (int)ctz32(m));
                 }
             }
-            __syncthreads();
+            phase_barrier();
             const int count = *qc;
-            if (tid == 0) q_count[phase ^ 1] = 0;
-            for (int i = tid; i < count; i += kThreads) {
+            if (me == 0) (*qcs)[phase ^ 1] = 0;
+            for (int i = me; i < count; i += team) {
                 const int item = queue[i], owner = item >> 7, k = (item >> 5) & 3, j = item & 31;
                 const GapTable& tab = s_tab[k == 0 ? 0 : 1];
                 uint32_t x, z;
@@ -171,7 +182,7 @@ k_ec_named_q(const __grid_constant__ EcNamedArgs a) {
                 uint32_t* const mine = acc + owner;
                 ec_fold_draw(px, pz, k, j, x, z, [mine](int row, uint32_t v) { atomicXor(mine + row * kThreads, v); });
             }
-            __syncthreads();
+            phase_barrier();
             if (active) {
                 uint32_t* const mine = acc + tid;
                 ec_apply_round(px, pz, sx, lx, sz, lz, lut_x, lut_z, w, [mine](int row) {

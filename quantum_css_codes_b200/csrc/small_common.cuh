@@ -176,19 +176,31 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
     const SideLut lut_x = stage_side<PX, true>(px, tx, cursor);
     const SideLut lut_z = stage_side<PZ, true>(pz, tz, cursor);
     uint32_t* const acc = reinterpret_cast<uint32_t*>(cursor);                      // [ROWS][W][kThreads]
-    uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * W * kThreads);  // [kThreads * W * N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ GapTable s_gap;
-    __shared__ int q_count[2];
-    const int tid = threadIdx.x;
+    __shared__ int q_count[kThreads / 32 + 1][2];
     if (tid < 32) s_gap.cdf[tid] = io.gap.cdf[tid];
     if (tid == 32) s_gap.inv = io.gap.inv;
-    if (tid < 2) q_count[tid] = 0;
+    if (tid <= kThreads / 32) q_count[tid][0] = q_count[tid][1] = 0;
     for (int i = tid; i < ROWS * W * kThreads; i += kThreads) acc[i] = 0u;
     __syncthreads();
     const uint32_t cdf31 = s_gap.cdf[31], look_hi = gap_look16(cdf31) << 16;
     Philox ph;
     ph.k0 = (uint32_t)io.seed;
     ph.k1 = (uint32_t)(io.seed >> 32);
+    // Queue scope (uniform over the launch).  CTA-wide: one queue, block barriers between the phases, phase 2 runs in
+    // as few warps as the items need.  Per warp: eight queues, warp barriers only -- every warp pays at least one
+    // phase-2 pass, so it needs enough items per warp (expected 32 W n cdf31 / 2^32 >= 12) and only pays off where the
+    // decode phase is uneven enough for block barriers to hurt (table-decoded sides: Golay-23 +11 %, QRM-15 +4 % at
+    // p = 1e-3; Steane, both sides mux trees: equal at 1e-3, -15 % at 1e-4).
+    const bool warpq = !(PX::kSliced && PZ::kSliced) && __umulhi(cdf31, (uint32_t)(32 * W * n)) >= 12u;
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(acc + ROWS * W * kThreads) + (warpq ? warp * (32 * W * N) : 0);
+    int (*const qcs)[2] = warpq ? &q_count[warp] : &q_count[kThreads / 32];
+    const int me = warpq ? lane : tid, team = warpq ? 32 : kThreads;
+    auto phase_barrier = [warpq]() {
+        if (warpq) __syncwarp();
+        else __syncthreads();
+    };
 
     Counters c = {0u, 0u, 0u, 0u, 0u};
     const int64_t units = io.words / W;                      // FAST: whole units only; thread-unit u = words W u .. W u + W - 1
@@ -199,7 +211,7 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
         const int64_t ubase = cta0 + it * step;
         const int64_t u = ubase + tid;
         const bool active = u < units;
-        int* const qc = &q_count[it & 1];
+        int* const qc = &(*qcs)[it & 1];
         // ---- 1: first looks (one block per EIGHT qubits, core.cuh); the hits collect in one mask per word, branch-free,
         //         and are pushed with one shared atomic per thread ----
         if (active) {
@@ -232,11 +244,11 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
                         queue[at++] = (uint16_t)((tid << 7) | (w << 5) | (int)ctz32(m));
             }
         }
-        __syncthreads();
+        phase_barrier();
         // ---- 2: finish the queued draws, one per lane ----
         const int count = *qc;
-        if (tid == 0) q_count[(it + 1) & 1] = 0;             // the other counter: untouched until the next phase 1
-        for (int k = tid; k < count; k += kThreads) {
+        if (me == 0) (*qcs)[(it + 1) & 1] = 0;               // the other counter: untouched until the next phase 1
+        for (int k = me; k < count; k += team) {
             const int item = queue[k], owner = item >> 7, w = (item >> 5) & 3, j = item & 31;
             uint32_t x, z;
             sample_site_word_gap(io.seed, io.first_word + (uint64_t)((ubase + owner) * W + w), (uint32_t)j, s_gap, cdf31, x, z);
@@ -254,7 +266,7 @@ __device__ __forceinline__ void run_small_gapq(const PX& px, const PZ& pz, const
                 if (pz.lbit(j)) atomicXor(mine + (MBX + 1 + MBZ) * W * kThreads, z);
             }
         }
-        __syncthreads();
+        phase_barrier();
         // ---- 3: decode and tally ----
         if (active) {
 #pragma unroll

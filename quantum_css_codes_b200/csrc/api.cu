@@ -223,16 +223,31 @@ int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, 
         if (w > maxw) maxw = w;
     }
     if (cols.empty()) cols.push_back(0);
-    QCSS_CUDA(d_ptr.reserve(ptr.size() * sizeof(int32_t)));
-    QCSS_CUDA(d_cols.reserve(cols.size() * sizeof(uint16_t)));
+    // padded copy: rows in groups of four entries, pad = n (launch.h)
+    std::vector<int32_t> ptr4(m + 1, 0);
+    std::vector<uint16_t> cols4;
+    for (int i = 0; i < m; ++i) {
+        for (int k = ptr[i]; k < ptr[i + 1]; ++k) cols4.push_back(cols[k]);
+        while (cols4.size() & 3) cols4.push_back((uint16_t)n);
+        ptr4[i + 1] = (int32_t)(cols4.size() / 4);
+    }
+    const size_t cols_pad = (cols.size() + 3) & ~(size_t)3;            // cols4 starts 8-byte aligned
+    QCSS_CUDA(d_ptr.reserve((ptr.size() + ptr4.size()) * sizeof(int32_t)));
+    QCSS_CUDA(d_cols.reserve((cols_pad + cols4.size() + 4) * sizeof(uint16_t)));
     QCSS_CUDA(cudaMemcpy(d_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    QCSS_CUDA(cudaMemcpy((int32_t*)d_ptr.p + ptr.size(), ptr4.data(), ptr4.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     QCSS_CUDA(cudaMemcpy(d_cols.p, cols.data(), cols.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (!cols4.empty())
+        QCSS_CUDA(cudaMemcpy((uint16_t*)d_cols.p + cols_pad, cols4.data(), cols4.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     sp.m = m;
     sp.n = n;
     sp.max_row_weight = maxw;
     sp.nnz = ptr[m];
     sp.row_ptr = (const int32_t*)d_ptr.p;
     sp.cols = (const uint16_t*)d_cols.p;
+    sp.groups = ptr4[m];
+    sp.row_ptr4 = (const int32_t*)d_ptr.p + ptr.size();
+    sp.cols4 = (const uint16_t*)d_cols.p + cols_pad;
     return QCSS_OK;
 }
 

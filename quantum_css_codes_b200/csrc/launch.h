@@ -38,6 +38,11 @@ struct SparseRows {            // CSR of one parity-check matrix, device pointer
     int m, n, max_row_weight, nnz;
     const int32_t* row_ptr;    // [m + 1]
     const uint16_t* cols;      // [nnz]
+    // the same supports with every row padded to a multiple of four entries (pad = column index n, which the fused
+    // sampler keeps as an all-zero row): four column indices per 8-byte load, no remainder loop (sample_tiles.cu)
+    int groups;                // total number of 4-entry groups
+    const int32_t* row_ptr4;   // [m + 1], in groups
+    const uint16_t* cols4;     // [4 * groups], 8-byte aligned
 };
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes, int64_t e_stride,
                                   uint32_t* s_planes, int64_t s_stride, int64_t words,

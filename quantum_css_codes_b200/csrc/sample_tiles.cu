@@ -9,9 +9,10 @@
 //            and Z words) in shared memory; on the gap path in two phases -- first blocks for everyone, a queue
 //            for the few site-words that hold an error, one queued item per lane (see the kernel);
 //   XOR      thread (row slot, 16-byte chunk q) folds the rows of parity_check_c2 over the X array and of
-//            parity_check_c1 over the Z array (CSR supports in shared memory, one LDS.128 per entry) and
-//            writes 16 bytes of the syndrome tile per row; optionally the sampled errors are written too.
-// INT-bound by construction: one Philox block per 32 shots per qubit (~80 instructions) against 7 loads +
+//            parity_check_c1 over the Z array (supports in shared memory, rows padded to groups of four entries
+//            with an all-zero row as the pad: one 8-byte index load and four LDS.128 per group, no remainder loop)
+//            and writes 16 bytes of the syndrome tile per row; optionally the sampled errors are written too.
+// INT-bound by construction: one first-look Philox block per 32 shots per EIGHT qubits (core.cuh) against 7 loads +
 // XORs per 128 shots per check.  Reading a resident batch instead costs (n + m) / 8 bytes per shot per type.
 #include <cuda_runtime.h>
 
@@ -40,22 +41,29 @@ struct SampleArgs {
     GapTable gap;
 };
 
-__device__ __forceinline__ void stage_csr(const SparseRows& h, uint16_t* ptr, uint16_t* cols) {
-    for (int i = threadIdx.x; i <= h.m; i += kSampleThreads) ptr[i] = (uint16_t)__ldg(h.row_ptr + i);
-    for (int k = threadIdx.x; k < h.nnz; k += kSampleThreads) cols[k] = __ldg(h.cols + k);
+// supports in the padded form (launch.h: rows in groups of four entries, pad = the all-zero row n)
+__device__ __forceinline__ void stage_csr(const SparseRows& h, uint16_t* ptr4, uint16_t* cols4) {
+    for (int i = threadIdx.x; i <= h.m; i += kSampleThreads) ptr4[i] = (uint16_t)__ldg(h.row_ptr4 + i);
+    for (int k = threadIdx.x; k < 4 * h.groups; k += kSampleThreads) cols4[k] = __ldg(h.cols4 + k);
 }
 
-__device__ __forceinline__ void xor_rows(const SparseRows& h, const uint16_t* ptr, const uint16_t* cols,
+__device__ __forceinline__ void xor_rows(const SparseRows& h, const uint16_t* ptr4, const uint16_t* cols4,
                                          const uint32_t* planes, uint32_t* out, int64_t tile, int sub, int64_t words,
                                          uint32_t tail_mask) {
     const int q = threadIdx.x & 1, slot = threadIdx.x >> 1;
     const int64_t w0 = tile * kTileWords + sub * kSubWords + q * 4;          // first of this thread's 4 words
+    const uint32_t* const mine = planes + q * 4;
     for (int i = slot; i < h.m; i += kSlots) {
         uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-        const int o0 = ptr[i], o1 = ptr[i + 1];
-        for (int k = o0; k < o1; ++k) {
-            const uint4 v = *reinterpret_cast<const uint4*>(planes + (size_t)cols[k] * kSubWords + q * 4);
-            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        const int g0 = ptr4[i], g1 = ptr4[i + 1];
+        for (int g = g0; g < g1; ++g) {                       // four entries per step: one 8-byte index load, four LDS.128
+            const uint2 cc = *reinterpret_cast<const uint2*>(cols4 + 4 * g);
+            const uint4 v0 = *reinterpret_cast<const uint4*>(mine + (cc.x & 0xFFFFu) * kSubWords);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(mine + (cc.x >> 16) * kSubWords);
+            const uint4 v2 = *reinterpret_cast<const uint4*>(mine + (cc.y & 0xFFFFu) * kSubWords);
+            const uint4 v3 = *reinterpret_cast<const uint4*>(mine + (cc.y >> 16) * kSubWords);
+            acc.x ^= v0.x ^ v1.x; acc.y ^= v0.y ^ v1.y; acc.z ^= v0.z ^ v1.z; acc.w ^= v0.w ^ v1.w;
+            acc.x ^= v2.x ^ v3.x; acc.y ^= v2.y ^ v3.y; acc.z ^= v2.z ^ v3.z; acc.w ^= v2.w ^ v3.w;
         }
         uint32_t o[4] = {acc.x, acc.y, acc.z, acc.w};
         if (w0 + 4 > words - 1) {
@@ -75,13 +83,13 @@ __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int n = a.hx.n;
-    uint32_t* const px = reinterpret_cast<uint32_t*>(smem);                  // [n][8]
-    uint32_t* const pz = px + (size_t)n * kSubWords;
-    uint16_t* const ptr_x = reinterpret_cast<uint16_t*>(pz + (size_t)n * kSubWords);
-    uint16_t* const cols_x = ptr_x + ((a.hx.m + 2) & ~1);
-    uint16_t* const ptr_z = cols_x + ((a.hx.nnz + 1) & ~1);
-    uint16_t* const cols_z = ptr_z + ((a.hz.m + 2) & ~1);
-    uint16_t* const queue = cols_z + ((a.hz.nnz + 1) & ~1);                  // [n * 8] site-words with an error
+    uint32_t* const px = reinterpret_cast<uint32_t*>(smem);                  // [n + 1][8]; row n stays zero (CSR pad)
+    uint32_t* const pz = px + (size_t)(n + 1) * kSubWords;
+    uint16_t* const cols_x = reinterpret_cast<uint16_t*>(pz + (size_t)(n + 1) * kSubWords);   // 8-byte aligned
+    uint16_t* const cols_z = cols_x + 4 * a.hx.groups;
+    uint16_t* const ptr_x = cols_z + 4 * a.hz.groups;
+    uint16_t* const ptr_z = ptr_x + ((a.hx.m + 2) & ~1);
+    uint16_t* const queue = ptr_z + ((a.hz.m + 2) & ~1);                     // [n * 8] site-words with an error
     __shared__ GapTable s_gap;
     __shared__ int q_count;
     if (threadIdx.x == 0) q_count = 0;
@@ -89,6 +97,7 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
     if (threadIdx.x == 32) s_gap.inv = a.gap.inv;
     if (a.sx != nullptr) stage_csr(a.hx, ptr_x, cols_x);
     if (a.sz != nullptr) stage_csr(a.hz, ptr_z, cols_z);
+    if (threadIdx.x < kSubWords) px[n * kSubWords + threadIdx.x] = pz[n * kSubWords + threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t cdf31 = s_gap.cdf[31], look_hi = gap_look16(cdf31) << 16;
     const int64_t tiles = (a.words + kTileWords - 1) / kTileWords;
@@ -111,7 +120,7 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
         if (a.use_gap) {
             // gap path: everything starts as "no error" (16-byte stores; px and pz are contiguous)
             uint4* const z4 = reinterpret_cast<uint4*>(px);
-            for (int i = threadIdx.x; i < 2 * total / 4; i += kSampleThreads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = threadIdx.x; i < 2 * (total + kSubWords) / 4; i += kSampleThreads) z4[i] = make_uint4(0u, 0u, 0u, 0u);
             if (a.ex != nullptr || a.ez != nullptr) {
                 for (int i = threadIdx.x; i < total / 4; i += kSampleThreads) {
                     const int j = i / (kSubWords / 4), c = i % (kSubWords / 4);
@@ -198,9 +207,9 @@ cudaError_t launch_sample_syndrome_tiles(const SparseRows& hx, const SparseRows&
                                          uint32_t* ex, uint32_t* ez, int64_t words, uint32_t tail_mask, uint64_t seed,
                                          uint64_t first_word, uint32_t thr, uint32_t use_gap, const GapTable& gap,
                                          cudaStream_t stream) {
-    if (hx.n != hz.n || hx.n * kSubWords > 65535 || hx.nnz > 65535 || hz.nnz > 65535 || hx.m > 65534 || hz.m > 65534) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)2 * hx.n * kSubWords * 4 +
-                        2 * (size_t)(((hx.m + 2) & ~1) + ((hx.nnz + 1) & ~1) + ((hz.m + 2) & ~1) + ((hz.nnz + 1) & ~1)) +
+    if (hx.n != hz.n || hx.n * kSubWords > 65535 || hx.groups > 65535 || hz.groups > 65535 || hx.m > 65534 || hz.m > 65534) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * (hx.n + 1) * kSubWords * 4 + 8 * (size_t)(hx.groups + hz.groups) +
+                        2 * (size_t)(((hx.m + 2) & ~1) + ((hz.m + 2) & ~1)) +
                         2 * (size_t)hx.n * kSubWords;                              // + the queue of erring site-words
     if (smem > 226 * 1024) return cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(k_sample_syndrome_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -231,14 +231,28 @@ int build_sparse(int m, int n, const uint8_t* H, SparseRows& sp, DevBuf& d_ptr, 
         while (cols4.size() & 3) cols4.push_back((uint16_t)n);
         ptr4[i + 1] = (int32_t)(cols4.size() / 4);
     }
+    // transpose (CSC), rows of a column in increasing order
+    std::vector<int32_t> cptr(n + 1, 0);
+    std::vector<uint16_t> rows((size_t)ptr[m] ? (size_t)ptr[m] : 1, 0);
+    for (int k = 0; k < ptr[m]; ++k) ++cptr[cols[k] + 1];
+    for (int j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+    {
+        std::vector<int32_t> at(cptr.begin(), cptr.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int k = ptr[i]; k < ptr[i + 1]; ++k) rows[at[cols[k]]++] = (uint16_t)i;
+    }
     const size_t cols_pad = (cols.size() + 3) & ~(size_t)3;            // cols4 starts 8-byte aligned
-    QCSS_CUDA(d_ptr.reserve((ptr.size() + ptr4.size()) * sizeof(int32_t)));
-    QCSS_CUDA(d_cols.reserve((cols_pad + cols4.size() + 4) * sizeof(uint16_t)));
+    QCSS_CUDA(d_ptr.reserve((ptr.size() + ptr4.size() + cptr.size()) * sizeof(int32_t)));
+    QCSS_CUDA(d_cols.reserve((cols_pad + cols4.size() + 4 + rows.size()) * sizeof(uint16_t)));
     QCSS_CUDA(cudaMemcpy(d_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     QCSS_CUDA(cudaMemcpy((int32_t*)d_ptr.p + ptr.size(), ptr4.data(), ptr4.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    QCSS_CUDA(cudaMemcpy((int32_t*)d_ptr.p + ptr.size() + ptr4.size(), cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     QCSS_CUDA(cudaMemcpy(d_cols.p, cols.data(), cols.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     if (!cols4.empty())
         QCSS_CUDA(cudaMemcpy((uint16_t*)d_cols.p + cols_pad, cols4.data(), cols4.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    QCSS_CUDA(cudaMemcpy((uint16_t*)d_cols.p + cols_pad + cols4.size() + 4, rows.data(), rows.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    sp.col_ptr = (const int32_t*)d_ptr.p + ptr.size() + ptr4.size();
+    sp.rows = (const uint16_t*)d_cols.p + cols_pad + cols4.size() + 4;
     sp.m = m;
     sp.n = n;
     sp.max_row_weight = maxw;

@@ -43,6 +43,10 @@ struct SparseRows {            // CSR of one parity-check matrix, device pointer
     int groups;                // total number of 4-entry groups
     const int32_t* row_ptr4;   // [m + 1], in groups
     const uint16_t* cols4;     // [4 * groups], 8-byte aligned
+    // the transpose (CSC): the checks each column takes part in -- the fused sampler's gap path scatters the few
+    // sampled errors into syndrome accumulators instead of gathering mostly-zero error words
+    const int32_t* col_ptr;    // [n + 1]
+    const uint16_t* rows;      // [nnz]
 };
 cudaError_t launch_syndrome_tiled(const SparseRows& h, const uint32_t* e_planes, int64_t e_stride,
                                   uint32_t* s_planes, int64_t s_stride, int64_t words,

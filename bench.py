@@ -53,9 +53,10 @@ LOP3_PEAK = 1.8471e13             # 32-bit lane-ops/s (LOP3 / IMAD / SHF / PRMT 
 ISSUE_PEAK = 148 * 4 * 32 * 1.965e9   # thread-instructions/s: 4 warp schedulers per SM, one warp-instruction per clock each
 # thread-instructions per sampled (32-shot word, qubit) site, counted by ncu (static, per kernel build):
 # profiles/r02_mc_fused_steane_gapq8_ncu_summary.txt (k_small_named_gapq: 2.227e8 warp-inst x 32 / (2^25 words x 7)) and
-# r02_hgp_fused_sampler_q8 (sample_tiles: 2.119e9 warp-inst x 32 / (2e7 / 32 x 1600 site-words)).  Round 1: 56 / 134 --
-# the first look at a site now costs 1/8 Philox block (core.cuh), so the same rate needs fewer instructions.
-INSTR_PER_SITE_WORD = {"gapq": 30.3, "sample_tiles": 67.8}
+# r02_hgp_fused_sampler_scatter (k_sample_scatter_tiles: 1.2213e9 warp-inst x 32 / (2e7 / 32 x 1600 site-words)).
+# Round 1: 56 / 134 -- the first look at a site now costs 1/8 Philox block (core.cuh) and the large-code kernel scatters
+# the few error words instead of gathering all of them, so the same rate needs fewer instructions.
+INSTR_PER_SITE_WORD = {"gapq": 30.3, "sample_tiles": 39.1}
 
 
 def parse_args():
@@ -708,7 +709,7 @@ def measure_other_configs(ctx, peak_gbs, scale=1.0):
                 "roofline": {"bound": "int", "achieved": instr, "peak": ISSUE_PEAK, "unit": "thread-instr/s",
                              "frac": instr / ISSUE_PEAK, "traffic": None,
                              "model": "thread-instructions per sampled site-word incl. the CSR XOR phase (STATIC, ncu: "
-                                      "profiles/r02_hgp_fused_sampler_q8_ncu_summary.txt: 67.8) x site-words/s per GPU; "
+                                      "profiles/r02_hgp_fused_sampler_scatter_ncu_summary.txt: 39.1) x site-words/s per GPU; "
                                       "peak = 148 SMs x 4 schedulers x 32 lanes x 1.965 GHz"}}
 
     def c4_dense():

@@ -156,7 +156,7 @@ QCSS_API int qcss_syndrome_dev(qcss_code* code, int which, const uint64_t* d_e_p
 QCSS_API int qcss_syndrome_tiles(qcss_code* code, int which, const uint64_t* e_tiles, int64_t shots, uint64_t* s_tiles);
 /*      K3 for codes of any size: the depolarising Philox sampler of qcss_mc_sample (same streams: counter =
  *      (global 32-shot word, qubit, block), key = seed) fused into the sparse syndrome kernel; the sampled
- *      errors stay in shared memory.  sx_tiles = syndromes of the X errors under parity_check_c2 (which = 2),
+ *      errors never reach HBM unless asked for.  sx_tiles = syndromes of the X errors under parity_check_c2 (which = 2),
  *      sz_tiles = syndromes of the Z errors under parity_check_c1 (which = 1), ex_tiles / ez_tiles = the
  *      sampled errors themselves; any may be NULL; all tile-major as above.  first_shot: multiple of 1024. */
 QCSS_API int qcss_sample_syndrome_tiles(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,

@@ -6,12 +6,18 @@ Pauli-frame Monte Carlo of repeated Steane error correction, restated in numpy i
 (csrc/ec_rounds.cuh) works in syndrome space instead; agreement of the two on identical Philox streams is
 the parity check for SURVEY 8 f-4.
 
-**Parity unpinned by the reference**: css_code.py only EMITS this gadget (CSSCode.error_correct,
-css_code.py:436-470) and test/test_fidelity.py runs it on a QVM with a T1/T2 noise model; there is no
-Pauli model to compare with.  What IS the reference's: the frame update of every round, which follows
-quil_classical_correct (css_code.py:649-685): syndrome of (measured word ^ frame) with the round's parity
-check, frame ^= table.get(key, 0); and which matrices / tables serve which Pauli type (css_code.py:456-470:
-X errors <- parity_check_c2 / _c2_syndromes, Z errors <- parity_check_c1 / _c1_syndromes).
+**What pins it.**  css_code.py only EMITS this gadget (CSSCode.error_correct, css_code.py:436-470) and
+test/test_fidelity.py runs it on a QVM with a T1/T2 noise model; the reference has no Pauli noise model, so WHERE
+errors enter (one depolarising layer on the data per round, one on each verified ancilla) is this model's choice.
+Everything else is the reference's and is pinned against it: tests/test_ec_gadget.py takes the instruction stream the
+UNMODIFIED reference emits for error_correct (tests/golden/ec_gadget_golden.json, recorded by
+oracle/gen_ec_gadget_golden.py under a pyquil stub), propagates explicit Pauli errors through its CNOT / H / MEASURE
+gates, runs its classical decoder text, and requires ``round_update`` below to give the same physical error and the
+same frame registers, error for error, over two consecutive rounds, for a self-dual code (Steane) and one whose two
+sides differ (Shor-9).  That covers: which errors copy where through the two transversal CNOTs, the order of the two
+halves, which parity check / table serves which Pauli type (css_code.py:456-470: X errors <- parity_check_c2 /
+_c2_syndromes, Z errors <- parity_check_c1 / _c1_syndromes), and the frame update of quil_classical_correct
+(css_code.py:649-685): syndrome of (measured word ^ frame), frame ^= table.get(key, 0).
 
 Model (per round r, streams = Philox site 32 * stream + qubit, oracle/philox.py):
   data      e ^= depolarising(p_data)                         stream 3r
@@ -45,23 +51,31 @@ def draw(seed, first_shot, shots, n, p, stream):
     return _bits(ex, shots), _bits(ez, shots)
 
 
+def round_update(code, e_x, e_z, f_x, f_z, d, a, b):
+    """One round of the model on explicit (shots, n) bit arrays, in place: physical data error (e_x, e_z), frame
+    (f_x, f_z); d, a, b = (x, z) pairs of this round's data / ancilla-A / ancilla-B errors.  The same update is what
+    tests/test_ec_gadget.py obtains by propagating (e, a, b) through the instruction stream the UNMODIFIED reference
+    emits for CSSCode.error_correct (tests/golden/ec_gadget_golden.json)."""
+    h2, table2, lz = ocss.pauli_side(code, 2)          # X errors
+    h1, table1, lx = ocss.pauli_side(code, 1)          # Z errors
+    e_x ^= d[0]
+    e_z ^= d[1]
+    e_z ^= a[1]
+    f_x ^= omc.decode_batch(h2, table2, lz, e_x ^ a[0] ^ f_x)["corr"].astype(np.uint8)
+    e_x ^= b[0]
+    f_z ^= omc.decode_batch(h1, table1, lx, e_z ^ b[1] ^ f_z)["corr"].astype(np.uint8)
+
+
 def ec_rounds(code, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0):
     """Tally dict of ``rounds`` rounds of Steane EC on ``shots`` shots for an oracle css code object."""
     n = code.n
-    h2, table2, lz = ocss.pauli_side(code, 2)          # X errors
-    h1, table1, lx = ocss.pauli_side(code, 1)          # Z errors
     e_x = np.zeros((shots, n), dtype=np.uint8)
     e_z = np.zeros((shots, n), dtype=np.uint8)
     f_x = np.zeros((shots, n), dtype=np.uint8)
     f_z = np.zeros((shots, n), dtype=np.uint8)
     for r in range(rounds):
-        d_x, d_z = draw(seed, first_shot, shots, n, p_data, 3 * r)
-        e_x ^= d_x
-        e_z ^= d_z
-        a_x, a_z = draw(seed, first_shot, shots, n, p_ancilla, 3 * r + 1)
-        e_z ^= a_z
-        f_x ^= omc.decode_batch(h2, table2, lz, e_x ^ a_x ^ f_x)["corr"].astype(np.uint8)
-        b_x, b_z = draw(seed, first_shot, shots, n, p_ancilla, 3 * r + 2)
-        e_x ^= b_x
-        f_z ^= omc.decode_batch(h1, table1, lx, e_z ^ b_z ^ f_z)["corr"].astype(np.uint8)
+        round_update(code, e_x, e_z, f_x, f_z,
+                     draw(seed, first_shot, shots, n, p_data, 3 * r),
+                     draw(seed, first_shot, shots, n, p_ancilla, 3 * r + 1),
+                     draw(seed, first_shot, shots, n, p_ancilla, 3 * r + 2))
     return omc.tally_xz(code, e_x ^ f_x, e_z ^ f_z)

@@ -4,8 +4,9 @@
 // |0>_L ancilla -> data, X-basis measurement, quil_classical_correct with parity_check_c1 / _c1_syndromes
 // on the Z frame -- tracked as Pauli errors instead of amplitudes, so the K1/K2/K3 device functions are its
 // whole inner loop.  The reference runs this circuit on a QVM (test/test_fidelity.py); it has no Pauli
-// model, so the noise model is this file's to define (parity unpinned by the reference, pinned by
-// oracle/ec_rounds.py on identical Philox streams):
+// model, so WHERE the noise enters is this file's to define; the gadget itself is pinned: oracle/ec_rounds.py states
+// the same rounds in error space (bit-exact on identical Philox streams) and tests/test_ec_gadget.py checks that
+// statement against the instruction stream the unmodified reference emits for error_correct:
 //
 //   per round r = 0 .. rounds-1, per shot
 //     1. data block:   e ^= depolarising(p_data)                         Philox stream 3r

@@ -1,7 +1,8 @@
 """Pauli-frame Monte Carlo of repeated Steane error correction (the gadget of
 CSSCode.error_correct, css_code.py:436-470, with the frame update of quil_classical_correct,
-css_code.py:649-685).  Parity unpinned by the reference (it only emits the circuit for a QVM); pinned by
-oracle/ec_rounds.py -- an error-space numpy restatement -- on identical Philox streams, bit-exact tallies.
+css_code.py:649-685).  The kernels are compared with oracle/ec_rounds.py -- an error-space numpy restatement -- on
+identical Philox streams, bit-exact tallies; that oracle's round model is pinned against the circuit the unmodified
+reference emits in tests/test_ec_gadget.py.
 
 CPU: the kernels' per-thread code (csrc/ec_rounds.cuh, syndrome space) run on the host (tests/hostemu)
 against the oracle; model sanity properties; world_size-2 gloo sharding.  GPU: the CUDA path through the

@@ -16,7 +16,7 @@ Specification (what quantum_css_codes_b200/csrc/core.cuh::sample_site_word imple
     as (x bits, z bits); a lane accepts the first attempt where x|z = 1.
   * outputs: x plane word (X or Y), z plane word (Z or Y).
 
-Gap sampler (core.cuh::sample_site_word_gap), used instead when thr < 2^25 (p < 1/128):
+Gap sampler (core.cuh::sample_site_word_gap), used instead when thr < 2^26 (p < 1/64):
   * table cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32), k = 0..31, (1-p)^(k+1) by repeated multiplication
     in IEEE double (gap_table); a uniform word u gives d = #{k : cdf[k] <= u} clean lanes before the
     next error (d = 32: none left in this word).
@@ -74,7 +74,7 @@ def gap_table(p):
 
 
 def uses_gap_sampler(p):
-    return threshold(p) < (1 << 25)
+    return threshold(p) < (1 << 26)
 
 
 def _blocks(seed, g, j, q):

@@ -518,8 +518,8 @@ int launch_mc(qcss_code* c, double p, int64_t shots, uint64_t seed, int64_t firs
     l.io.seed = seed;
     l.io.first_word = (uint64_t)(first_shot / 32);
     l.io.thr = thr;
-    // error rates below 1/128 take the gap sampler (measured crossover on Steane: p ~ 0.008)
-    l.io.use_gap = (thr < (1u << 25)) ? 1u : 0u;
+    // error rates below 1/64 take the gap sampler (core.cuh::kGapThreshold: measured crossover p ~ 0.02)
+    l.io.use_gap = (thr < kGapThreshold) ? 1u : 0u;
     gap_table_from_p(p, &l.io.gap);
     l.named_id = c->named_id;
     l.sample = true;
@@ -560,8 +560,8 @@ int launch_ec(qcss_code* c, double p_data, double p_anc, int rounds, int64_t sho
     l.ec.rounds = rounds;
     l.ec.seed = seed;
     l.ec.first_word = (uint64_t)(first_shot / 32);
-    l.ec.gap_p = (l.ec.thr_p < (1u << 25)) ? 1u : 0u;                    // same sampler rule as qcss_mc_run
-    l.ec.gap_q = (l.ec.thr_q < (1u << 25)) ? 1u : 0u;
+    l.ec.gap_p = (l.ec.thr_p < kGapThreshold) ? 1u : 0u;                    // same sampler rule as qcss_mc_run
+    l.ec.gap_q = (l.ec.thr_q < kGapThreshold) ? 1u : 0u;
     l.gapq = options().gapq != 0;
     gap_table_from_p(p_data, &l.ec.tab_p);
     gap_table_from_p(p_anc, &l.ec.tab_q);
@@ -826,7 +826,7 @@ static int launch_sample_tiles_checked(qcss_code* c, double p, int64_t shots, ui
     if (shots == 0) return QCSS_OK;
     GapTable gap;
     gap_table_from_p(p, &gap);
-    const uint32_t use_gap = (thr < (1u << 25)) ? 1u : 0u;
+    const uint32_t use_gap = (thr < kGapThreshold) ? 1u : 0u;
     cudaError_t e = launch_sample_syndrome_tiles(c->sp2, c->sp1, (uint32_t*)d_sx, (uint32_t*)d_sz, (uint32_t*)d_ex,
                                                  (uint32_t*)d_ez, (shots + 31) / 32, tail_mask_for(shots), seed,
                                                  (uint64_t)(first_shot / 32), thr, use_gap, gap, stream);

@@ -175,7 +175,7 @@ QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t th
     }
 }
 
-// Gap sampler (p < 1/128): instead of deciding 32 lanes bit by bit, draw the number of error-free lanes
+// Gap sampler (p < 1/64): instead of deciding 32 lanes bit by bit, draw the number of error-free lanes
 // before the next error by inverse CDF.  cdf[k] = floor((1 - (1-p)^(k+1)) * 2^32) (host table, computed
 // by repeated multiplication in double precision so that C and numpy agree bit for bit); a 32-bit
 // uniform u gives d = #{k : cdf[k] <= u} clean lanes, d = 32 meaning "no further error in this word".
@@ -192,6 +192,11 @@ QCSS_HD void sample_site_word(uint64_t seed, uint64_t g, uint32_t j, uint32_t th
 //                         exactly against cdf[31]) and the second draw (w2, w3); blocks q >= 2 give two draws each,
 //                         (w0, w1) then (w2, w3).
 // Expected blocks per site-word: 1/8 + 32 p (bit-serial: 2.2).
+// Which sampler a rate takes: thr = floor(p * 2^32) below this bound -> gap sampler.  Measured on B200 with the queue
+// kernels (Steane, 2^30 shots): the gap form costs 0.147 + 152 p picoseconds per shot, the bit-serial form a flat 3.4 --
+// equal at p = 0.021; 1/64 is the last power of two on the right side (p = 0.0078: 7.3e11 against 3.1e11 shots/s).
+constexpr uint32_t kGapThreshold = 1u << 26;
+
 struct GapTable {
     uint32_t cdf[32];
     uint32_t inv;            // floor((2^32 - 1) / max(cdf[0], 1)): first guess d ~ u / cdf[0]
@@ -265,8 +270,8 @@ QCSS_HD uint32_t gap_half(const uint32_t (&h)[4], int c) {
 // h < gap_look16(cdf31)  <=>  the site may hold an error (its first uniform can still be below cdf31)
 QCSS_HD uint32_t gap_look16(uint32_t cdf31) { return (cdf31 >> 16) + 1u; }
 
-// the same test on the block words without extracting the half: look_hi = gap_look16(cdf31) << 16 (p < 1/128 keeps
-// cdf31 below 2^30, so the shift cannot overflow)
+// the same test on the block words without extracting the half: look_hi = gap_look16(cdf31) << 16 (p < 1/64 keeps
+// cdf31 below 0.4 * 2^32, so the shift cannot overflow)
 QCSS_HD bool gap_look(const uint32_t (&h)[4], int c, uint32_t look_hi) {
     return (c & 1) ? (h[c >> 1] < look_hi) : ((h[c >> 1] << 16) < look_hi);
 }

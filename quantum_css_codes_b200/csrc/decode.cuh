@@ -37,7 +37,7 @@ struct DecodeIO {
     uint64_t seed;
     uint64_t first_word;         // global index of word 0 (first_shot / 32)
     uint32_t thr;                // floor(p * 2^32)
-    uint32_t use_gap;            // p < 1/128: gap sampler (core.cuh) with the table below, else bit-serial
+    uint32_t use_gap;            // p < 1/64: gap sampler (core.cuh) with the table below, else bit-serial
     GapTable gap;
 };
 

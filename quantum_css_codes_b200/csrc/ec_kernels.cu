@@ -71,7 +71,7 @@ k_ec_named(const __grid_constant__ EcNamedArgs a) {
     run_ec(px, pz, a.ec, tx, tz);
 }
 
-// ---- CTA-wide two-phase form (both error rates below 1/128, static descriptors) ------------------------------
+// ---- CTA-wide two-phase form (both error rates below 1/64, static descriptors) ------------------------------
 // Same idea as small_common.cuh::k_small_named_gapq: in the in-place kernel a warp walks the gap logic whenever any
 // of its lanes holds an error, three draws per qubit per round.  Here, per round: (1) every thread computes the
 // first-look Philox blocks of its 3 n site-words (one per eight sites) and queues those that may hold an error as (thread, stream, qubit); (2) the queue

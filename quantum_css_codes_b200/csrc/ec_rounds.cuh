@@ -42,7 +42,7 @@ struct EcParams {
     uint64_t seed;
     uint64_t first_word;
     uint32_t thr_p, thr_q;       // floor(p * 2^32) for the data and ancilla error rates
-    uint32_t gap_p, gap_q;       // non-zero: gap sampler (rate < 1/128) with the table below
+    uint32_t gap_p, gap_q;       // non-zero: gap sampler (rate < 1/64) with the table below
     GapTable tab_p, tab_q;
 };
 

@@ -15,7 +15,7 @@ struct SmallLaunch {
     DecodeIO io;
     int named_id;              // index into named::kNamed, or -1 for the generic kernels
     bool sample;               // fused Philox sampler instead of loading error planes
-    bool gapq = true;          // sampler form below p = 1/128 (options.h): two-phase queue or in place
+    bool gapq = true;          // sampler form below p = 1/64 (options.h): two-phase queue or in place
 };
 cudaError_t launch_small(const SmallLaunch& l, cudaStream_t stream);
 int match_named(const GenericSide& x, const uint32_t* rows_x, uint32_t lx, const GenericSide& z,

@@ -8,7 +8,7 @@
 namespace qcss {
 
 struct Options {
-    int gapq = 1;         // Monte-Carlo below p = 1/128: CTA-wide two-phase gap sampler (1) or in-place form (0)
+    int gapq = 1;         // Monte-Carlo below p = 1/64: CTA-wide two-phase gap sampler (1) or in-place form (0)
     int dense = -1;       // large check matrices: -1 = by size and density, 0 = sparse kernels, 1 = tensor cores
     int named = 1;        // 1 = use a built-in static descriptor when the code matches one, 0 = generic kernels
     int gf2_kernel = 0;   // batched RREF: 0 = by shape, 1 = column-by-column, 2 = m4r (one-warp panel), 3 = m4r2, 4 = m4r4

@@ -4,7 +4,7 @@
 //
 // One CTA works on a sub-tile of 256 shots (8 words) at a time:
 //   sample   thread t draws site-words (qubit j, word w), j * 8 + w = t, t + 1024, ... with the K3 sampler
-//            (core.cuh: gap sampler below p = 1/128, bit-serial above; Philox counter = (global word, site = j,
+//            (core.cuh: gap sampler below p = 1/64, bit-serial above; Philox counter = (global word, site = j,
 //            block), key = seed -- the stream of qcss_mc_sample with n > 32 sites) into two n x 32 B arrays (X
 //            and Z words) in shared memory; on the gap path in two phases -- first blocks for everyone, a queue
 //            for the few site-words that hold an error, one queued item per lane (see the kernel);
@@ -79,7 +79,7 @@ __device__ __forceinline__ void xor_rows(const SparseRows& h, const uint16_t* pt
     }
 }
 
-// p >= 1/128 (bit-serial sampler): most site-words hold errors, so the error words are materialised in shared memory
+// p >= 1/64 (bit-serial sampler): most site-words hold errors, so the error words are materialised in shared memory
 // and the checks gather them.
 __global__ void __launch_bounds__(kSampleThreads, 1)
 k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
@@ -121,7 +121,7 @@ k_sample_syndrome_tiles(const __grid_constant__ SampleArgs a) {
     }
 }
 
-// p < 1/128 (gap sampler): 97 % of the site-words (p = 1e-3) hold no error, so no error word is ever stored.  Per
+// p < 1/64 (gap sampler): 97 % of the site-words (p = 1e-3) hold no error, so no error word is ever stored.  Per
 // sub-tile of 256 shots:
 //   1  first-look Philox block of every eight site-words (core.cuh; two per iteration: independent 10-round chains);
 //      the few sites that may hold an error are QUEUED instead of being finished in place -- with ~1 erring lane per

@@ -143,7 +143,7 @@ k_small_named(const __grid_constant__ NamedArgs a) {
     named_body<DX, DZ, VEC, SAMPLE, FAST>(a);
 }
 
-// ---- fused gap sampler, CTA-wide two-phase form (Monte-Carlo tallies of the static kernels, p < 1/128) ----------
+// ---- fused gap sampler, CTA-wide two-phase form (Monte-Carlo tallies of the static kernels, p < 1/64) ----------
 // k_small_named finishes every draw in place: thread = one 32-shot word, loop over the n qubits, and whenever ANY
 // lane of the warp holds an error at that qubit (65 % of the warp-instructions at p = 1e-3, for one useful lane on
 // average) the whole warp walks the gap logic -- ncu: 92 instructions per site-word of which the Philox rounds are
@@ -451,7 +451,7 @@ cudaError_t launch_named(const SmallLaunch& l, cudaStream_t stream) {
     // Golay-23 with VEC = 4: the first-error path inlined at 92 sites ran at 4.2e10 shots/s).
     constexpr int SVEC = 1;
     if (l.sample && l.io.use_gap && l.gapq) {
-        // Monte-Carlo tallies below p = 1/128: the CTA-wide two-phase gap sampler for the whole words
+        // Monte-Carlo tallies below p = 1/64: the CTA-wide two-phase gap sampler for the whole words
         using Shape = GapqShape<StaticPolicy<DX>, StaticPolicy<DZ>>;
         return launch_split<Shape::kW>(k_small_named_gapq<DX, DZ>, k_small_named<DX, DZ, SVEC, true, false>, a, l,
                                        smem_fast + Shape::kSmem, smem, stream);

@@ -182,7 +182,7 @@ def decode(side_x, side_z, ex_planes=None, ez_planes=None, shots=0, named_id=-1,
 
 def ec_run(side_x, side_z, p_data, p_ancilla, rounds, shots, seed=0, first_shot=0, named_id=-1, queue_form=False):
     """Host emulation of qcss_ec_run (api.cu::launch_ec + ec_kernels.cu): returns the tally dict.
-    ``queue_form``: replay the CTA-wide two-phase kernel (k_ec_named_q; static descriptors, both rates < 1/128)."""
+    ``queue_form``: replay the CTA-wide two-phase kernel (k_ec_named_q; static descriptors, both rates < 1/64)."""
     from oracle import philox as _ophilox
     L = lib()
     assert L.emu_sizeof_ec() == ctypes.sizeof(EcParams)

@@ -228,7 +228,7 @@ int emu_mc_gapq(const GenericSide* x, const GenericSide* z, const DecodeIO* io, 
     return 0;
 }
 
-// ec_kernels.cu::k_ec_named_q (static descriptors, both rates below 1/128)
+// ec_kernels.cu::k_ec_named_q (static descriptors, both rates below 1/64)
 __attribute__((visibility("default")))
 int emu_ecq(const GenericSide* x, const GenericSide* z, const EcParams* ec, int named_id, uint64_t* tally) {
 #define EMU_ECQ_CASE(ID, DX, DZ) \

@@ -24,7 +24,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMED = {"steane": 0, "qrm15": 1, "golay23": 2}
 CASES = [(0.05, 0.0, 1, 999), (0.03, 0.02, 3, 1000), (1e-3, 5e-3, 4, 2048), (0.2, 1e-3, 2, 333),
          (0.0, 0.1, 2, 640), (0.004, 0.3, 2, 500), (0.05, 0.05, 0, 256),
-         (2e-3, 3e-3, 3, 5000), (0.0, 5e-3, 2, 3000), (5e-3, 0.0, 2, 1000), (7e-3, 7e-3, 6, 9000)]
+         (2e-3, 3e-3, 3, 5000), (0.0, 5e-3, 2, 3000), (5e-3, 0.0, 2, 1000), (7e-3, 7e-3, 6, 9000),
+         (0.012, 0.015, 3, 4000)]
 _cache = {}
 
 
@@ -53,9 +54,9 @@ def test_hostemu_matches_oracle(name, static):
 @pytest.mark.parametrize("name", list(NAMED))
 def test_hostemu_queue_form_matches_oracle(name):
     """The CTA-wide two-phase EC kernel replayed on the host over its own helpers (ec_fold_draw / ec_apply_round and
-    the delta-row map): oracle tallies for every case with both rates below 1/128, ragged tails included."""
+    the delta-row map): oracle tallies for every case with both rates below 1/64, ragged tails included."""
     code, sx, sz = build(name)
-    for p, q, rounds, shots in [c for c in CASES if c[0] < 1 / 128 and c[1] < 1 / 128] + [(3e-3, 3e-3, 2, 128 * 9 + 5)]:
+    for p, q, rounds, shots in [c for c in CASES if c[0] < 1 / 64 and c[1] < 1 / 64] + [(3e-3, 3e-3, 2, 128 * 9 + 5)]:
         got = emu.ec_run(sx, sz, p, q, rounds, shots, seed=0xABCDEF12345, first_shot=256, named_id=NAMED[name], queue_form=True)
         want = oec.ec_rounds(code, p, q, rounds, shots, seed=0xABCDEF12345, first_shot=256)
         assert got == want, (p, q, rounds, shots)
@@ -189,7 +190,7 @@ def test_gpu_sharding_invariance_and_rates():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["steane", "qrm15", "golay23"])
 def test_gpu_queue_kernel_equals_in_place_kernel(name):
-    """Both error rates below 1/128: the CTA-wide two-phase kernel (k_ec_named_q) against the in-place one
+    """Both error rates below 1/64: the CTA-wide two-phase kernel (k_ec_named_q) against the in-place one
     (option "gapq" = 0) on the same Philox streams, many CTA iterations, ragged tail, offset shard."""
     dev = device_code(name)
     runs = [((1e-3, 1e-3, 10, 30_000_017), {}), ((5e-3, 2e-3, 3, 10_000_000), {}),

@@ -228,7 +228,7 @@ def test_specialize_through_csscode_and_cache():
 # ---- fused Philox sampler -----------------------------------------------------------------------
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("p", [1e-3, 0.05, 0.5, 0.0, 1.0])
+@pytest.mark.parametrize("p", [1e-3, 0.012, 0.0156, 0.0157, 0.05, 0.5, 0.0, 1.0])
 def test_fused_sampler_bit_exact_vs_oracle(name, p):
     code, ref = pair(name)
     shots, seed, first = 6000, 0xC0FFEE1234, 128 * 11
@@ -239,11 +239,12 @@ def test_fused_sampler_bit_exact_vs_oracle(name, p):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("p,shots", [(1e-3, 300_000_077), (5e-3, 50_000_000), (0.0078, 20_000_033), (1e-5, 100_000_000)])
+@pytest.mark.parametrize("p,shots", [(1e-3, 300_000_077), (5e-3, 50_000_000), (0.0078, 20_000_033), (0.0156, 20_000_033),
+                                     (1e-5, 100_000_000)])
 def test_gap_sampler_queue_kernel_equals_in_place_kernel(name, p, shots):
-    """The CTA-wide two-phase gap sampler (k_small_named_gapq, default below p = 1/128) and the in-place kernel
+    """The CTA-wide two-phase gap sampler (k_small_named_gapq, default below p = 1/64) and the in-place kernel
     (option "gapq" = 0) draw from the same Philox streams: identical tallies, at sizes that give every CTA many
-    iterations, queue loads from almost empty (p = 1e-5) to ~22 % of the site-words (p just below 1/128), and a
+    iterations, queue loads from almost empty (p = 1e-5) to ~40 % of the site-words (p just below 1/64), and a
     ragged tail; a non-aligned first_shot shard as well."""
     code, _ = pair(name)
     with _native.option("gapq", 0):

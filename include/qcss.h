@@ -84,7 +84,7 @@ QCSS_API int qcss_host_alloc(void** ptr, size_t bytes);          /* pinned host 
 QCSS_API int qcss_host_free(void* ptr);
 /* Kernel SELECTION options (process-wide).  Each one chooses between implementations whose results are
  * bit-identical -- the parity tests run both sides -- and none is ever read from the environment:
- *   "gapq"       1 (default) CTA-wide two-phase gap sampler below p = 1/128, 0 the in-place form
+ *   "gapq"       1 (default) two-phase (queue) gap sampler below p = 1/64, 0 the in-place form
  *   "dense"      -1 (default) large check matrices go to the tensor-core kernel by size and density,
  *                0 never, 1 always; taken at qcss_code_create
  *   "named"      1 (default) use a built-in static descriptor when the code matches one, 0 generic kernels;
@@ -226,9 +226,9 @@ QCSS_API int qcss_events_from_planes_dev(qcss_code* code, const uint64_t* d_ex, 
 
 /* ---- K3 fused Philox sampler + K1 + K2 (no reference counterpart).
  *      Depolarising noise: each qubit of each shot gets X, Y or Z with probability p/3 each.  For
- *      p >= 1/128 the per-shot error probability is exactly floor(p * 2^32) / 2^32; below that the
- *      gaps between errors are drawn by inverse CDF from a table quantised to 2^-32.  Streams are keyed by (seed, global shot word,
- *      qubit) so results do not depend on how shots are split over calls or GPUs;
+ *      p >= 1/64 the per-shot error probability is exactly floor(p * 2^32) / 2^32; below that the
+ *      gaps between errors are drawn by inverse CDF from a table quantised to 2^-32.  Streams are keyed by
+ *      (seed, global shot word, qubit) so results do not depend on how shots are split over calls or GPUs;
  *      first_shot must be a multiple of 128. ------------------------------------------------ */
 QCSS_API int qcss_mc_run(qcss_code* code, double p, int64_t shots, uint64_t seed, int64_t first_shot,
                 qcss_tally* tally);

@@ -1,9 +1,10 @@
 """K4 timing over widths at 1024 rows: separates discovery from replay cost per block.
-   python tools/gf2_shapes.py [batch] [gf2_kernel option]"""
+   python tools/gf2_shapes.py [batch] [gf2_kernel option] [library]"""
 import os, sys, json
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quantum_css_codes_b200 import _native
+if len(sys.argv) > 3: _native.LIB_PATH = os.path.abspath(sys.argv[3])     # A/B: another build of the library
 lib = _native.load()
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 if len(sys.argv) > 2: _native.check(lib.qcss_set_option(b"gf2_kernel", int(sys.argv[2])))

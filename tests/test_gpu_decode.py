@@ -400,6 +400,30 @@ def test_fused_sampler_midsize_code():
         assert np.array_equal(s_z, omc.syndromes_batch(mats[0], want_z))
 
 
+@pytest.mark.parametrize("n,m1,m2", [(41, 9, 23), (70, 100, 3), (127, 64, 64), (1000, 17, 700)])
+@pytest.mark.parametrize("p", [2e-3, 0.0156, 0.0157, 0.2])
+def test_fused_sampler_ragged_shapes(n, m1, m2, p):
+    """Both fused kernels (scatter below p = 1/64, gather above) on shapes that stress their index arithmetic: n not
+    a multiple of 8 (partial first-look groups), more checks than qubits, rows of weight 0 .. 9 (padded 4-entry
+    groups), columns no check touches (empty transposed supports), a ragged last tile."""
+    rng = np.random.default_rng(n * 1000 + m1)
+    mats = []
+    for m in (m1, m2):
+        h = np.zeros((m, n), dtype=np.int64)
+        for i in range(m):
+            h[i, rng.choice(n - 3, size=int(rng.integers(0, 10)), replace=False)] = 1     # the last 3 columns stay empty
+        mats.append(h)
+    code = SyndromeCode(mats[0], mats[1])
+    shots = 2 * 1024 + 333
+    s_x, s_z, e_x, e_z = code.sample_syndromes(p, shots, seed=77, first_shot=1024, return_errors=True)
+    want_x, want_z = ophilox.sample_bits(77, 1024, shots, n, p)
+    assert np.array_equal(e_x, want_x) and np.array_equal(e_z, want_z)
+    assert np.array_equal(s_x, omc.syndromes_batch(mats[1], want_x))
+    assert np.array_equal(s_z, omc.syndromes_batch(mats[0], want_z))
+    only_x, only_z = code.sample_syndromes(p, shots, seed=77, first_shot=1024)
+    assert np.array_equal(only_x, s_x) and np.array_equal(only_z, s_z)
+
+
 @pytest.mark.parametrize("n,m,row_w,shots", [(40, 20, 5, 3000), (300, 130, 9, 1025), (700, 1024, 3, 5000),
                                              (3000, 900, 6, 2500)])
 def test_tile_major_random_sparse(n, m, row_w, shots):

@@ -842,14 +842,28 @@ def measure_e2e(ctx, dev, ex, ez, n, stride, shots, args, first_shot):
         tx.copy_(ex[:, :stride_e2e])
         tz.copy_(ez[:, :stride_e2e])
         torch.cuda.synchronize()
+        if world > 1:                                            # the ranks of one box share its cores
+            _native.set_option("host_threads", max(1, (os.cpu_count() or 1) // world))
         sec, tally = wall(lambda: dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride_e2e, shots), args.e2e_steps)
-        ctx.launches += (args.e2e_steps + 1) * max(1, -(-nbytes // (32 << 20)))
+        sent, team = dev.last_transfer()
+        ctx.launches += (args.e2e_steps + 1) * 2 * max(1, -(-nbytes // (32 << 20)))
         ok = [tally[k] for k in _native.TALLY_FIELDS[1:]] == resident
         out = {"value": world * shots / sec, "unit": "shots/s", "shots_per_gpu_per_step": shots,
-               "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": 48,
+               "h2d_bytes_per_step": int(sent), "d2h_bytes_per_step": 48, "host_plane_bytes_per_step": int(2 * nbytes),
+               "host_compaction_threads": team,
                "steps": args.e2e_steps, "ms_per_step": 1e3 * sec,
-               "api": "qcss_decode_xz (pinned host bit planes, chunked H2D overlapped with kernels)",
+               "api": "qcss_decode_xz (pinned host bit planes; zero words suppressed by host threads, chunked H2D, "
+                      "expanded and decoded on the device)" if team else
+                      "qcss_decode_xz (pinned host bit planes, chunked H2D overlapped with kernels)",
+               "host_read_gbs_per_gpu": 2 * nbytes / sec / 1e9,
                "matches_resident_tally": bool(ok)}
+        if team:                                                  # the same call with plain copies, for comparison
+            with _native.option("host_compact", 0):
+                sec_p, tally_p = wall(lambda: dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride_e2e, shots), args.e2e_steps)
+            out["plain_copy"] = {"value": world * shots / sec_p, "ms_per_step": 1e3 * sec_p, "h2d_bytes_per_step": int(2 * nbytes),
+                                 "h2d_achieved_gbs_per_gpu": 2 * nbytes / sec_p / 1e9,
+                                 "matches_resident_tally": [tally_p[k] for k in _native.TALLY_FIELDS[1:]] == resident}
+            sec = sec_p                                           # the link figures below describe the plain copy
         # raw host->device ceiling of this box at this N: the same bytes with no kernels at all
         slot = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
         src = torch.from_numpy(hx.view(np.uint8))[: 64 << 20]

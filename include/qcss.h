@@ -91,6 +91,9 @@ QCSS_API int qcss_host_free(void* ptr);
  *                taken at qcss_code_create
  *   "gf2_kernel" 0 (default) batched RREF kernel by shape, 1 column-by-column, 2 m4r, 3 m4r2 (rows <= 1024),
  *                4 m4r4 (32 < rows <= 1024); a forced kernel falls back to the next one its shape limits allow
+ *   "host_compact" 1 (default) qcss_decode_xz zero-word-suppresses sparse host planes with a team of host threads before
+ *                the copy (csrc/host_compact.h), 0 always the plain chunked copy
+ *   "host_threads" size of that team: 0 (default) = min(16, hardware threads); fewer than 4 disables the path
  * QCSS_ERR_INVALID for an unknown name or a value out of range. */
 QCSS_API int qcss_set_option(const char* name, int value);
 QCSS_API int qcss_get_option(const char* name, int* value);
@@ -186,6 +189,11 @@ QCSS_API int qcss_decode(qcss_code* code, int which, const uint64_t* e_planes, i
  * in chunks (copies overlap the kernels). */
 QCSS_API int qcss_decode_xz(qcss_code* code, const uint64_t* ex_planes, const uint64_t* ez_planes,
                    int64_t e_stride, int64_t shots, qcss_tally* tally);
+/* How the last qcss_decode_xz call on this code moved its planes: bytes sent host -> device and the size of the host
+ * team that compacted them (0 = plain chunked copies).  Sparse planes (a 64-bit plane word is non-zero with probability
+ * 6 % at p = 1e-3) are zero-word-suppressed by host threads before they cross the link -- option "host_compact" (1 / 0),
+ * "host_threads" (0 = min(16, hardware threads)); csrc/host_compact.h.  Same tallies either way. */
+QCSS_API int qcss_code_last_transfer(const qcss_code* code, int64_t* h2d_bytes, int* host_threads);
 /* General device-pointer form, asynchronous on `stream` (a cudaStream_t, NULL = default). */
 QCSS_API int qcss_decode_dev(qcss_code* code, const qcss_decode_io* io, int64_t shots, void* stream);
 

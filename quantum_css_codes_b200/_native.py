@@ -72,6 +72,7 @@ PROTOTYPES = {
                                               ctypes.POINTER(ctypes.c_void_p)]),
     "qcss_code_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "qcss_code_kernel_name": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    "qcss_code_last_transfer": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]),
     "qcss_code_spec_source": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64,
                                              ctypes.POINTER(ctypes.c_int64)]),
     "qcss_code_load_specialized": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]),
@@ -382,6 +383,12 @@ class DeviceCode:
         check(self._lib.qcss_decode_xz(self.handle, _ptr(ex_planes), _ptr(ez_planes),
                                        ex_planes.shape[1], shots, ctypes.byref(tally)))
         return tally.as_dict()
+
+    def last_transfer(self):
+        """(bytes sent host -> device, size of the compacting host team) of the last ``qcss_decode_xz`` call."""
+        nbytes, threads = ctypes.c_int64(0), ctypes.c_int(0)
+        check(self._lib.qcss_code_last_transfer(self.handle, ctypes.byref(nbytes), ctypes.byref(threads)))
+        return int(nbytes.value), int(threads.value)
 
     def decode_xz_host_ptr(self, ex_ptr, ez_ptr, stride, shots):
         """Same call with raw (e.g. pinned) host pointers -- the e2e benchmark path."""

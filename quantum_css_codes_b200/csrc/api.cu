@@ -10,10 +10,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qcss.h"
+#include "host_compact.h"
 #include "launch.h"
 #include "options.h"
 #include "small_common.cuh"      // NamedArgs, launch-shape helpers (no kernel is instantiated in this file)
@@ -112,6 +115,13 @@ struct qcss_code {
     DevBuf slot_rx[kSlots], slot_rz[kSlots];          // raw (shots, n) rows / event lists of the format entry points
     DevBuf buf_a, buf_b, buf_c, buf_d, buf_e;
     DevBuf tally;
+    // compacting host->device path of qcss_decode_xz (host_compact.h): pinned staging, its device mirror, copy-done events
+    void* zs_host[kSlots] = {nullptr, nullptr, nullptr};
+    size_t zs_host_cap[kSlots] = {0, 0, 0};
+    DevBuf zs_dev[kSlots];
+    cudaEvent_t zs_ev[kSlots] = {nullptr, nullptr, nullptr};
+    int64_t last_h2d_bytes = 0;         // bytes the last host-buffer decode call sent over the link
+    int last_host_threads = 0;          // size of its compacting team (0: plain copies)
 };
 
 namespace {
@@ -632,6 +642,8 @@ QCSS_API int qcss_set_option(const char* name, int value) {
     else if (key == "dense" && value >= -1 && value <= 1) o.dense = value;
     else if (key == "named" && (value == 0 || value == 1)) o.named = value;
     else if (key == "gf2_kernel" && value >= 0 && value <= 4) o.gf2_kernel = value;
+    else if (key == "host_compact" && (value == 0 || value == 1)) o.host_compact = value;
+    else if (key == "host_threads" && value >= 0 && value <= 256) o.host_threads = value;
     else return fail(QCSS_ERR_INVALID, "unknown option or value out of range: %s = %d", name, value);
     return QCSS_OK;
 }
@@ -644,6 +656,8 @@ QCSS_API int qcss_get_option(const char* name, int* value) {
     else if (key == "dense") *value = o.dense;
     else if (key == "named") *value = o.named;
     else if (key == "gf2_kernel") *value = o.gf2_kernel;
+    else if (key == "host_compact") *value = o.host_compact;
+    else if (key == "host_threads") *value = o.host_threads;
     else return fail(QCSS_ERR_INVALID, "unknown option: %s", name);
     return QCSS_OK;
 }
@@ -752,6 +766,9 @@ QCSS_API int qcss_code_destroy(qcss_code* c) {
         c->slot_rx[i].release();
         c->slot_rz[i].release();
         if (c->slot_stream[i]) cudaStreamDestroy(c->slot_stream[i]);
+        if (c->zs_host[i]) cudaFreeHost(c->zs_host[i]);
+        c->zs_dev[i].release();
+        if (c->zs_ev[i]) cudaEventDestroy(c->zs_ev[i]);
     }
     c->buf_a.release(); c->buf_b.release(); c->buf_c.release(); c->buf_d.release(); c->buf_e.release();
     c->tally.release();
@@ -985,6 +1002,163 @@ QCSS_API int qcss_decode(qcss_code* c, int which, const uint64_t* e_planes, int6
     return QCSS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// qcss_decode_xz on SPARSE host planes: host threads compact each chunk (bitmap of non-zero words + the words,
+// host_compact.h) into pinned staging while the previous chunks are copied, expanded (k_zs_expand) and decoded on the
+// slot streams.  The link carries ~8 % of the bytes at p = 1e-3; the call is then bound by how fast the host cores read
+// the planes (100 GB/s with 16 threads on this pool's boxes against 55 GB/s of PCIe).  A chunk whose non-zero words do
+// not fit half its size goes over uncompacted.  The result is the plain path's, bit for bit (same kernel, same planes).
+int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int64_t shots, int threads) {
+    const int n = c->n, rows = 2 * n, T = threads;
+    const int64_t total_words = (shots + 63) / 64;
+    int64_t chunk_words = ((int64_t)(32u << 20) / ((int64_t)n * 8)) / kZsBlockWords * kZsBlockWords;
+    if (chunk_words < kZsBlockWords) chunk_words = kZsBlockWords;
+    const int64_t nchunks = (total_words + chunk_words - 1) / chunk_words;
+    const int bpr_max = (int)(chunk_words / kZsBlockWords);
+    const size_t tasks_max = (size_t)rows * bpr_max;
+    const size_t bm_bytes = tasks_max * 32 * 8, off_bytes = (tasks_max * 4 + 7) & ~(size_t)7;
+    const size_t region_cap = ((size_t)rows * chunk_words / 2) / T + kZsBlockWords + 8;       // words per worker
+    const size_t stage_bytes = bm_bytes + off_bytes + (size_t)T * region_cap * 8;
+    if ((size_t)T * region_cap >= ((size_t)1 << 32)) return fail(QCSS_ERR_INVALID, "chunk too large for 32-bit value offsets");
+    const size_t slot_bytes = (size_t)n * chunk_words * 8;
+    for (int i = 0; i < kSlots; ++i) {
+        QCSS_CUDA(c->slot_x[i].reserve(slot_bytes));
+        QCSS_CUDA(c->slot_z[i].reserve(slot_bytes));
+        QCSS_CUDA(c->zs_dev[i].reserve(stage_bytes));
+        if (c->zs_host_cap[i] < stage_bytes) {
+            if (c->zs_host[i]) cudaFreeHost(c->zs_host[i]);
+            c->zs_host[i] = nullptr;
+            c->zs_host_cap[i] = 0;
+            QCSS_CUDA(cudaHostAlloc(&c->zs_host[i], stage_bytes, cudaHostAllocDefault));
+            c->zs_host_cap[i] = stage_bytes;
+        }
+        if (c->zs_ev[i] == nullptr) QCSS_CUDA(cudaEventCreateWithFlags(&c->zs_ev[i], cudaEventDisableTiming));
+    }
+    // chunk c may be compacted into staging slot c % kSlots once `allowed` >= c (the copy of chunk c - kSlots is done)
+    std::atomic<int64_t> allowed{kSlots - 1};
+    std::atomic<int> stop{0};
+    std::vector<std::atomic<int>> done((size_t)nchunks);
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    std::vector<size_t> used((size_t)nchunks * T, 0);
+    auto geometry = [&](int64_t ci, int64_t& w0, int64_t& cw, int& bpr) {
+        w0 = ci * chunk_words;
+        cw = (total_words - w0 < chunk_words) ? (total_words - w0) : chunk_words;
+        bpr = (int)((cw + kZsBlockWords - 1) / kZsBlockWords);
+    };
+    auto worker = [&](int t) {
+        for (int64_t ci = 0; ci < nchunks; ++ci) {
+            while (allowed.load(std::memory_order_acquire) < ci) {
+                if (stop.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            if (stop.load(std::memory_order_relaxed)) return;
+            int64_t w0, cw;
+            int bpr;
+            geometry(ci, w0, cw, bpr);
+            const int tasks = rows * bpr;
+            uint8_t* const base = static_cast<uint8_t*>(c->zs_host[ci % kSlots]);
+            used[(size_t)ci * T + t] = zs_compact_range(ex, ez, e_stride, n, w0, cw, bpr, (int)((int64_t)tasks * t / T),
+                                                        (int)((int64_t)tasks * (t + 1) / T), reinterpret_cast<uint64_t*>(base),
+                                                        reinterpret_cast<uint32_t*>(base + bm_bytes),
+                                                        reinterpret_cast<uint64_t*>(base + bm_bytes + off_bytes),
+                                                        (size_t)t * region_cap, region_cap);
+            done[(size_t)ci].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> team;
+    team.reserve((size_t)T);
+    for (int t = 0; t < T; ++t) team.emplace_back(worker, t);
+    int rc = QCSS_OK;
+    cudaError_t err = cudaSuccess;
+    int64_t sent = 0;
+    for (int64_t ci = 0; ci < nchunks && rc == QCSS_OK && err == cudaSuccess; ++ci) {
+        const int slot = (int)(ci % kSlots);
+        cudaStream_t st = c->slot_stream[slot];
+        if (ci >= 1) {                                       // staging of chunk ci - 1 is free once its copies have landed
+            err = cudaEventSynchronize(c->zs_ev[(ci - 1) % kSlots]);
+            allowed.store(ci - 1 + kSlots, std::memory_order_release);
+            if (err != cudaSuccess) break;
+        }
+        while (done[(size_t)ci].load(std::memory_order_acquire) < T) std::this_thread::yield();
+        int64_t w0, cw;
+        int bpr;
+        geometry(ci, w0, cw, bpr);
+        const int64_t cshots = (w0 + cw == total_words) ? (shots - w0 * 64) : cw * 64;
+        const int tasks = rows * bpr;
+        bool fits = true;
+        for (int t = 0; t < T; ++t) fits = fits && used[(size_t)ci * T + t] != SIZE_MAX;
+        uint8_t* const h = static_cast<uint8_t*>(c->zs_host[slot]);
+        uint8_t* const d = static_cast<uint8_t*>(c->zs_dev[slot].p);
+        if (fits) {
+            err = cudaMemcpyAsync(d, h, (size_t)tasks * 32 * 8, cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(d + bm_bytes, h + bm_bytes, (size_t)tasks * 4, cudaMemcpyHostToDevice, st);
+            sent += (int64_t)tasks * (32 * 8 + 4);
+            for (int t = 0; t < T && err == cudaSuccess; ++t) {
+                const size_t words = used[(size_t)ci * T + t];
+                if (words == 0) continue;
+                const size_t at = bm_bytes + off_bytes + (size_t)t * region_cap * 8;
+                err = cudaMemcpyAsync(d + at, h + at, words * 8, cudaMemcpyHostToDevice, st);
+                sent += (int64_t)words * 8;
+            }
+            if (err == cudaSuccess) err = cudaEventRecord(c->zs_ev[slot], st);
+            if (err == cudaSuccess)
+                err = launch_zs_expand(reinterpret_cast<const uint64_t*>(d), reinterpret_cast<const uint32_t*>(d + bm_bytes),
+                                       reinterpret_cast<const uint64_t*>(d + bm_bytes + off_bytes),
+                                       static_cast<uint64_t*>(c->slot_x[slot].p), static_cast<uint64_t*>(c->slot_z[slot].p), n, bpr,
+                                       chunk_words, cw, st);
+        } else {                                             // dense chunk: the plain strided copy
+            err = cudaMemcpy2DAsync(c->slot_x[slot].p, chunk_words * 8, ex + w0, e_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess)
+                err = cudaMemcpy2DAsync(c->slot_z[slot].p, chunk_words * 8, ez + w0, e_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess) err = cudaEventRecord(c->zs_ev[slot], st);
+            sent += 2 * cw * 8 * n;
+        }
+        if (err != cudaSuccess) break;
+        qcss_decode_io io;
+        memset(&io, 0, sizeof(io));
+        io.ex = (const uint64_t*)c->slot_x[slot].p;
+        io.ez = (const uint64_t*)c->slot_z[slot].p;
+        io.e_stride = chunk_words;
+        io.tally = (uint64_t*)c->tally.p;
+        rc = launch_decode(c, &io, cshots, st);
+    }
+    stop.store(1, std::memory_order_relaxed);
+    allowed.store(nchunks + kSlots, std::memory_order_release);
+    for (auto& th : team) th.join();
+    for (int i = 0; i < kSlots; ++i) {
+        const cudaError_t e2 = cudaStreamSynchronize(c->slot_stream[i]);
+        if (err == cudaSuccess) err = e2;
+    }
+    c->last_h2d_bytes = sent;
+    c->last_host_threads = T;
+    if (rc != QCSS_OK) return rc;
+    QCSS_CUDA(err);
+    return QCSS_OK;
+}
+
+// the compacting path pays when the planes are sparse, long enough to amortise a thread team, and cores are there
+int compacting_threads(const qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t shots) {
+    if (options().host_compact == 0) return 0;
+    const int64_t total_words = (shots + 63) / 64;
+    if ((int64_t)c->n * total_words * 16 < ((int64_t)64 << 20)) return 0;          // < 64 MB of planes: one plain copy
+    int threads = options().host_threads;
+    if (threads <= 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        if (threads > 16) threads = 16;
+    }
+    if (threads < 4) return 0;
+    const int64_t probe = total_words < 65536 ? total_words : 65536;
+    if (zs_density(ex, probe) > 0.25 || zs_density(ez, probe) > 0.25) return 0;    // dense planes: nothing to gain
+    return threads;
+}
+
+}  // namespace
+
+extern "C" {
+
 QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int64_t shots,
                    qcss_tally* tally) {
     if (!c || !tally) return fail(QCSS_ERR_INVALID, "code or tally is NULL");
@@ -997,6 +1171,14 @@ QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez
     QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
+    if (const int threads = compacting_threads(c, ex, ez, shots)) {
+        rc = decode_xz_compacted(c, ex, ez, e_stride, shots, threads);
+        if (rc) return rc;
+        uint64_t hz[6];
+        QCSS_CUDA(cudaMemcpy(hz, c->tally.p, sizeof(hz), cudaMemcpyDeviceToHost));
+        tally_from(hz, shots, tally);
+        return QCSS_OK;
+    }
     // chunk = a slice of every plane, sized so one slot holds ~32 MB per Pauli type
     const int64_t total_words = (shots + 63) / 64;
     int64_t chunk_words = ((int64_t)(32u << 20) / ((int64_t)c->n * 8)) & ~(int64_t)1;
@@ -1031,9 +1213,18 @@ QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez
         }
     }
     for (int i = 0; i < kSlots; ++i) QCSS_CUDA(cudaStreamSynchronize(c->slot_stream[i]));
+    c->last_h2d_bytes = 2 * total_words * 8 * (int64_t)c->n;
+    c->last_host_threads = 0;
     uint64_t h[6];
     QCSS_CUDA(cudaMemcpy(h, c->tally.p, sizeof(h), cudaMemcpyDeviceToHost));
     tally_from(h, shots, tally);
+    return QCSS_OK;
+}
+
+QCSS_API int qcss_code_last_transfer(const qcss_code* c, int64_t* h2d_bytes, int* host_threads) {
+    if (!c) return fail(QCSS_ERR_INVALID, "code is NULL");
+    if (h2d_bytes) *h2d_bytes = c->last_h2d_bytes;
+    if (host_threads) *host_threads = c->last_host_threads;
     return QCSS_OK;
 }
 

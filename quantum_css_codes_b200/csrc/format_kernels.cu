@@ -371,4 +371,55 @@ cudaError_t launch_events_from_planes(const uint32_t* d_ex, const uint32_t* d_ez
     return cudaGetLastError();
 }
 
+// ---- compacted host planes -> dense planes (host_compact.h) --------------------------------------------------------
+// One warp per block of 2048 plane words: lane l holds bitmap word l (64 words of the block) and the exclusive prefix of
+// its population count; in round r the warp writes words 32 r .. 32 r + 31 -- one coalesced 256-byte store -- each lane
+// fetching its value, if its bit is set, at rank = prefix of the bitmap word + bits below its own.
+namespace {
+
+__global__ void __launch_bounds__(kFmtThreads)
+k_zs_expand(const unsigned long long* __restrict__ bm, const uint32_t* __restrict__ off,
+            const unsigned long long* __restrict__ vals, unsigned long long* __restrict__ out_x,
+            unsigned long long* __restrict__ out_z, int n, int blocks_per_row, int tasks, int64_t slot_stride, int64_t cw) {
+    const int lane = threadIdx.x & 31;
+    const int task = (int)(((int64_t)blockIdx.x * kFmtThreads + threadIdx.x) >> 5);
+    if (task >= tasks) return;                               // whole warps leave together
+    const int row = task / blocks_per_row, blk = task % blocks_per_row;
+    unsigned long long* const dst = (row < n ? out_x + (int64_t)row * slot_stride : out_z + (int64_t)(row - n) * slot_stride) +
+                                    (int64_t)blk * 2048;
+    const int64_t left = cw - (int64_t)blk * 2048;           // words of this block inside the chunk
+    const unsigned long long mine = bm[(size_t)task * 32 + lane];
+    int incl = __popcll(mine);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int excl = incl - __popcll(mine);
+    const unsigned long long* const v = vals + off[task];
+#pragma unroll 4
+    for (int r = 0; r < 64; ++r) {
+        const unsigned long long word = __shfl_sync(0xFFFFFFFFu, mine, r >> 1);
+        const int before = __shfl_sync(0xFFFFFFFFu, excl, r >> 1);
+        const int bit = ((r & 1) << 5) + lane;
+        unsigned long long value = 0ull;
+        if ((word >> bit) & 1ull) value = v[before + __popcll(word & ((1ull << bit) - 1ull))];
+        if (32 * r + lane < left) dst[32 * r + lane] = value;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_zs_expand(const uint64_t* d_bm, const uint32_t* d_off, const uint64_t* d_vals, uint64_t* d_x, uint64_t* d_z,
+                             int n, int blocks_per_row, int64_t slot_stride, int64_t cw, cudaStream_t stream) {
+    const int tasks = 2 * n * blocks_per_row;
+    if (tasks <= 0) return cudaSuccess;
+    const int64_t threads = (int64_t)tasks * 32;
+    k_zs_expand<<<(unsigned)((threads + kFmtThreads - 1) / kFmtThreads), kFmtThreads, 0, stream>>>(
+        reinterpret_cast<const unsigned long long*>(d_bm), d_off, reinterpret_cast<const unsigned long long*>(d_vals),
+        reinterpret_cast<unsigned long long*>(d_x), reinterpret_cast<unsigned long long*>(d_z), n, blocks_per_row, tasks,
+        slot_stride, cw);
+    return cudaGetLastError();
+}
+
 }  // namespace qcss

@@ -116,6 +116,9 @@ cudaError_t launch_unpack_planes(const uint32_t* d_planes, int64_t stride32, int
 cudaError_t launch_decode_events(const GenericSide& x, const uint32_t* rows_x, uint32_t lmask_x, const GenericSide& z,
                                  const uint32_t* rows_z, uint32_t lmask_z, const unsigned long long* d_events, int64_t count,
                                  int64_t shots, unsigned long long* d_tally, unsigned long long* d_aux, cudaStream_t stream);
+// compacted host planes (host_compact.h) -> the dense planes of one chunk: d_x / d_z rows of slot_stride words, cw valid
+cudaError_t launch_zs_expand(const uint64_t* d_bm, const uint32_t* d_off, const uint64_t* d_vals, uint64_t* d_x, uint64_t* d_z,
+                             int n, int blocks_per_row, int64_t slot_stride, int64_t cw, cudaStream_t stream);
 cudaError_t launch_events_from_planes(const uint32_t* d_ex, const uint32_t* d_ez, int n, int64_t stride32, int64_t words,
                                       uint32_t tail_mask, int64_t first_shot, unsigned long long* d_events, int64_t capacity,
                                       unsigned long long* d_count, unsigned long long* d_work, int ctas, cudaStream_t stream);

@@ -207,3 +207,52 @@ def test_allow_multi_logical_decode_matches_oracle(make):
                  lambda: code.error_correct_monte_carlo(1e-3, 1e-3, 2, 1000)):
         with pytest.raises(_native.NativeLibraryError):
             call()
+
+
+def _sparse_planes(rng, n, words, stride, density_of_chunk):
+    """(n, stride) uint64 planes; ``density_of_chunk(word index array) -> probability`` that a word is non-zero."""
+    out = np.zeros((n, stride), dtype=np.uint64)
+    prob = density_of_chunk(np.arange(words))
+    for j in range(n):
+        hit = rng.random(words) < prob
+        vals = (np.uint64(1) << rng.integers(0, 64, size=words).astype(np.uint64)) | \
+               (rng.integers(0, 1 << 62, size=words).astype(np.uint64) * (rng.random(words) < 0.05).astype(np.uint64))
+        out[j, :words] = np.where(hit, vals, np.uint64(0))
+    return out
+
+
+@pytest.mark.parametrize("name,shots", [("steane", (1 << 27) + 64 * 2048 * 3 + 77), ("golay23", (1 << 25) + 12345)])
+@pytest.mark.parametrize("profile", ["sparse", "dense_later", "dense"])
+def test_decode_xz_host_compaction_equals_plain_copy(name, shots, profile):
+    """qcss_decode_xz on host planes: the compacting path (host threads suppress zero words, k_zs_expand rebuilds the
+    chunk in HBM; csrc/host_compact.h) against the plain chunked copy (option host_compact = 0): identical tallies
+    for sparse planes, for planes whose later chunks are too dense to compact (those go over uncompacted), for dense
+    planes (the probe declines), with a ragged last chunk and a padded stride; and against the oracle on the head."""
+    code = CSSCode(*[np.array(h) for h in getattr(codes, name)()])
+    ref = ocss.build_css(*[np.array(h) for h in getattr(codes, name)()])
+    rng = np.random.default_rng(len(name) + shots % 97)
+    words = (shots + 63) // 64
+    stride = ((shots + 127) // 128) * 2 + 6
+    if profile == "sparse":
+        dens = lambda w: np.full(w.shape, 0.06)
+    elif profile == "dense_later":
+        dens = lambda w: np.where(w < words // 3, 0.03, 0.9)
+    else:
+        dens = lambda w: np.full(w.shape, 0.7)
+    ex = _sparse_planes(rng, code.n, words, stride, dens)
+    ez = _sparse_planes(rng, code.n, words, stride, dens)
+    tail = shots % 64
+    if tail:                                                  # bits past the last shot must not exist (plane contract)
+        ex[:, words - 1] &= np.uint64((1 << tail) - 1)
+        ez[:, words - 1] &= np.uint64((1 << tail) - 1)
+    dev = code.device
+    with _native.option("host_compact", 0):
+        want = dev.decode_xz_planes(ex, ez, shots)
+    got = dev.decode_xz_planes(ex, ez, shots)
+    assert got == want and want["shots"] == shots
+    with _native.option("host_threads", 5):                   # an odd team size: uneven task ranges
+        assert dev.decode_xz_planes(ex, ez, shots) == want
+    head = 64 * 1000
+    bits = lambda p: np.unpackbits(np.ascontiguousarray(p[:, :1000]).view(np.uint8), axis=1, bitorder="little").T
+    assert dev.decode_xz_planes(np.ascontiguousarray(ex[:, :1000]), np.ascontiguousarray(ez[:, :1000]), head) == \
+        omc.tally_xz(ref, bits(ex), bits(ez))

@@ -848,22 +848,29 @@ def measure_e2e(ctx, dev, ex, ez, n, stride, shots, args, first_shot):
         sent, team = dev.last_transfer()
         ctx.launches += (args.e2e_steps + 1) * 2 * max(1, -(-nbytes // (32 << 20)))
         ok = [tally[k] for k in _native.TALLY_FIELDS[1:]] == resident
-        out = {"value": world * shots / sec, "unit": "shots/s", "shots_per_gpu_per_step": shots,
-               "h2d_bytes_per_step": int(sent), "d2h_bytes_per_step": 48, "host_plane_bytes_per_step": int(2 * nbytes),
-               "host_compaction_threads": team,
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * sec,
-               "api": "qcss_decode_xz (pinned host bit planes; zero words suppressed by host threads, chunked H2D, "
-                      "expanded and decoded on the device)" if team else
-                      "qcss_decode_xz (pinned host bit planes, chunked H2D overlapped with kernels)",
-               "host_read_gbs_per_gpu": 2 * nbytes / sec / 1e9,
-               "matches_resident_tally": bool(ok)}
-        if team:                                                  # the same call with plain copies, for comparison
+
+        def describe(sec_, sent_, team_, ok_):
+            return {"value": world * shots / sec_, "unit": "shots/s", "shots_per_gpu_per_step": shots,
+                    "h2d_bytes_per_step": int(sent_), "d2h_bytes_per_step": 48, "host_plane_bytes_per_step": int(2 * nbytes),
+                    "host_compaction_threads": team_, "steps": args.e2e_steps, "ms_per_step": 1e3 * sec_,
+                    "api": "qcss_decode_xz (pinned host bit planes; zero words suppressed by host threads, chunked H2D, "
+                           "expanded and decoded on the device)" if team_ else
+                           "qcss_decode_xz (pinned host bit planes, chunked H2D overlapped with kernels; option host_compact = 0)",
+                    "host_read_gbs_per_gpu": 2 * nbytes / sec_ / 1e9, "matches_resident_tally": bool(ok_)}
+        out = describe(sec, sent, team, ok)
+        if team:
+            # the same call with plain copies: which of the two wins depends on cores per GPU against the link rate (16
+            # cores against 55 GB/s at N = 1: the team; 4 cores against 23 GB/s on the 8-GPU box: the copies).  Both are one
+            # public option apart; the headline is the faster one, the other is recorded beside it.
             with _native.option("host_compact", 0):
                 sec_p, tally_p = wall(lambda: dev.decode_xz_host_ptr(hx_ptr, hz_ptr, stride_e2e, shots), args.e2e_steps)
-            out["plain_copy"] = {"value": world * shots / sec_p, "ms_per_step": 1e3 * sec_p, "h2d_bytes_per_step": int(2 * nbytes),
-                                 "h2d_achieved_gbs_per_gpu": 2 * nbytes / sec_p / 1e9,
-                                 "matches_resident_tally": [tally_p[k] for k in _native.TALLY_FIELDS[1:]] == resident}
-            sec = sec_p                                           # the link figures below describe the plain copy
+            plain = describe(sec_p, 2 * nbytes, 0, [tally_p[k] for k in _native.TALLY_FIELDS[1:]] == resident)
+            if sec_p < sec:
+                out, plain = plain, out
+                out["other_path"] = plain
+            else:
+                out["other_path"] = plain
+            sec = sec_p                                           # the link figures below describe the plain copies
         # raw host->device ceiling of this box at this N: the same bytes with no kernels at all
         slot = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
         src = torch.from_numpy(hx.view(np.uint8))[: 64 << 20]

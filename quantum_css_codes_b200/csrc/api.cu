@@ -1144,10 +1144,13 @@ int compacting_threads(const qcss_code* c, const uint64_t* ex, const uint64_t* e
     if (options().host_compact == 0) return 0;
     const int64_t total_words = (shots + 63) / 64;
     if ((int64_t)c->n * total_words * 16 < ((int64_t)64 << 20)) return 0;          // < 64 MB of planes: one plain copy
+    // a core streams 7-13 GB/s (profiles/r02_host_scan_bw.jsonl): left to itself the path needs eight of them to beat the
+    // link (measured on an 8-GPU box with 4 cores per rank: 18 GB/s per GPU against 23 GB/s of plain copies)
     int threads = options().host_threads;
     if (threads <= 0) {
         threads = (int)std::thread::hardware_concurrency();
         if (threads > 16) threads = 16;
+        if (threads < 8) return 0;
     }
     if (threads < 4) return 0;
     const int64_t probe = total_words < 65536 ? total_words : 65536;

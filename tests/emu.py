@@ -50,7 +50,8 @@ class EcParams(ctypes.Structure):
 def _needs_build():
     if not os.path.exists(LIB):
         return True
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("core.cuh", "decode.cuh", "ec_rounds.cuh", "named_codes.inc")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("core.cuh", "decode.cuh", "ec_rounds.cuh", "named_codes.inc",
+                                                     "host_compact.h", "host_compact.cpp")]
     return os.path.getmtime(LIB) < max(os.path.getmtime(p) for p in deps)
 
 
@@ -63,7 +64,8 @@ def lib():
         if _needs_build():
             nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
             cmd = [nvcc, "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
-                   "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, SRC]
+                   "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, SRC,
+                   os.path.join(CSRC, "host_compact.cpp")]
             subprocess.run(cmd, check=True, capture_output=True)
         _lib = ctypes.CDLL(LIB)
         assert _lib.emu_sizeof_side() == ctypes.sizeof(GenericSide)
@@ -228,3 +230,24 @@ def mc_gapq(side_x, side_z, p, shots, seed=0, first_shot=0, named_id=-1):
     assert rc == 0
     return dict(shots=shots, fail_x=int(tally[1]), fail_z=int(tally[2]), fail_any=int(tally[3]),
                 miss_x=int(tally[4]), miss_z=int(tally[5]))
+
+
+def zs_roundtrip(ex, ez, w0, cw, threads):
+    """Host side of the compacting qcss_decode_xz path (csrc/host_compact.cpp: the product's own code) followed by a
+    host restatement of k_zs_expand's index arithmetic: returns the rebuilt (n, cw) chunks of both plane sets, or None
+    when a worker's share of non-zero words exceeds its region (the product then sends the chunk uncompacted)."""
+    ex = np.ascontiguousarray(ex, dtype=np.uint64)
+    ez = np.ascontiguousarray(ez, dtype=np.uint64)
+    n, stride = ex.shape
+    assert ez.shape == ex.shape and w0 + cw <= stride
+    out_x = np.full((n, cw), 0xDEADBEEF, dtype=np.uint64)
+    out_z = np.full((n, cw), 0xDEADBEEF, dtype=np.uint64)
+    fn = lib().emu_zs_roundtrip
+    fn.restype = ctypes.c_int
+    rc = fn(ctypes.c_void_p(ex.ctypes.data), ctypes.c_void_p(ez.ctypes.data), ctypes.c_int64(stride), n,
+            ctypes.c_int64(w0), ctypes.c_int64(cw), threads, ctypes.c_void_p(out_x.ctypes.data),
+            ctypes.c_void_p(out_z.ctypes.data))
+    if rc == 1:
+        return None
+    assert rc == 0
+    return out_x, out_z

@@ -6,8 +6,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../quantum_css_codes_b200/csrc/decode.cuh"
 #include "../../quantum_css_codes_b200/csrc/ec_rounds.cuh"
+#include "../../quantum_css_codes_b200/csrc/host_compact.h"
 #include "../../quantum_css_codes_b200/csrc/named_codes.inc"
 
 using namespace qcss;
@@ -311,6 +314,43 @@ int emu_named_side(int id, int which_x, int* n, int* m, uint32_t* rows, uint32_t
     const named::SideInfo& s = which_x ? named::kNamed[id].x : named::kNamed[id].z;
     *n = s.n; *m = s.m; *l = s.l;
     for (int t = 0; t < 16; ++t) rows[t] = s.rows[t];
+    return 0;
+}
+
+// The compacting host->device path of qcss_decode_xz: csrc/host_compact.cpp (the product's code, linked into this
+// library) compacts one chunk the way api.cu::decode_xz_compacted lays it out -- `threads` workers with contiguous task
+// ranges and their own value regions -- and the loop below rebuilds the chunk with the index arithmetic of
+// format_kernels.cu::k_zs_expand (lane l: bitmap word l and the exclusive prefix of the population counts; round r:
+// words 32 r .. 32 r + 31, value rank = prefix + bits below).  0 = ok, 1 = a region overflowed.
+__attribute__((visibility("default")))
+int emu_zs_roundtrip(const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int n, int64_t w0, int64_t cw, int threads,
+                     uint64_t* out_x, uint64_t* out_z) {
+    const int rows = 2 * n, bpr = (int)((cw + kZsBlockWords - 1) / kZsBlockWords), tasks = rows * bpr;
+    const size_t region_cap = ((size_t)rows * cw / 2) / threads + kZsBlockWords + 8;
+    std::vector<uint64_t> bm((size_t)tasks * 32, ~0ull), vals((size_t)threads * region_cap, 0x5555555555555555ull);
+    std::vector<uint32_t> off((size_t)tasks, 0xFFFFFFFFu);
+    for (int t = 0; t < threads; ++t) {
+        const size_t used = zs_compact_range(ex, ez, e_stride, n, w0, cw, bpr, (int)((int64_t)tasks * t / threads),
+                                             (int)((int64_t)tasks * (t + 1) / threads), bm.data(), off.data(), vals.data(),
+                                             (size_t)t * region_cap, region_cap);
+        if (used == SIZE_MAX) return 1;
+    }
+    for (int task = 0; task < tasks; ++task) {
+        const int row = task / bpr, blk = task % bpr;
+        uint64_t* dst = (row < n ? out_x + (int64_t)row * cw : out_z + (int64_t)(row - n) * cw) + (int64_t)blk * kZsBlockWords;
+        const int64_t left = cw - (int64_t)blk * kZsBlockWords;
+        int excl[32], acc = 0;
+        for (int l = 0; l < 32; ++l) { excl[l] = acc; acc += __builtin_popcountll(bm[(size_t)task * 32 + l]); }
+        const uint64_t* v = vals.data() + off[task];
+        for (int r = 0; r < 64; ++r)
+            for (int lane = 0; lane < 32; ++lane) {
+                const uint64_t word = bm[(size_t)task * 32 + (r >> 1)];
+                const int bit = ((r & 1) << 5) + lane;
+                uint64_t value = 0;
+                if ((word >> bit) & 1ull) value = v[excl[r >> 1] + __builtin_popcountll(word & ((1ull << bit) - 1ull))];
+                if (32 * r + lane < left) dst[32 * r + lane] = value;
+            }
+    }
     return 0;
 }
 

@@ -239,3 +239,22 @@ def test_two_phase_gap_sampler_replay(name, static, p):
     got = emu.mc_gapq(sx, sz, p, shots, seed, first, NAMED[name] if static else -1)
     ox, oz = ophilox.sample_bits(seed, first, shots, code.n, p)
     assert got == omc.tally_xz(code, ox, oz)
+
+
+@pytest.mark.parametrize("n,cw,w0,threads,density", [(7, 5000, 3, 4, 0.06), (1, 1, 0, 1, 1.0), (3, 2048, 0, 16, 0.0),
+                                                     (5, 2049, 7, 5, 0.3), (23, 4096 + 63, 1, 7, 0.02), (2, 64, 5, 3, 0.5)])
+def test_host_plane_compaction_round_trip(n, cw, w0, threads, density):
+    """csrc/host_compact.cpp (zero-word suppression of host planes before the copy, the product's own code) followed by
+    k_zs_expand's index arithmetic restated on the host gives back the chunk, word for word: ragged block ends, empty
+    and full blocks, uneven worker ranges, an offset into a padded stride."""
+    rng = np.random.default_rng(n * 100 + cw)
+    stride = w0 + cw + 9
+    def planes_():
+        p = rng.integers(1, 1 << 63, size=(n, stride), dtype=np.uint64)
+        return np.where(rng.random((n, stride)) < density, p, np.uint64(0))
+    ex, ez = planes_(), planes_()
+    got = emu.zs_roundtrip(ex, ez, w0, cw, threads)
+    if got is None:                                           # more than half the words are non-zero somewhere
+        assert density >= 0.3
+        return
+    assert np.array_equal(got[0], ex[:, w0:w0 + cw]) and np.array_equal(got[1], ez[:, w0:w0 + cw])

@@ -948,16 +948,25 @@ def measure_e2e_formats(ctx, dev, ex, ez, n, stride, shots, args, resident, wall
         torch.from_numpy(hz.view(np.uint8))[:nb].copy_(rows_z.view(-1))
         torch.cuda.synchronize()
         del rows_x, rows_z
-        sec, tally = wall(lambda: dev.decode_xz_shots_host_ptr(hx_ptr, hz_ptr, 1, sm_shots), args.e2e_steps)
-        ctx.launches += (args.e2e_steps + 1) * 3 * max(1, -(-nb // (32 << 20)))
-        ok = [tally[f] for f in _native.TALLY_FIELDS[1:]] == want
-        out["e2e_shot_major"] = {"value": world * sm_shots / sec, "unit": "shots/s", "shots_per_gpu_per_step": sm_shots,
-                                 "h2d_bytes_per_step": 2 * nb, "d2h_bytes_per_step": 48, "bytes_per_shot": 2.0 * n,
-                                 "steps": args.e2e_steps, "ms_per_step": 1e3 * sec,
-                                 "h2d_achieved_gbs_per_gpu": 2 * nb / sec / 1e9,
-                                 "api": "qcss_decode_xz_shots (the reference's (shots, n) uint8 arrays, pinned; transposed "
-                                        "to bit planes on the device)",
-                                 "matches_resident_tally": bool(ok)}
+        def shot_major():
+            sec, tally = wall(lambda: dev.decode_xz_shots_host_ptr(hx_ptr, hz_ptr, 1, sm_shots), args.e2e_steps)
+            sent, team = dev.last_transfer()
+            ctx.launches += (args.e2e_steps + 1) * 4 * max(1, -(-nb // (32 << 20)))
+            return {"value": world * sm_shots / sec, "unit": "shots/s", "shots_per_gpu_per_step": sm_shots,
+                    "h2d_bytes_per_step": int(sent), "d2h_bytes_per_step": 48, "bytes_per_shot": 2.0 * n,
+                    "host_compaction_threads": team, "steps": args.e2e_steps, "ms_per_step": 1e3 * sec,
+                    "host_read_gbs_per_gpu": 2 * nb / sec / 1e9,
+                    "api": "qcss_decode_xz_shots (the reference's (shots, n) uint8 arrays, pinned; " +
+                           ("zero words suppressed by host threads, " if team else "") + "transposed to bit planes on the device)",
+                    "matches_resident_tally": [tally[f] for f in _native.TALLY_FIELDS[1:]] == want}
+        best = shot_major()
+        if best["host_compaction_threads"]:                       # both forms of the call, the faster one reported (see e2e)
+            with _native.option("host_compact", 0):
+                plain = shot_major()
+            if plain["value"] > best["value"]:
+                best, plain = plain, best
+            best["other_path"] = plain
+        out["e2e_shot_major"] = best
     except Exception as exc:
         out["e2e_shot_major"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out

@@ -1006,16 +1006,19 @@ QCSS_API int qcss_decode(qcss_code* c, int which, const uint64_t* e_planes, int6
 
 namespace {
 
-// qcss_decode_xz on SPARSE host planes: host threads compact each chunk (bitmap of non-zero words + the words,
-// host_compact.h) into pinned staging while the previous chunks are copied, expanded (k_zs_expand) and decoded on the
-// slot streams.  The link carries ~8 % of the bytes at p = 1e-3; the call is then bound by how fast the host cores read
-// the planes (100 GB/s with 16 threads on this pool's boxes against 55 GB/s of PCIe).  A chunk whose non-zero words do
-// not fit half its size goes over uncompacted.  The result is the plain path's, bit for bit (same kernel, same planes).
-int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int64_t shots, int threads) {
-    const int n = c->n, rows = 2 * n, T = threads;
-    const int64_t total_words = (shots + 63) / 64;
-    int64_t chunk_words = ((int64_t)(32u << 20) / ((int64_t)n * 8)) / kZsBlockWords * kZsBlockWords;
-    if (chunk_words < kZsBlockWords) chunk_words = kZsBlockWords;
+// The compacting host->device pipeline (host_compact.h).  Two sets of `n_rows` rows of `total_words` 64-bit words each
+// (bit planes: n rows, `src_stride` words apart; the reference's (shots, n) arrays: one contiguous row per Pauli type) are
+// cut into chunks of `chunk_words` words per row (a multiple of kZsBlockWords); host threads compact chunk after chunk
+// (bitmap of non-zero words + the words) into a ring of pinned staging buffers while the main thread copies the finished
+// ones, k_zs_expand rebuilds them in dst_x / dst_z (rows `dst_stride` words apart) and `after(chunk, slot, w0, cw,
+// stream)` launches whatever consumes a chunk.  A chunk whose non-zero words do not fit half its size goes over with
+// plain copies.  At p = 1e-3 the link carries ~8 % of the plane bytes (1 % of the uint8 rows); the call is then bound by
+// how fast the host cores read memory (113 GB/s with 16 threads on this pool's boxes against 55 GB/s of PCIe).
+template <class After>
+int zs_pipeline(qcss_code* c, const uint64_t* src_x, const uint64_t* src_z, int64_t src_stride, int n_rows, int64_t total_words,
+                int64_t chunk_words, DevBuf (&dst_x)[kSlots], DevBuf (&dst_z)[kSlots], int64_t dst_stride, int threads,
+                After after) {
+    const int n = n_rows, rows = 2 * n, T = threads;
     const int64_t nchunks = (total_words + chunk_words - 1) / chunk_words;
     const int bpr_max = (int)(chunk_words / kZsBlockWords);
     const size_t tasks_max = (size_t)rows * bpr_max;
@@ -1023,10 +1026,7 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
     const size_t region_cap = ((size_t)rows * chunk_words / 2) / T + kZsBlockWords + 8;       // words per worker
     const size_t stage_bytes = bm_bytes + off_bytes + (size_t)T * region_cap * 8;
     if ((size_t)T * region_cap >= ((size_t)1 << 32)) return fail(QCSS_ERR_INVALID, "chunk too large for 32-bit value offsets");
-    const size_t slot_bytes = (size_t)n * chunk_words * 8;
     for (int i = 0; i < kSlots; ++i) {
-        QCSS_CUDA(c->slot_x[i].reserve(slot_bytes));
-        QCSS_CUDA(c->slot_z[i].reserve(slot_bytes));
         QCSS_CUDA(c->zs_dev[i].reserve(stage_bytes));
         if (c->zs_host_cap[i] < stage_bytes) {
             if (c->zs_host[i]) cudaFreeHost(c->zs_host[i]);
@@ -1037,7 +1037,7 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
         }
         if (c->zs_ev[i] == nullptr) QCSS_CUDA(cudaEventCreateWithFlags(&c->zs_ev[i], cudaEventDisableTiming));
     }
-    // chunk c may be compacted into staging slot c % kSlots once `allowed` >= c (the copy of chunk c - kSlots is done)
+    // chunk ci may be compacted into staging slot ci % kSlots once `allowed` >= ci (the copy of chunk ci - kSlots is done)
     std::atomic<int64_t> allowed{kSlots - 1};
     std::atomic<int> stop{0};
     std::vector<std::atomic<int>> done((size_t)nchunks);
@@ -1060,7 +1060,7 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
             geometry(ci, w0, cw, bpr);
             const int tasks = rows * bpr;
             uint8_t* const base = static_cast<uint8_t*>(c->zs_host[ci % kSlots]);
-            used[(size_t)ci * T + t] = zs_compact_range(ex, ez, e_stride, n, w0, cw, bpr, (int)((int64_t)tasks * t / T),
+            used[(size_t)ci * T + t] = zs_compact_range(src_x, src_z, src_stride, n, w0, cw, bpr, (int)((int64_t)tasks * t / T),
                                                         (int)((int64_t)tasks * (t + 1) / T), reinterpret_cast<uint64_t*>(base),
                                                         reinterpret_cast<uint32_t*>(base + bm_bytes),
                                                         reinterpret_cast<uint64_t*>(base + bm_bytes + off_bytes),
@@ -1086,7 +1086,6 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
         int64_t w0, cw;
         int bpr;
         geometry(ci, w0, cw, bpr);
-        const int64_t cshots = (w0 + cw == total_words) ? (shots - w0 * 64) : cw * 64;
         const int tasks = rows * bpr;
         bool fits = true;
         for (int t = 0; t < T; ++t) fits = fits && used[(size_t)ci * T + t] != SIZE_MAX;
@@ -1107,23 +1106,17 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
             if (err == cudaSuccess)
                 err = launch_zs_expand(reinterpret_cast<const uint64_t*>(d), reinterpret_cast<const uint32_t*>(d + bm_bytes),
                                        reinterpret_cast<const uint64_t*>(d + bm_bytes + off_bytes),
-                                       static_cast<uint64_t*>(c->slot_x[slot].p), static_cast<uint64_t*>(c->slot_z[slot].p), n, bpr,
-                                       chunk_words, cw, st);
+                                       static_cast<uint64_t*>(dst_x[slot].p), static_cast<uint64_t*>(dst_z[slot].p), n, bpr,
+                                       dst_stride, cw, st);
         } else {                                             // dense chunk: the plain strided copy
-            err = cudaMemcpy2DAsync(c->slot_x[slot].p, chunk_words * 8, ex + w0, e_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
+            err = cudaMemcpy2DAsync(dst_x[slot].p, dst_stride * 8, src_x + w0, src_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
             if (err == cudaSuccess)
-                err = cudaMemcpy2DAsync(c->slot_z[slot].p, chunk_words * 8, ez + w0, e_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
+                err = cudaMemcpy2DAsync(dst_z[slot].p, dst_stride * 8, src_z + w0, src_stride * 8, cw * 8, n, cudaMemcpyHostToDevice, st);
             if (err == cudaSuccess) err = cudaEventRecord(c->zs_ev[slot], st);
             sent += 2 * cw * 8 * n;
         }
         if (err != cudaSuccess) break;
-        qcss_decode_io io;
-        memset(&io, 0, sizeof(io));
-        io.ex = (const uint64_t*)c->slot_x[slot].p;
-        io.ez = (const uint64_t*)c->slot_z[slot].p;
-        io.e_stride = chunk_words;
-        io.tally = (uint64_t*)c->tally.p;
-        rc = launch_decode(c, &io, cshots, st);
+        rc = after(ci, slot, w0, cw, st);
     }
     stop.store(1, std::memory_order_relaxed);
     allowed.store(nchunks + kSlots, std::memory_order_release);
@@ -1139,11 +1132,36 @@ int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, in
     return QCSS_OK;
 }
 
-// the compacting path pays when the planes are sparse, long enough to amortise a thread team, and cores are there
-int compacting_threads(const qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t shots) {
-    if (options().host_compact == 0) return 0;
+// qcss_decode_xz on sparse host planes through the pipeline above; the result is the plain path's, bit for bit (same
+// kernel, same planes).
+int decode_xz_compacted(qcss_code* c, const uint64_t* ex, const uint64_t* ez, int64_t e_stride, int64_t shots, int threads) {
+    const int n = c->n;
     const int64_t total_words = (shots + 63) / 64;
-    if ((int64_t)c->n * total_words * 16 < ((int64_t)64 << 20)) return 0;          // < 64 MB of planes: one plain copy
+    int64_t chunk_words = ((int64_t)(32u << 20) / ((int64_t)n * 8)) / kZsBlockWords * kZsBlockWords;
+    if (chunk_words < kZsBlockWords) chunk_words = kZsBlockWords;
+    const size_t slot_bytes = (size_t)n * chunk_words * 8;
+    for (int i = 0; i < kSlots; ++i) {
+        QCSS_CUDA(c->slot_x[i].reserve(slot_bytes));
+        QCSS_CUDA(c->slot_z[i].reserve(slot_bytes));
+    }
+    return zs_pipeline(c, ex, ez, e_stride, n, total_words, chunk_words, c->slot_x, c->slot_z, chunk_words, threads,
+                       [&](int64_t, int slot, int64_t w0, int64_t cw, cudaStream_t st) {
+                           const int64_t cshots = (w0 + cw == total_words) ? (shots - w0 * 64) : cw * 64;
+                           qcss_decode_io io;
+                           memset(&io, 0, sizeof(io));
+                           io.ex = (const uint64_t*)c->slot_x[slot].p;
+                           io.ez = (const uint64_t*)c->slot_z[slot].p;
+                           io.e_stride = chunk_words;
+                           io.tally = (uint64_t*)c->tally.p;
+                           return launch_decode(c, &io, cshots, st);
+                       });
+}
+
+// the compacting path pays when the data is sparse, long enough to amortise a thread team, and cores are there
+int compacting_threads(const uint64_t* x, const uint64_t* z, int64_t words_per_set) {
+    if (options().host_compact == 0) return 0;
+    if (words_per_set * 16 < ((int64_t)64 << 20)) return 0;                        // < 64 MB in all: one plain copy
+    if ((((uintptr_t)x) | ((uintptr_t)z)) & 7u) return 0;                          // word loads want 8-byte alignment
     // a core streams 7-13 GB/s (profiles/r02_host_scan_bw.jsonl): left to itself the path needs eight of them to beat the
     // link (measured on an 8-GPU box with 4 cores per rank: 18 GB/s per GPU against 23 GB/s of plain copies)
     int threads = options().host_threads;
@@ -1153,8 +1171,8 @@ int compacting_threads(const qcss_code* c, const uint64_t* ex, const uint64_t* e
         if (threads < 8) return 0;
     }
     if (threads < 4) return 0;
-    const int64_t probe = total_words < 65536 ? total_words : 65536;
-    if (zs_density(ex, probe) > 0.25 || zs_density(ez, probe) > 0.25) return 0;    // dense planes: nothing to gain
+    const int64_t probe = words_per_set < 65536 ? words_per_set : 65536;
+    if (zs_density(x, probe) > 0.25 || zs_density(z, probe) > 0.25) return 0;      // dense data: nothing to gain
     return threads;
 }
 
@@ -1174,7 +1192,7 @@ QCSS_API int qcss_decode_xz(qcss_code* c, const uint64_t* ex, const uint64_t* ez
     QCSS_CUDA(c->tally.reserve(6 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 6 * sizeof(uint64_t), c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
-    if (const int threads = compacting_threads(c, ex, ez, shots)) {
+    if (const int threads = compacting_threads(ex, ez, (int64_t)c->n * ((shots + 63) / 64))) {
         rc = decode_xz_compacted(c, ex, ez, e_stride, shots, threads);
         if (rc) return rc;
         uint64_t hz[6];
@@ -1733,23 +1751,24 @@ QCSS_API int qcss_decode_xz_shots(qcss_code* c, const void* ex, const void* ez, 
     QCSS_CUDA(c->tally.reserve(8 * sizeof(uint64_t)));
     QCSS_CUDA(cudaMemsetAsync(c->tally.p, 0, 8 * sizeof(uint64_t), c->stream));
     QCSS_CUDA(cudaStreamSynchronize(c->stream));
-    const int64_t cs = chunk_shots_for(c->n, elem_bytes, shots);
-    const int64_t cwords = cs / 64;                                   // uint64 words per plane per chunk (even)
+    int64_t cs = chunk_shots_for(c->n, elem_bytes, shots);
     const size_t row_bytes = (size_t)c->n * elem_bytes;
+    // 0/1 rows of a low-rate batch are almost all zero words (uint8, n = 7, p = 1e-3: 99 %): whole groups of 16384 shots
+    // (a whole number of 2048-word blocks for any row size) go through the compacting pipeline, the rest as plain copies
+    constexpr int64_t kGroup = 16384;
+    const int64_t main_shots = shots / kGroup * kGroup;
+    int threads = 0;
+    if (main_shots > 0 && cs >= kGroup)
+        threads = compacting_threads((const uint64_t*)ex, (const uint64_t*)ez, (int64_t)((size_t)main_shots * row_bytes / 8));
+    if (threads) cs = cs / kGroup * kGroup;
+    const int64_t cwords = cs / 64;                                   // uint64 words per plane per chunk (even)
     for (int i = 0; i < kSlots && shots > 0; ++i) {
         QCSS_CUDA(c->slot_rx[i].reserve((size_t)cs * row_bytes));
         QCSS_CUDA(c->slot_rz[i].reserve((size_t)cs * row_bytes));
         QCSS_CUDA(c->slot_x[i].reserve((size_t)c->n * cwords * 8));
         QCSS_CUDA(c->slot_z[i].reserve((size_t)c->n * cwords * 8));
     }
-    int slot = 0;
-    for (int64_t s0 = 0; s0 < shots; s0 += cs, slot = (slot + 1) % kSlots) {
-        const int64_t part = shots - s0 < cs ? shots - s0 : cs;
-        cudaStream_t st = c->slot_stream[slot];
-        QCSS_CUDA(cudaMemcpyAsync(c->slot_rx[slot].p, (const uint8_t*)ex + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
-                                  cudaMemcpyHostToDevice, st));
-        QCSS_CUDA(cudaMemcpyAsync(c->slot_rz[slot].p, (const uint8_t*)ez + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
-                                  cudaMemcpyHostToDevice, st));
+    auto consume = [&](int slot, int64_t part, cudaStream_t st) -> int {       // raw rows of a slot -> planes -> tallies
         QCSS_CUDA(launch_pack_shots(c->slot_rx[slot].p, elem_bytes, c->n, part, (uint32_t*)c->slot_x[slot].p, cwords * 2, st));
         QCSS_CUDA(launch_pack_shots(c->slot_rz[slot].p, elem_bytes, c->n, part, (uint32_t*)c->slot_z[slot].p, cwords * 2, st));
         qcss_decode_io io;
@@ -1758,7 +1777,31 @@ QCSS_API int qcss_decode_xz_shots(qcss_code* c, const void* ex, const void* ez, 
         io.ez = (const uint64_t*)c->slot_z[slot].p;
         io.e_stride = cwords;
         io.tally = (uint64_t*)c->tally.p;
-        rc = launch_decode(c, &io, part, st);
+        return launch_decode(c, &io, part, st);
+    };
+    int64_t first_plain = 0;
+    c->last_h2d_bytes = 0;
+    c->last_host_threads = 0;
+    if (threads) {
+        const int64_t chunk_words = (int64_t)((size_t)cs * row_bytes / 8), total_words = (int64_t)((size_t)main_shots * row_bytes / 8);
+        rc = zs_pipeline(c, (const uint64_t*)ex, (const uint64_t*)ez, total_words, 1, total_words, chunk_words, c->slot_rx, c->slot_rz,
+                         chunk_words, threads, [&](int64_t ci, int slot, int64_t, int64_t, cudaStream_t st) {
+                             const int64_t s0 = ci * cs;
+                             return consume(slot, main_shots - s0 < cs ? main_shots - s0 : cs, st);
+                         });
+        if (rc) return rc;
+        first_plain = main_shots;
+    }
+    int slot = 0;
+    for (int64_t s0 = first_plain; s0 < shots; s0 += cs, slot = (slot + 1) % kSlots) {
+        const int64_t part = shots - s0 < cs ? shots - s0 : cs;
+        cudaStream_t st = c->slot_stream[slot];
+        QCSS_CUDA(cudaMemcpyAsync(c->slot_rx[slot].p, (const uint8_t*)ex + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        QCSS_CUDA(cudaMemcpyAsync(c->slot_rz[slot].p, (const uint8_t*)ez + (size_t)s0 * row_bytes, (size_t)part * row_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        c->last_h2d_bytes += 2 * part * (int64_t)row_bytes;
+        rc = consume(slot, part, st);
         if (rc) {
             for (int i = 0; i < kSlots; ++i) cudaStreamSynchronize(c->slot_stream[i]);
             return rc;

@@ -256,3 +256,28 @@ def test_decode_xz_host_compaction_equals_plain_copy(name, shots, profile):
     bits = lambda p: np.unpackbits(np.ascontiguousarray(p[:, :1000]).view(np.uint8), axis=1, bitorder="little").T
     assert dev.decode_xz_planes(np.ascontiguousarray(ex[:, :1000]), np.ascontiguousarray(ez[:, :1000]), head) == \
         omc.tally_xz(ref, bits(ex), bits(ez))
+
+
+@pytest.mark.parametrize("dtype,shots", [(np.uint8, 6_000_000 + 333), (np.int64, 900_000 + 77)])
+def test_decode_xz_shots_host_compaction_equals_plain_copy(dtype, shots):
+    """The reference's (shots, n) arrays through qcss_decode_xz_shots: whole 16384-shot groups go through the compacting
+    pipeline, the ragged rest as plain copies; identical tallies with the option off, with an odd team, and the
+    oracle's on the head."""
+    code = CSSCode(*[np.array(h) for h in codes.steane()])
+    ref = ocss.build_css(*[np.array(h) for h in codes.steane()])
+    rng = np.random.default_rng(5)
+    ex = (rng.random((shots, code.n)) < 2e-3).astype(dtype)
+    ez = (rng.random((shots, code.n)) < 2e-3).astype(dtype)
+    if dtype is np.int64:
+        ex[::1000] *= 3                                      # only bit 0 counts (np.mod(x, 2))
+    with _native.option("host_compact", 0):
+        want = code.decode_xz(ex, ez)
+        assert code.device.last_transfer()[1] == 0
+    got = code.decode_xz(ex, ez)
+    sent, team = code.device.last_transfer()
+    assert got == want
+    if team:                                                 # boxes with fewer than eight hardware threads keep the plain copies
+        assert sent < ex.nbytes // 4
+    with _native.option("host_threads", 5):
+        assert code.decode_xz(ex, ez) == want and code.device.last_transfer()[1] == 5
+    assert code.decode_xz(ex[:50_000], ez[:50_000]) == omc.tally_xz(ref, ex[:50_000] & 1, ez[:50_000] & 1)

@@ -1070,7 +1070,14 @@ int zs_pipeline(qcss_code* c, const uint64_t* src_x, const uint64_t* src_z, int6
     };
     std::vector<std::thread> team;
     team.reserve((size_t)T);
-    for (int t = 0; t < T; ++t) team.emplace_back(worker, t);
+    try {
+        for (int t = 0; t < T; ++t) team.emplace_back(worker, t);
+    } catch (...) {                                          // no more threads to be had: nothing has been enqueued yet
+        stop.store(1, std::memory_order_relaxed);
+        allowed.store(nchunks + kSlots, std::memory_order_release);
+        for (auto& th : team) th.join();
+        return fail(QCSS_ERR_NOMEM, "could not start %d host threads for the compacting copy (option host_compact = 0 disables it)", T);
+    }
     int rc = QCSS_OK;
     cudaError_t err = cudaSuccess;
     int64_t sent = 0;

@@ -108,16 +108,14 @@ def depolarising(rng, shots, n, p):
     return ((kind == 1) | (kind == 2)).astype(np.uint8), ((kind == 3) | (kind == 2)).astype(np.uint8)
 
 
-@pytest.mark.parametrize("name", ["steane", "shor9"])
-@pytest.mark.parametrize("p", [0.02, 0.15])
-def test_round_model_equals_the_reference_gadget(name, p):
+def _compare(name, p, round_update, shots=3000):
+    """Runs two rounds through the recorded gadget and through ``round_update``; returns True when they agree."""
     with open(GOLDEN) as fh:
         gold = json.load(fh)[name]
     n, program = gold["n"], gold["program"]
     code = ocss.build_css(*[np.array(h) for h in getattr(codes, name)()])
     assert code.n == n
     rng = np.random.default_rng(7 + n)
-    shots = 3000
     fr = Frame(n, gold["scratch"], shots)
     # model state: physical error e and frame f, both starting from something non-trivial
     e_x, e_z = depolarising(rng, shots, n, p)
@@ -136,11 +134,51 @@ def test_round_model_equals_the_reference_gadget(name, p):
                  random_codewords(rng, code.parity_check_c1, shots)]       # X-basis measurement: a word of C_1
         run_gadget(program, fr, [a, b], words)
         # model side
-        oec.round_update(code, e_x, e_z, f_x, f_z, d, a, b)
+        round_update(code, e_x, e_z, f_x, f_z, d, a, b)
         gx, gz = fr.block("d")
-        assert np.array_equal(gx, e_x) and np.array_equal(gz, e_z)
-        assert np.array_equal(fr.mem["dx"].T, f_x) and np.array_equal(fr.mem["dz"].T, f_z)
+        if not (np.array_equal(gx, e_x) and np.array_equal(gz, e_z) and
+                np.array_equal(fr.mem["dx"].T, f_x) and np.array_equal(fr.mem["dz"].T, f_z)):
+            return False
     assert f_x.any() and f_z.any() and (e_x ^ f_x).any()
+    return True
+
+
+@pytest.mark.parametrize("name", ["steane", "shor9"])
+@pytest.mark.parametrize("p", [0.02, 0.15])
+def test_round_model_equals_the_reference_gadget(name, p):
+    assert _compare(name, p, oec.round_update)
+
+
+def _mutants():
+    """Wrong models the comparison must reject: each changes ONE thing the gadget fixes."""
+    from oracle import montecarlo as omc
+
+    def make(drop_back_action=False, swap_sides=False, bx_early=False):
+        def update(code, e_x, e_z, f_x, f_z, d, a, b):
+            h2, t2, lz = ocss.pauli_side(code, 1 if swap_sides else 2)
+            h1, t1, lx = ocss.pauli_side(code, 2 if swap_sides else 1)
+            e_x ^= d[0]
+            e_z ^= d[1]
+            if not drop_back_action:
+                e_z ^= a[1]
+            if bx_early:
+                e_x ^= b[0]
+            f_x ^= omc.decode_batch(h2, t2, lz, e_x ^ a[0] ^ f_x)["corr"].astype(np.uint8)
+            if not bx_early:
+                e_x ^= b[0]
+            f_z ^= omc.decode_batch(h1, t1, lx, e_z ^ b[1] ^ f_z)["corr"].astype(np.uint8)
+        return update
+    return {"no_z_back_action": make(drop_back_action=True), "sides_swapped": make(swap_sides=True),
+            "ancilla_b_x_before_the_x_measurement": make(bx_early=True)}
+
+
+@pytest.mark.parametrize("mutant", ["no_z_back_action", "sides_swapped", "ancilla_b_x_before_the_x_measurement"])
+def test_the_comparison_rejects_wrong_models(mutant):
+    """The pin has teeth: a model without the CNOT's Z back-action, with the two sides' matrices exchanged (only a code
+    whose sides differ can tell: Shor-9), or with the |0>_L ancilla's X errors reaching the data before the X measurement
+    does NOT reproduce the reference's gadget."""
+    assert not _compare("shor9", 0.02, _mutants()[mutant])
+    assert _compare("shor9", 0.02, oec.round_update)
 
 
 def test_golden_is_the_gadget_of_css_code_error_correct():

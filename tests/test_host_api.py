@@ -145,7 +145,7 @@ def test_library_reads_no_environment_knobs(monkeypatch):
         monkeypatch.setenv(name, "1")
     lib = _native.load()
     import ctypes
-    for key, default in (("gapq", 1), ("dense", -1), ("named", 1), ("gf2_kernel", 0)):
+    for key, default in (("gapq", 1), ("dense", -1), ("named", 1), ("gf2_kernel", 0), ("host_compact", 1), ("host_threads", 0)):
         val = ctypes.c_int(99)
         assert lib.qcss_get_option(key.encode(), ctypes.byref(val)) == 0 and val.value == default
     with _native.option("gf2_kernel", 2):
@@ -155,6 +155,11 @@ def test_library_reads_no_environment_knobs(monkeypatch):
         _native.set_option("gapq", 7)
     with pytest.raises(ValueError):
         _native.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        _native.set_option("host_threads", 1000)
+    with _native.option("host_compact", 0), _native.option("host_threads", 12):
+        assert lib.qcss_get_option(b"host_threads", ctypes.byref(val)) == 0 and val.value == 12
+    assert lib.qcss_get_option(b"host_compact", ctypes.byref(val)) == 0 and val.value == 1
 
 
 def test_no_cpu_fallback_without_gpu():
